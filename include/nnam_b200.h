@@ -1,0 +1,107 @@
+/* nnam_b200 -- C ABI of the B200-native network-output hot path.
+ *
+ * The reference (OrcusCZ/NNAcousticModeling) has NO FFI/plugin interface: the path sits behind plain
+ * Python call surfaces.  Each entry point below therefore cites the reference Python
+ * symbol whose arithmetic it replaces; the Python host layer (nnacousticmodeling_b200/) binds these
+ * with ctypes and keeps the reference's names (get_nn, MLP, LSTM, predict, ...).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns all buffers, kernels never allocate; `stream` is a cudaStream_t passed as void*;
+ *   - every function returns 0 on success or a negative NNAM_ERR_* code; nnam_last_error() returns a
+ *     thread-local human-readable message for the last failure;
+ *   - re-entrant across streams and devices (one host thread per GPU is the intended use).
+ *   - bf16 matrices are row-major with a leading dimension in ELEMENTS that is a multiple of 8.
+ */
+#ifndef NNAM_B200_H_
+#define NNAM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNAM_ABI_VERSION 1
+
+/* error codes */
+#define NNAM_OK 0
+#define NNAM_ERR_ARG (-1)     /* invalid argument (message says which) */
+#define NNAM_ERR_CUDA (-2)    /* CUDA runtime / driver error */
+#define NNAM_ERR_UNSUPPORTED (-3)
+
+/* activations (chainer_networks.py: F.relu / F.sigmoid / F.tanh chosen in predict_folds.py:144-152) */
+#define NNAM_ACT_NONE 0
+#define NNAM_ACT_RELU 1
+#define NNAM_ACT_SIGMOID 2 /* Chainer formulation tanh(x/2)/2 + 1/2 */
+#define NNAM_ACT_TANH 3
+
+/* output kinds of kernels that can emit GEMM operands */
+#define NNAM_OUT_BF16 0       /* bf16 (hi only) */
+#define NNAM_OUT_BF16_SPLIT 1 /* bf16 hi + bf16 lo, hi + lo ~= fp32 value (16 mantissa bits) */
+#define NNAM_OUT_F32 2        /* fp32 */
+
+/* recurrent cell kinds for nnam_rnn_seq */
+#define NNAM_CELL_LSTM 0     /* L.LSTM / L.StatefulZoneoutLSTM at inference (chainer_networks.py:44-101) */
+#define NNAM_CELL_GRU 1      /* MGRU.py:67-85 family: flags choose reset gate and activation */
+#define NNAM_CELL_PEEPHOLE 2 /* L.StatefulPeepholeLSTM (chainer_networks.py:103-121) */
+
+int nnam_abi_version(void);
+const char* nnam_last_error(void);
+/* Number of SMs of the current device (grid sizing), or a negative error. */
+int nnam_sm_count(void);
+
+/* K1 -- context splice + Kaldi feature transform (+ i-vector append), one pass.
+ * Replaces prepareBatch (scripts/util/kw_nn_utils.py:19-43) == splicing (scripts/util/kw_utils.py:24-36),
+ * applyKaldiFeatureTransform (kw_nn_utils.py:13-17) and the i-vector concatenate (evaluate.py:169-171,
+ * train.py:255-258) in the order splice -> transform -> concat.
+ *
+ *   out[f - f0][w*dim + d] = (x[clamp(f + w - splice, 0, n_total-1)][d] + add_shift[w*dim+d]) * rescale[w*dim+d]
+ *   out[f - f0][winlen*dim + j] = ivec[f][j]
+ *
+ * for f in [f0, f1).  The clamp is at the ends of the WHOLE array (reference quirk Q1), so a shard is
+ * described in global frame coordinates: `x` points at global row `x_row0` and holds rows
+ * [x_row0, x_row0 + x_rows) which must cover [max(f0-splice,0), min(f1+splice, n_total)).  `ivec` (may be
+ * NULL, ivec_dim 0) points at global row f0.  add_shift/rescale may both be NULL (no transform); the
+ * add and the multiply are separately rounded (__fadd_rn/__fmul_rn), so fp32 output is bit-exact.
+ * out_kind F32: out_hi is float[(f1-f0), ldo]; BF16: out_hi bf16; BF16_SPLIT: out_hi + out_lo.  Columns
+ * [winlen*dim + ivec_dim, ldo) are zero-filled.  */
+int nnam_splice_transform(const float* x, long long x_row0, long long x_rows, long long n_total, int dim,
+                          int splice, const float* add_shift, const float* rescale, const float* ivec,
+                          int ivec_dim, long long f0, long long f1, void* out_hi, void* out_lo, long long ldo,
+                          int out_kind, void* stream);
+
+/* fp32 -> bf16 (hi) or bf16 hi/lo split of a row-major matrix, zero-padding columns [cols, ldd).
+ * Used to stage weights (Chainer npz, (out,in) fp32) and already-spliced inputs of model(x).  */
+int nnam_convert_f32(const float* src, long long rows, int cols, long long lds, void* dst_hi, void* dst_lo,
+                     long long ldd, int out_kind, void* stream);
+
+/* K2 -- out = act(A . W^T + bias): every L.Linear of chainer_networks.py (F.linear: x.dot(W.T) + b) and the
+ * batched `upward` / `W_*` projections of the recurrent links.  A [M,K] (lda), W [N,K] (ldw) bf16 K-major.
+ * nsplit 1: bf16; nsplit 3: bf16x3 fp32-accurate mode (needs a_lo, w_lo).  bias may be NULL.
+ * out_kind selects bf16 / bf16 split / fp32 output with leading dimension ldo >= roundup(N,16).  */
+int nnam_linear_bias_act(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
+                         long long ldw, const float* bias, void* out_hi, void* out_lo, long long ldo, int M,
+                         int N, int K, int act, int out_kind, int nsplit, void* stream);
+
+/* K4 -- fused ensemble mean -> RPL4 -> minus log-prior -> log-softmax head.
+ * Replaces `y - logsum(y, axis=1)` (predict_folds.py:57,88; kw_utils.py:38-43), `y = y - ap` +
+ * log-softmax (evaluateModelForTest.py:75-77,110-112), NNWithRPL.__call__ (evaluate.py:35-51), RPL4
+ * (RPL.py:68-74) and the dev-mode fold averaging (predict_folds.py:199-219).
+ *
+ *   h = sum_k weights[k] * (pre_normalize ? log_softmax(logits[k]) : logits[k])
+ *   if rpl_w: x = log_softmax(h); g = x + x*rpl_w + rpl_b; h = logaddexp(g, rpl_lb)
+ *   if prior: h = h - prior_scale * prior
+ *   out = h - logsumexp(h)            (skipped when final_normalize == 0)
+ *
+ * logits: array of n_inputs DEVICE pointers stored in HOST memory (logits_host[k] -> float[rows, ld_in]).
+ * out: float[rows, ld_out] (ld_out == n_classes gives the reference's contiguous (N, C) layout).  */
+int nnam_head(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in,
+              int pre_normalize, const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior,
+              float prior_scale, int final_normalize, float* out, long long ld_out, long long rows,
+              int n_classes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNAM_B200_H_ */

@@ -1,0 +1,10 @@
+"""nnacousticmodeling_b200 -- B200-native network-output hot path of OrcusCZ/NNAcousticModeling.
+
+Feature matrix (+ offsets, i-vectors, Kaldi feature transform) -> per-frame pdf log-likelihoods,
+behind the reference's Python surface (get_nn / model specs / predict / evaluateModelTestTri),
+computed by hand-written sm_100a CUDA kernels in ``libnnam_b200.so`` (C ABI: include/nnam_b200.h).
+There is no CPU fallback.
+"""
+from ._native import NnamError, build  # noqa: F401
+
+__version__ = "0.1.0"

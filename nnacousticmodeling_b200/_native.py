@@ -1,0 +1,112 @@
+"""Build + load the C-ABI shared library (include/nnam_b200.h).
+
+The library is built IN-TREE with nvcc for sm_100a and loaded with ctypes; there is no CPU
+fallback -- if it is missing or fails to load, every op raises ``NnamError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libnnam_b200.so")
+SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class NnamError(RuntimeError):
+    pass
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _sources():
+    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = _sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
+    deps.append(os.path.join(PKG_DIR, "..", "include", "nnam_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA translation unit for sm_100a into ``libnnam_b200.so`` (in-tree)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise NnamError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+_SIGNATURES = {
+    "nnam_abi_version": (c_int, []),
+    "nnam_last_error": (c_char_p, []),
+    "nnam_sm_count": (c_int, []),
+    "nnam_splice_transform": (c_int, [c_void_p, c_longlong, c_longlong, c_longlong, c_int, c_int, c_void_p, c_void_p,
+                                      c_void_p, c_int, c_longlong, c_longlong, c_void_p, c_void_p, c_longlong, c_int,
+                                      c_void_p]),
+    "nnam_convert_f32": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_longlong, c_int,
+                                 c_void_p]),
+    "nnam_linear_bias_act": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
+                                     c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p]),
+    "nnam_head": (c_int, [POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_float, c_int, c_void_p, c_longlong, c_longlong, c_int, c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib():
+    """Return the loaded ctypes library; fail loudly when it is absent (no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NnamError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "nnacousticmodeling_b200 has no CPU or PyTorch fallback.")
+        try:
+            handle = ctypes.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise NnamError(f"cannot load {LIB_PATH}: {e}") from e
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        if handle.nnam_abi_version() != 1:
+            raise NnamError("libnnam_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().nnam_last_error()
+        raise NnamError(f"nnam_b200 error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,294 @@
+// K1 -- context splice + Kaldi feature transform (+ i-vector append), and fp32 -> bf16(/split) staging.
+//
+// Reference semantics (bit-exact in fp32): prepareBatch, scripts/util/kw_nn_utils.py:19-43 (== splicing,
+// scripts/util/kw_utils.py:24-36); applyKaldiFeatureTransform, kw_nn_utils.py:13-17 ((x + addShift) * rescale
+// as two separately rounded fp32 ops); i-vector concatenate AFTER the transform, evaluate.py:169-171.
+//
+// HBM-bound gather.  A block owns TILE_F consecutive frames.  Because the splice window of frame f is the
+// CONTIGUOUS raw span rows [f-S, f+S] (dim floats each), the block stages rows [f0-S, f0+TILE_F+S) in shared
+// memory with coalesced 128-bit loads (clamped at the ends of the whole array), and output element (f, c) is
+// simply smem[(f - f0) * dim + c]: every output row is produced with 128-bit shared loads and coalesced
+// 128-bit global stores.  Algorithmic traffic: read dim*4 (+ivec) and write (winlen*dim + ivec)*elem bytes
+// per frame.
+#include "ptx.cuh"
+#include "nnam_internal.h"
+
+namespace nnam {
+
+constexpr int SPLICE_TILE_F = 64;
+constexpr int SPLICE_THREADS = 256;
+
+struct SpliceParams {
+  const float* x;
+  long long x_row0, n_total;
+  int dim, splice, winlen;
+  const float* add_shift;
+  const float* rescale;
+  const float* ivec;
+  int ivec_dim;
+  long long f0, f1;
+  void* out_hi;
+  void* out_lo;
+  long long ldo;
+  int spl_cols;  // winlen * dim
+};
+
+// value of output column c for tile-local frame r (raw rows staged at s_x, transform at s_add / s_mul)
+__device__ __forceinline__ float splice_elem(const SpliceParams& p, const float* s_x, const float* s_add,
+                                             const float* s_mul, int r, long long f, int c) {
+  if (c < p.spl_cols) {
+    float v = s_x[r * p.dim + c];
+    if (s_add != nullptr) v = __fmul_rn(__fadd_rn(v, s_add[c]), s_mul[c]);
+    return v;
+  }
+  c -= p.spl_cols;
+  if (c < p.ivec_dim) return __ldg(p.ivec + (f - p.f0) * p.ivec_dim + c);
+  return 0.0f;
+}
+
+template <int OUT_KIND, bool VEC>
+__global__ void __launch_bounds__(SPLICE_THREADS) splice_transform_kernel(const SpliceParams p) {
+  extern __shared__ __align__(16) float s_mem[];
+  const int halo_rows = SPLICE_TILE_F + 2 * p.splice;
+  float* s_x = s_mem;                        // halo_rows * dim
+  float* s_add = s_x + halo_rows * p.dim;    // spl_cols (only when a transform is given)
+  float* s_mul = s_add + p.spl_cols;
+  const bool has_ft = p.add_shift != nullptr;
+  const long long tile_f0 = p.f0 + static_cast<long long>(blockIdx.x) * SPLICE_TILE_F;
+  const int tile_n = static_cast<int>(min(static_cast<long long>(SPLICE_TILE_F), p.f1 - tile_f0));
+  const int need_rows = tile_n + 2 * p.splice;
+
+  // ---- stage raw rows (clamped to the whole array) and the transform vectors
+  if (VEC) {
+    const int vpr = p.dim >> 2;
+    for (int i = threadIdx.x; i < need_rows * vpr; i += SPLICE_THREADS) {
+      const int row = i / vpr, v = i - row * vpr;
+      long long g = tile_f0 - p.splice + row;
+      g = g < 0 ? 0 : (g >= p.n_total ? p.n_total - 1 : g);
+      const float4 val = __ldg(reinterpret_cast<const float4*>(p.x + (g - p.x_row0) * p.dim) + v);
+      reinterpret_cast<float4*>(s_x)[i] = val;
+    }
+  } else {
+    for (int i = threadIdx.x; i < need_rows * p.dim; i += SPLICE_THREADS) {
+      const int row = i / p.dim, d = i - row * p.dim;
+      long long g = tile_f0 - p.splice + row;
+      g = g < 0 ? 0 : (g >= p.n_total ? p.n_total - 1 : g);
+      s_x[i] = __ldg(p.x + (g - p.x_row0) * p.dim + d);
+    }
+  }
+  if (has_ft) {
+    for (int i = threadIdx.x; i < p.spl_cols; i += SPLICE_THREADS) {
+      s_add[i] = __ldg(p.add_shift + i);
+      s_mul[i] = __ldg(p.rescale + i);
+    }
+  }
+  __syncthreads();
+  const float* t_add = has_ft ? s_add : nullptr;
+
+  // ---- emit
+  if (OUT_KIND == NNAM_OUT_F32) {
+    float* out = static_cast<float*>(p.out_hi) + (tile_f0 - p.f0) * p.ldo;
+    if (VEC) {
+      const int vpr = static_cast<int>(p.ldo >> 2);
+      for (int i = threadIdx.x; i < tile_n * vpr; i += SPLICE_THREADS) {
+        const int r = i / vpr, c = (i - r * vpr) << 2;
+        float4 o;
+        if (c + 4 <= p.spl_cols) {
+          const float4 v = *reinterpret_cast<const float4*>(s_x + r * p.dim + c);
+          if (has_ft) {
+            const float4 a = *reinterpret_cast<const float4*>(s_add + c);
+            const float4 m = *reinterpret_cast<const float4*>(s_mul + c);
+            o.x = __fmul_rn(__fadd_rn(v.x, a.x), m.x);
+            o.y = __fmul_rn(__fadd_rn(v.y, a.y), m.y);
+            o.z = __fmul_rn(__fadd_rn(v.z, a.z), m.z);
+            o.w = __fmul_rn(__fadd_rn(v.w, a.w), m.w);
+          } else {
+            o = v;
+          }
+        } else if (c >= p.spl_cols && c + 4 <= p.spl_cols + p.ivec_dim) {
+          o = __ldg(reinterpret_cast<const float4*>(p.ivec + (tile_f0 + r - p.f0) * p.ivec_dim + (c - p.spl_cols)));
+        } else {
+          o.x = splice_elem(p, s_x, t_add, s_mul, r, tile_f0 + r, c);
+          o.y = splice_elem(p, s_x, t_add, s_mul, r, tile_f0 + r, c + 1);
+          o.z = splice_elem(p, s_x, t_add, s_mul, r, tile_f0 + r, c + 2);
+          o.w = splice_elem(p, s_x, t_add, s_mul, r, tile_f0 + r, c + 3);
+        }
+        reinterpret_cast<float4*>(out + static_cast<long long>(r) * p.ldo)[c >> 2] = o;
+      }
+    } else {
+      const int ld = static_cast<int>(p.ldo);
+      for (int i = threadIdx.x; i < tile_n * ld; i += SPLICE_THREADS) {
+        const int r = i / ld, c = i - r * ld;
+        out[static_cast<long long>(r) * p.ldo + c] = splice_elem(p, s_x, t_add, s_mul, r, tile_f0 + r, c);
+      }
+    }
+  } else {
+    // bf16 (hi) or bf16 hi/lo split: 8 elements (16 B) per thread per store; ldo % 8 == 0 is required.
+    __nv_bfloat16* out_hi = static_cast<__nv_bfloat16*>(p.out_hi) + (tile_f0 - p.f0) * p.ldo;
+    __nv_bfloat16* out_lo =
+        OUT_KIND == NNAM_OUT_BF16_SPLIT ? static_cast<__nv_bfloat16*>(p.out_lo) + (tile_f0 - p.f0) * p.ldo : nullptr;
+    const int vpr = static_cast<int>(p.ldo >> 3);
+    for (int i = threadIdx.x; i < tile_n * vpr; i += SPLICE_THREADS) {
+      const int r = i / vpr, c = (i - r * vpr) << 3;
+      float v[8];
+      if (VEC && c + 8 <= p.spl_cols) {
+        const float4 v0 = *reinterpret_cast<const float4*>(s_x + r * p.dim + c);
+        const float4 v1 = *reinterpret_cast<const float4*>(s_x + r * p.dim + c + 4);
+        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
+        v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+        if (has_ft) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __fmul_rn(__fadd_rn(v[j], s_add[c + j]), s_mul[c + j]);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = splice_elem(p, s_x, t_add, s_mul, r, tile_f0 + r, c + j);
+      }
+      uint32_t h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      reinterpret_cast<uint4*>(out_hi + static_cast<long long>(r) * p.ldo)[c >> 3] = make_uint4(h[0], h[1], h[2], h[3]);
+      if (OUT_KIND == NNAM_OUT_BF16_SPLIT) {
+        uint32_t l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          l[j] = pack_bf16x2(v[2 * j] - bf16_round(v[2 * j]), v[2 * j + 1] - bf16_round(v[2 * j + 1]));
+        reinterpret_cast<uint4*>(out_lo + static_cast<long long>(r) * p.ldo)[c >> 3] =
+            make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+}
+
+template <int OUT_KIND>
+static int launch_splice(const SpliceParams& p, bool vec, cudaStream_t stream) {
+  const long long frames = p.f1 - p.f0;
+  const long long blocks = (frames + SPLICE_TILE_F - 1) / SPLICE_TILE_F;
+  if (blocks > 0x7fffffffLL) return set_error(NNAM_ERR_ARG, "splice: too many frames for one launch");
+  const size_t smem = (static_cast<size_t>(SPLICE_TILE_F + 2 * p.splice) * p.dim + 2 * static_cast<size_t>(p.spl_cols)) *
+                      sizeof(float);
+  if (smem > 200 * 1024) return set_error(NNAM_ERR_UNSUPPORTED, "splice: window too large for shared memory");
+  if (smem > 48 * 1024) {
+    cudaError_t e;
+    if (vec)
+      e = cudaFuncSetAttribute(splice_transform_kernel<OUT_KIND, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
+    else
+      e = cudaFuncSetAttribute(splice_transform_kernel<OUT_KIND, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
+    if (e != cudaSuccess) return set_cuda_error(e, "splice: cudaFuncSetAttribute");
+  }
+  if (vec)
+    splice_transform_kernel<OUT_KIND, true><<<static_cast<unsigned>(blocks), SPLICE_THREADS, smem, stream>>>(p);
+  else
+    splice_transform_kernel<OUT_KIND, false><<<static_cast<unsigned>(blocks), SPLICE_THREADS, smem, stream>>>(p);
+  return check_launch("splice_transform_kernel");
+}
+
+int splice_transform(const float* x, long long x_row0, long long x_rows, long long n_total, int dim, int splice,
+                     const float* add_shift, const float* rescale, const float* ivec, int ivec_dim, long long f0,
+                     long long f1, void* out_hi, void* out_lo, long long ldo, int out_kind, cudaStream_t stream) {
+  if (f1 < f0 || f0 < 0 || f1 > n_total) return set_error(NNAM_ERR_ARG, "splice: bad frame range [%lld,%lld)", f0, f1);
+  if (f1 == f0) return NNAM_OK;  // empty input: nothing to do
+  if (dim <= 0 || splice < 0 || ivec_dim < 0) return set_error(NNAM_ERR_ARG, "splice: bad dims");
+  if ((add_shift == nullptr) != (rescale == nullptr))
+    return set_error(NNAM_ERR_ARG, "splice: add_shift and rescale must be given together");
+  if (ivec_dim > 0 && ivec == nullptr) return set_error(NNAM_ERR_ARG, "splice: ivec_dim > 0 but ivec is NULL");
+  const long long lo = f0 - splice < 0 ? 0 : f0 - splice;
+  const long long hi = f1 + splice > n_total ? n_total : f1 + splice;
+  if (x_row0 > lo || x_row0 + x_rows < hi)
+    return set_error(NNAM_ERR_ARG, "splice: x rows [%lld,%lld) do not cover the halo [%lld,%lld)", x_row0,
+                     x_row0 + x_rows, lo, hi);
+  SpliceParams p;
+  p.x = x;
+  p.x_row0 = x_row0;
+  p.n_total = n_total;
+  p.dim = dim;
+  p.splice = splice;
+  p.winlen = 2 * splice + 1;
+  p.add_shift = add_shift;
+  p.rescale = rescale;
+  p.ivec = ivec;
+  p.ivec_dim = ivec_dim;
+  p.f0 = f0;
+  p.f1 = f1;
+  p.out_hi = out_hi;
+  p.out_lo = out_lo;
+  p.ldo = ldo;
+  p.spl_cols = p.winlen * dim;
+  const int cols = p.spl_cols + ivec_dim;
+  if (ldo < cols) return set_error(NNAM_ERR_ARG, "splice: ldo %lld < %d output columns", ldo, cols);
+  const bool aligned_in = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                          (ivec_dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(ivec) & 15) == 0);
+  switch (out_kind) {
+    case NNAM_OUT_F32: {
+      const bool vec = aligned_in && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out_hi) & 15) == 0);
+      return launch_splice<NNAM_OUT_F32>(p, vec, stream);
+    }
+    case NNAM_OUT_BF16:
+    case NNAM_OUT_BF16_SPLIT: {
+      if (ldo % 8 || (reinterpret_cast<uintptr_t>(out_hi) & 15))
+        return set_error(NNAM_ERR_ARG, "splice: bf16 output needs ldo %% 8 == 0 and a 16-byte aligned buffer");
+      if (out_kind == NNAM_OUT_BF16_SPLIT) {
+        if (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 15))
+          return set_error(NNAM_ERR_ARG, "splice: split output needs an aligned out_lo");
+        return launch_splice<NNAM_OUT_BF16_SPLIT>(p, aligned_in, stream);
+      }
+      return launch_splice<NNAM_OUT_BF16>(p, aligned_in, stream);
+    }
+    default:
+      return set_error(NNAM_ERR_ARG, "splice: unknown out_kind %d", out_kind);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 -> bf16 / bf16 split staging of weights and pre-spliced inputs (8 elements per thread).
+template <bool SPLIT>
+__global__ void convert_f32_kernel(const float* __restrict__ src, long long rows, int cols, long long lds,
+                                   __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldd) {
+  const long long vpr = ldd >> 3;
+  const long long total = rows * vpr;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vpr;
+    const int c = static_cast<int>(i - r * vpr) << 3;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (c + j < cols) ? __ldg(src + r * lds + c + j) : 0.0f;
+    uint32_t h[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    reinterpret_cast<uint4*>(hi + r * ldd)[c >> 3] = make_uint4(h[0], h[1], h[2], h[3]);
+    if (SPLIT) {
+      uint32_t l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        l[j] = pack_bf16x2(v[2 * j] - bf16_round(v[2 * j]), v[2 * j + 1] - bf16_round(v[2 * j + 1]));
+      reinterpret_cast<uint4*>(lo + r * ldd)[c >> 3] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+int convert_f32(const float* src, long long rows, int cols, long long lds, void* dst_hi, void* dst_lo, long long ldd,
+                int out_kind, cudaStream_t stream) {
+  if (rows < 0 || cols <= 0 || lds < cols || ldd < cols) return set_error(NNAM_ERR_ARG, "convert: bad shape");
+  if (rows == 0) return NNAM_OK;
+  if (ldd % 8 || (reinterpret_cast<uintptr_t>(dst_hi) & 15)) return set_error(NNAM_ERR_ARG, "convert: ldd %% 8 / alignment");
+  const long long total = rows * (ldd >> 3);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (out_kind == NNAM_OUT_BF16_SPLIT) {
+    if (!dst_lo || (reinterpret_cast<uintptr_t>(dst_lo) & 15)) return set_error(NNAM_ERR_ARG, "convert: dst_lo");
+    convert_f32_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        src, rows, cols, lds, static_cast<__nv_bfloat16*>(dst_hi), static_cast<__nv_bfloat16*>(dst_lo), ldd);
+  } else if (out_kind == NNAM_OUT_BF16) {
+    convert_f32_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        src, rows, cols, lds, static_cast<__nv_bfloat16*>(dst_hi), nullptr, ldd);
+  } else {
+    return set_error(NNAM_ERR_ARG, "convert: out_kind must be BF16 or BF16_SPLIT");
+  }
+  return check_launch("convert_f32_kernel");
+}
+
+}  // namespace nnam

@@ -1,0 +1,135 @@
+"""torch-tensor front ends of the C-ABI ops.  PyTorch is plumbing only: it owns device memory and
+streams; all arithmetic happens in libnnam_b200.so."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _native
+from ._native import NnamError, check
+
+ACT = {"identity": 0, "none": 0, None: 0, "relu": 1, "sigmoid": 2, "tanh": 3}
+OUT_BF16, OUT_BF16_SPLIT, OUT_F32 = 0, 1, 2
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise NnamError(f"{name}: expected a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise NnamError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if t.dim() == 2 and t.stride(1) != 1:
+        raise NnamError(f"{name}: rows must be contiguous")
+
+
+def round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def splice_transform(x, n_total, splice, add_shift=None, rescale=None, ivec=None, f0=0, f1=None, x_row0=0,
+                     out_kind=OUT_F32, ldo=None, out=None):
+    """K1.  x: (rows, dim) f32 holding global rows [x_row0, x_row0+rows); returns (out_hi, out_lo)."""
+    _req(x, torch.float32, "x")
+    _req(ivec, torch.float32, "ivec")
+    _req(add_shift, torch.float32, "add_shift")
+    _req(rescale, torch.float32, "rescale")
+    if not x.is_contiguous() or (ivec is not None and not ivec.is_contiguous()):
+        raise NnamError("splice: x and ivec must be contiguous")
+    rows, dim = x.shape
+    if f1 is None:
+        f1 = n_total
+    ivec_dim = 0 if ivec is None else ivec.shape[1]
+    cols = (2 * splice + 1) * dim + ivec_dim
+    if add_shift is not None and add_shift.numel() != (2 * splice + 1) * dim:
+        raise NnamError(f"splice: transform has {add_shift.numel()} entries, expected {(2 * splice + 1) * dim}")
+    if ivec is not None and ivec.shape[0] < f1 - f0:
+        raise NnamError("splice: ivec has fewer rows than the frame range")
+    if ldo is None:
+        ldo = cols if out_kind == OUT_F32 else round_up(cols, 8)
+    n = f1 - f0
+    dt = torch.float32 if out_kind == OUT_F32 else torch.bfloat16
+    if out is None:
+        hi = torch.empty((n, ldo), dtype=dt, device=x.device)
+        lo = torch.empty((n, ldo), dtype=dt, device=x.device) if out_kind == OUT_BF16_SPLIT else None
+    else:
+        hi, lo = out
+    check(_native.lib().nnam_splice_transform(_ptr(x), x_row0, rows, n_total, dim, splice, _ptr(add_shift),
+                                              _ptr(rescale), _ptr(ivec), ivec_dim, f0, f1, _ptr(hi), _ptr(lo), ldo,
+                                              out_kind, _stream()))
+    return hi, lo
+
+
+def convert_f32(src, out_kind=OUT_BF16, ldd=None, out=None):
+    """fp32 (rows, cols) -> bf16 hi (and lo) with zero padding up to ldd columns."""
+    _req(src, torch.float32, "src")
+    rows, cols = src.shape
+    if ldd is None:
+        ldd = round_up(cols, 8)
+    if out is None:
+        hi = torch.empty((rows, ldd), dtype=torch.bfloat16, device=src.device)
+        lo = torch.empty((rows, ldd), dtype=torch.bfloat16, device=src.device) if out_kind == OUT_BF16_SPLIT else None
+    else:
+        hi, lo = out
+    check(_native.lib().nnam_convert_f32(_ptr(src), rows, cols, src.stride(0), _ptr(hi), _ptr(lo), ldd, out_kind,
+                                         _stream()))
+    return hi, lo
+
+
+def linear_bias_act(a_hi, a_lo, w_hi, w_lo, bias, M, N, K, act="identity", out_kind=OUT_BF16, nsplit=1, out=None,
+                    ldo=None):
+    """K2.  out = act(A . W^T + bias).  a_*: (>=M, lda) bf16, w_*: (>=N, ldw) bf16 (K-major)."""
+    for t, n in ((a_hi, "a_hi"), (a_lo, "a_lo"), (w_hi, "w_hi"), (w_lo, "w_lo")):
+        _req(t, torch.bfloat16, n)
+    _req(bias, torch.float32, "bias")
+    if ldo is None:
+        ldo = round_up(N, 16)
+    dt = torch.float32 if out_kind == OUT_F32 else torch.bfloat16
+    if out is None:
+        hi = torch.empty((M, ldo), dtype=dt, device=a_hi.device)
+        lo = torch.empty((M, ldo), dtype=dt, device=a_hi.device) if out_kind == OUT_BF16_SPLIT else None
+    else:
+        hi, lo = out
+    check(_native.lib().nnam_linear_bias_act(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(w_hi), _ptr(w_lo),
+                                             w_hi.stride(0), _ptr(bias), _ptr(hi), _ptr(lo), ldo, M, N, K,
+                                             ACT[act], out_kind, nsplit, _stream()))
+    return hi, lo
+
+
+def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=None, prior=None, prior_scale=1.0,
+         final_normalize=True, out=None):
+    """K4.  logits: one (rows, ld) f32 tensor or a list of them (ensemble)."""
+    if isinstance(logits, torch.Tensor):
+        logits = [logits]
+    for t in logits:
+        _req(t, torch.float32, "logits")
+    ld_in = logits[0].stride(0)
+    if any(t.stride(0) != ld_in for t in logits):
+        raise NnamError("head: all inputs must share one leading dimension")
+    if rows is None:
+        rows = logits[0].shape[0]
+    if out is None:
+        out = torch.empty((rows, n_classes), dtype=torch.float32, device=logits[0].device)
+    _req(out, torch.float32, "out")
+    k = len(logits)
+    ptrs = (ctypes.c_void_p * k)(*[t.data_ptr() for t in logits])
+    wts = None if weights is None else (ctypes.c_float * k)(*[float(w) for w in weights])
+    rw = rb = rlb = None
+    if rpl is not None:
+        rw, rb, rlb = rpl
+        for t in (rw, rb, rlb):
+            _req(t, torch.float32, "rpl")
+    _req(prior, torch.float32, "prior")
+    check(_native.lib().nnam_head(ptrs, wts, k, ld_in, int(bool(pre_normalize)), _ptr(rw), _ptr(rb), _ptr(rlb),
+                                  _ptr(prior), float(prior_scale), int(bool(final_normalize)), _ptr(out),
+                                  out.stride(0), rows, n_classes, _stream()))
+    return out
