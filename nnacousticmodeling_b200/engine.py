@@ -1,0 +1,318 @@
+"""Device-side planning for the hot path: weight packing, workspaces, the chunked
+splice -> GEMM stack -> head pipeline with overlapped D2H, and utterance sharding.
+
+HBM layout (per device)
+  raw features      fp32 (rows, dim)            uploaded once per shard, with a +-splice halo
+  layer inputs      bf16 (chunk, ld)  [+ lo]    ld = roundup(K, 8); hi/lo pair in 'fp32' (bf16x3) mode
+  weights           bf16 (N, roundup(K, 8)) [+ lo], bias fp32 (N)   Chainer (out, in) layout, K-major
+  logits            fp32 (chunk, roundup(C, 16))
+  log-likelihoods   fp32 (chunk, C)  double-buffered, copied to the (pinned) host array on a side stream
+"""
+from __future__ import annotations
+
+import threading
+
+import numpy as np
+import torch
+
+from . import ops
+from ._native import NnamError
+from .ops import OUT_BF16, OUT_BF16_SPLIT, OUT_F32, round_up
+
+DEFAULT_CHUNK = 65536
+
+
+def _device(dev):
+    if isinstance(dev, torch.device):
+        return dev
+    if dev is None:
+        dev = 0
+    if int(dev) < 0:
+        raise NnamError("gpu < 0 (CPU) is not supported: nnacousticmodeling_b200 has no CPU path")
+    return torch.device("cuda", int(dev))
+
+
+def empty_pinned(shape, dtype=np.float32):
+    """Page-locked host array (NumPy view of a pinned torch tensor) for H2D/D2H at PCIe speed."""
+    tdt = {np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32}[np.dtype(dtype)]
+    return torch.empty(tuple(shape), dtype=tdt, pin_memory=True).numpy()
+
+
+def _as_host_tensor(a):
+    """NumPy array -> torch CPU tensor sharing memory (pinned-ness is preserved)."""
+    if isinstance(a, torch.Tensor):
+        return a
+    return torch.from_numpy(a)
+
+
+# ------------------------------------------------------------------------------------------
+# packed parameters
+# ------------------------------------------------------------------------------------------
+class LinearDev:
+    """One Linear layer on a device: bf16 (hi[, lo]) K-major weights + fp32 bias."""
+
+    def __init__(self, w, b, device, split):
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        self.n, self.k = w.shape
+        kind = OUT_BF16_SPLIT if split else OUT_BF16
+        wd = torch.from_numpy(w).to(device)
+        self.w_hi, self.w_lo = ops.convert_f32(wd, kind)
+        self.bias = None if b is None else torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(device)
+        self.split = split
+
+    def __call__(self, a_hi, a_lo, rows, act, out_kind, out=None):
+        return ops.linear_bias_act(a_hi, a_lo, self.w_hi, self.w_lo, self.bias, rows, self.n, self.k, act=act,
+                                   out_kind=out_kind, nsplit=3 if self.split else 1, out=out)
+
+
+class Workspace:
+    """Grow-only named device buffers (the kernels never allocate)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.buf = {}
+
+    def get(self, name, rows, cols, dtype):
+        t = self.buf.get(name)
+        need = rows * cols
+        if t is None or t.numel() < need or t.dtype != dtype:
+            t = torch.empty(need, dtype=dtype, device=self.device)
+            self.buf[name] = t
+        return t[:need].view(rows, cols)
+
+
+class Plan:
+    """Per (model, device, precision) packed parameters."""
+
+    def __init__(self, model, device):
+        self.device = device
+        self.split = model.precision == "fp32"
+        self.act_kind = OUT_BF16_SPLIT if self.split else OUT_BF16
+        self.ws = Workspace(device)
+        p = model.params
+        with torch.cuda.device(device):
+            if model.network == "ff":
+                self.layers = [LinearDev(p[f"layer_{l}/W"], p[f"layer_{l}/b"], device, self.split)
+                               for l in range(model.layers)]
+                self.out = LinearDev(p["out/W"], p["out/b"], device, self.split)
+            else:
+                from . import recurrent_engine
+                recurrent_engine.build_plan(self, model)
+            torch.cuda.current_stream().synchronize()
+
+
+def get_plan(model, device):
+    device = _device(device)
+    key = (device.index, model.precision, model._version)
+    plan = model._plans.get(key)
+    if plan is None:
+        if not model.params:
+            raise NnamError(f"{type(model).__name__} has no parameters: load_npz() or init_params() first")
+        plan = Plan(model, device)
+        model._plans = {k: v for k, v in model._plans.items() if k[2] == model._version}
+        model._plans[key] = plan
+    return plan
+
+
+# ------------------------------------------------------------------------------------------
+# MLP stack on already-staged bf16 inputs
+# ------------------------------------------------------------------------------------------
+def mlp_logits(model, plan, a_hi, a_lo, rows, tag="mlp"):
+    """Run the Linear stack; returns fp32 logits (rows, roundup(C, 16)) in workspace memory."""
+    ws = plan.ws
+    act = model.activation.name
+    cap = a_hi.shape[0]
+    for l, lin in enumerate(plan.layers):
+        ld = round_up(lin.n, 16)
+        hi = ws.get(f"{tag}.h{l % 2}.hi", cap, ld, torch.bfloat16)
+        lo = ws.get(f"{tag}.h{l % 2}.lo", cap, ld, torch.bfloat16) if plan.split else None
+        lin(a_hi, a_lo, rows, act, plan.act_kind, out=(hi, lo))
+        a_hi, a_lo = hi, lo
+    ldc = round_up(plan.out.n, 16)
+    logits = ws.get(f"{tag}.logits", cap, ldc, torch.float32)
+    plan.out(a_hi, a_lo, rows, "identity", OUT_F32, out=(logits, None))
+    return logits
+
+
+def call_model(model, x):
+    """``model(x)``: (B, D_in) float32 -> (B, C) raw logits.  NumPy in -> NumPy out; CUDA tensor in ->
+    CUDA tensor out (mirrors Chainer's xp-array behaviour).  Recurrent models are stateful per call."""
+    is_np = not isinstance(x, torch.Tensor)
+    if hasattr(x, "data") and not isinstance(x, (np.ndarray, torch.Tensor)):  # chainer.Variable-like
+        x = x.data
+    if is_np:
+        xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+        device = _device(model._device)
+    else:
+        xt = x
+        device = x.device if x.is_cuda else _device(model._device)
+    plan = get_plan(model, device)
+    with torch.cuda.device(device):
+        xd = xt.to(device, dtype=torch.float32)
+        if xd.dim() != 2 or xd.shape[1] != model.in_size:
+            raise NnamError(f"model(x): expected (B, {model.in_size}) input, got {tuple(xd.shape)}")
+        if model.recurrent:
+            from . import recurrent_engine
+            logits = recurrent_engine.step(model, plan, xd)
+        else:
+            rows = xd.shape[0]
+            a_hi, a_lo = ops.convert_f32(xd.contiguous(), plan.act_kind)
+            if model.network == "tdnn":
+                from . import tdnn_engine
+                logits = tdnn_engine.logits(model, plan, a_hi, a_lo, rows)
+            else:
+                logits = mlp_logits(model, plan, a_hi, a_lo, rows, tag="call")
+            logits = logits[:rows, :model.n_out].clone()
+        if is_np:
+            return logits.cpu().numpy()
+        return logits
+
+
+# ------------------------------------------------------------------------------------------
+# sharding: contiguous ranges, no collective
+# ------------------------------------------------------------------------------------------
+def partition_frames(n_frames, parts):
+    """Equal contiguous frame ranges for feed-forward nets (per-frame independent given the halo)."""
+    cuts = [(n_frames * i) // parts for i in range(parts + 1)]
+    return [(cuts[i], cuts[i + 1]) for i in range(parts)]
+
+
+def partition_utterances(offsets, parts):
+    """Contiguous utterance ranges with ~equal frame counts (prefix-sum cut points on ``offsets``)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n_utt = len(offsets) - 1
+    total = int(offsets[-1])
+    cuts = [0]
+    for i in range(1, parts):
+        target = total * i / parts
+        u = int(np.searchsorted(offsets, target, side="left"))
+        if u > 0 and abs(offsets[u - 1] - target) <= abs(offsets[min(u, n_utt)] - target):
+            u -= 1
+        cuts.append(min(max(u, cuts[-1]), n_utt))
+    cuts.append(n_utt)
+    return [(cuts[i], cuts[i + 1]) for i in range(parts)]
+
+
+# ------------------------------------------------------------------------------------------
+# feed-forward frame pipeline: splice -> GEMMs -> head -> D2H
+# ------------------------------------------------------------------------------------------
+class HeadSpec:
+    """What the head applies after the logits (K4 arguments)."""
+
+    def __init__(self, prior=None, prior_scale=1.0, rpl=None, weights=None, pre_normalize=False,
+                 final_normalize=True):
+        self.prior, self.prior_scale, self.rpl = prior, prior_scale, rpl
+        self.weights, self.pre_normalize, self.final_normalize = weights, pre_normalize, final_normalize
+
+
+def _dev_vec(a, device):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32).reshape(-1)).to(device)
+
+
+def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, device=0, head=None,
+                      chunk=DEFAULT_CHUNK, presliced=False):
+    """Feed-forward hot loop on ONE device for frames [f0, f1) of the whole array ``x``.
+
+    models    : one MLP or a list (ensemble -> logits combined in the head with head.weights)
+    x         : (N, dim) float32 raw features, host array or CUDA tensor (already resident) -- or, with
+                presliced=True, the already spliced/transformed (N, D_in) matrix (evaluate.py hands such
+                data to the model)
+    ivectors  : optional (N, I) host array or CUDA tensor, appended after splice + transform
+    out       : (N, C) float32; rows [f0, f1) are written.  Host array (pinned => async D2H overlapped
+                with the next chunk on a side stream) or CUDA tensor (results stay in HBM).
+    """
+    if not isinstance(models, (list, tuple)):
+        models = [models]
+    device = _device(device)
+    head = head or HeadSpec()
+    n_total = x.shape[0]
+    f1 = n_total if f1 is None else f1
+    if f1 <= f0:
+        return out
+    n_out = models[0].n_out
+    halo = 0 if presliced else splice
+    lo, hi = max(f0 - halo, 0), min(f1 + halo, n_total)
+    with torch.cuda.device(device):
+        plans = [get_plan(m, device) for m in models]
+        plan0 = plans[0]
+        ws = plan0.ws
+        main = torch.cuda.current_stream()
+        side = plan0.__dict__.setdefault("_side_stream", torch.cuda.Stream(device=device))
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            x_dev, lo = x, 0
+        else:
+            x_dev = ws.get("ff.x", hi - lo, x.shape[1], torch.float32)
+            x_dev.copy_(_as_host_tensor(x)[lo:hi], non_blocking=True)
+        iv_dev, iv0 = None, f0
+        if ivectors is not None:
+            if isinstance(ivectors, torch.Tensor) and ivectors.is_cuda:
+                iv_dev, iv0 = ivectors, 0
+            else:
+                iv_dev = ws.get("ff.iv", f1 - f0, ivectors.shape[1], torch.float32)
+                iv_dev.copy_(_as_host_tensor(ivectors)[f0:f1], non_blocking=True)
+        add = mul = None
+        if ft is not None and not presliced:
+            add, mul = _dev_vec(ft["addShift"], device), _dev_vec(ft["rescale"], device)
+        prior = _dev_vec(head.prior, device)
+        rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
+        out_on_device = isinstance(out, torch.Tensor) and out.is_cuda
+        out_h = None if out_on_device else _as_host_tensor(out)
+        chunk = min(chunk, f1 - f0)
+        d_in = models[0].in_size
+        ld_in = round_up(d_in, 8)
+        a_hi = ws.get("ff.a.hi", chunk, ld_in, torch.bfloat16)
+        a_lo = ws.get("ff.a.lo", chunk, ld_in, torch.bfloat16) if plan0.split else None
+        out_dev = None if out_on_device else [ws.get(f"ff.out{i}", chunk, n_out, torch.float32) for i in range(2)]
+        copied = [None, None]
+        for ci, c0 in enumerate(range(f0, f1, chunk)):
+            c1 = min(c0 + chunk, f1)
+            rows = c1 - c0
+            if presliced:
+                ops.convert_f32(x_dev[c0 - lo:c1 - lo], plan0.act_kind, ldd=ld_in, out=(a_hi, a_lo))
+            else:
+                ops.splice_transform(x_dev, n_total, splice, add, mul,
+                                     None if iv_dev is None else iv_dev[c0 - iv0:c1 - iv0], f0=c0, f1=c1, x_row0=lo,
+                                     out_kind=plan0.act_kind, ldo=ld_in, out=(a_hi, a_lo))
+            logits = [mlp_logits(m, p, a_hi, a_lo, rows, tag=f"ff{k}") for k, (m, p) in enumerate(zip(models, plans))]
+            hkw = dict(rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
+                       prior_scale=head.prior_scale, final_normalize=head.final_normalize)
+            if out_on_device:
+                ops.head(logits, n_out, out=out[c0:c1], **hkw)
+                continue
+            buf = ci % 2
+            if copied[buf] is not None:
+                main.wait_event(copied[buf])  # the side stream still reads this buffer
+            ops.head(logits, n_out, out=out_dev[buf], **hkw)
+            done = torch.cuda.Event()
+            done.record(main)
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                out_h[c0:c1].copy_(out_dev[buf][:rows], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            copied[buf] = ev
+        side.synchronize()
+        main.synchronize()
+    return out
+
+
+def run_sharded(fn, shards, devices):
+    """Run ``fn(shard, device)`` for every (shard, device) pair, one host thread per device."""
+    if len(devices) == 1:
+        return [fn(shards[0], devices[0])]
+    res, errs = [None] * len(devices), []
+
+    def work(i):
+        try:
+            res[i] = fn(shards[i], devices[i])
+        except BaseException as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(devices))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise errs[0]
+    return res

@@ -13,6 +13,30 @@ ACT = {"identity": 0, "none": 0, None: 0, "relu": 1, "sigmoid": 2, "tanh": 3}
 OUT_BF16, OUT_BF16_SPLIT, OUT_F32 = 0, 1, 2
 
 
+# launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing for the roofline block)
+LAUNCHES = {"splice": 0, "convert": 0, "gemm": 0, "head": 0, "rnn": 0}
+PROFILE = None  # set to a list to record (kernel, start_event, end_event, work) per launch
+
+
+class _Prof:
+    def __init__(self, name, work):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        LAUNCHES[self.name] += 1
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e.record()
+            PROFILE.append((self.name, self.s, self.e, self.work))
+        return False
+
+
 def _ptr(t):
     return 0 if t is None else t.data_ptr()
 
@@ -63,9 +87,11 @@ def splice_transform(x, n_total, splice, add_shift=None, rescale=None, ivec=None
         lo = torch.empty((n, ldo), dtype=dt, device=x.device) if out_kind == OUT_BF16_SPLIT else None
     else:
         hi, lo = out
-    check(_native.lib().nnam_splice_transform(_ptr(x), x_row0, rows, n_total, dim, splice, _ptr(add_shift),
-                                              _ptr(rescale), _ptr(ivec), ivec_dim, f0, f1, _ptr(hi), _ptr(lo), ldo,
-                                              out_kind, _stream()))
+    work = n * (dim * 4 + ivec_dim * 4 + cols * (4 if out_kind == OUT_F32 else (2 if out_kind == OUT_BF16 else 4)))
+    with _Prof("splice", work):
+        check(_native.lib().nnam_splice_transform(_ptr(x), x_row0, rows, n_total, dim, splice, _ptr(add_shift),
+                                              _ptr(rescale), _ptr(ivec), ivec_dim, f0, f1, _ptr(hi), _ptr(lo),
+                                                  ldo, out_kind, _stream()))
     return hi, lo
 
 
@@ -80,8 +106,9 @@ def convert_f32(src, out_kind=OUT_BF16, ldd=None, out=None):
         lo = torch.empty((rows, ldd), dtype=torch.bfloat16, device=src.device) if out_kind == OUT_BF16_SPLIT else None
     else:
         hi, lo = out
-    check(_native.lib().nnam_convert_f32(_ptr(src), rows, cols, src.stride(0), _ptr(hi), _ptr(lo), ldd, out_kind,
-                                         _stream()))
+    with _Prof("convert", rows * cols * 4):
+        check(_native.lib().nnam_convert_f32(_ptr(src), rows, cols, src.stride(0), _ptr(hi), _ptr(lo), ldd,
+                                             out_kind, _stream()))
     return hi, lo
 
 
@@ -99,9 +126,10 @@ def linear_bias_act(a_hi, a_lo, w_hi, w_lo, bias, M, N, K, act="identity", out_k
         lo = torch.empty((M, ldo), dtype=dt, device=a_hi.device) if out_kind == OUT_BF16_SPLIT else None
     else:
         hi, lo = out
-    check(_native.lib().nnam_linear_bias_act(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(w_hi), _ptr(w_lo),
-                                             w_hi.stride(0), _ptr(bias), _ptr(hi), _ptr(lo), ldo, M, N, K,
-                                             ACT[act], out_kind, nsplit, _stream()))
+    with _Prof("gemm", 2.0 * M * N * K):  # ALGORITHMIC flops (one pass, unpadded), whatever nsplit is
+        check(_native.lib().nnam_linear_bias_act(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(w_hi), _ptr(w_lo),
+                                                 w_hi.stride(0), _ptr(bias), _ptr(hi), _ptr(lo), ldo, M, N, K,
+                                                 ACT[act], out_kind, nsplit, _stream()))
     return hi, lo
 
 
@@ -129,7 +157,8 @@ def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=No
         for t in (rw, rb, rlb):
             _req(t, torch.float32, "rpl")
     _req(prior, torch.float32, "prior")
-    check(_native.lib().nnam_head(ptrs, wts, k, ld_in, int(bool(pre_normalize)), _ptr(rw), _ptr(rb), _ptr(rlb),
-                                  _ptr(prior), float(prior_scale), int(bool(final_normalize)), _ptr(out),
-                                  out.stride(0), rows, n_classes, _stream()))
+    with _Prof("head", rows * n_classes * 4 * (k + 1)):
+        check(_native.lib().nnam_head(ptrs, wts, k, ld_in, int(bool(pre_normalize)), _ptr(rw), _ptr(rb), _ptr(rlb),
+                                      _ptr(prior), float(prior_scale), int(bool(final_normalize)), _ptr(out),
+                                      out.stride(0), rows, n_classes, _stream()))
     return out

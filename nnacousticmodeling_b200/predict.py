@@ -1,0 +1,165 @@
+"""``predict()`` and the ``predict_folds`` CLI of the reference (scripts/common/predict_folds.py),
+re-hosted on the B200 kernels.  Same signature and file conventions; ``gpu`` may also be a list of
+device indices (utterance/frame ranges are sharded across them with no collective)."""
+from __future__ import annotations
+
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+
+from . import engine, functions as F
+from ._native import NnamError
+from .features import adapt_transform, loadKaldiFeatureTransform
+from .networks import Classifier, get_nn, is_nn_recurrent, load_npz
+
+
+def _devices(gpu):
+    devs = list(gpu) if isinstance(gpu, (list, tuple)) else [gpu]
+    if any(int(d) < 0 for d in devs):
+        raise NnamError("gpu < 0 (CPU) is not supported by nnacousticmodeling_b200")
+    return [int(d) for d in devs]
+
+
+def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft, progress=True, ivectors=None,
+            out=None, fix_timedelay_tail=False):
+    """predict_folds.py:27-95.  Returns (N, num_classes) float32 log-softmax outputs.
+
+    Extensions: ``ivectors`` (N, I) are appended AFTER splice + transform (train.py:255-258 /
+    evaluate.py:169-171 order); ``out`` may be a caller-owned (pinned) array;
+    ``fix_timedelay_tail`` fills the last ``timedelay`` frames that the reference leaves 0 (quirk Q4).
+    """
+    devs = _devices(gpu)
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    n = x.shape[0]
+    if out is None:
+        out = np.zeros((n, num_classes), dtype=np.float32)
+    elif out.shape != (n, num_classes) or out.dtype != np.float32:
+        raise NnamError("predict: out must be float32 of shape (N, num_classes)")
+    if n == 0:
+        return out
+    if is_nn_recurrent(network):
+        from . import recurrent_engine
+        if offsets is None:
+            raise NnamError("predict: recurrent networks need utterance offsets")
+        offsets = np.asarray(offsets)
+        shards = engine.partition_utterances(offsets, len(devs))
+        engine.run_sharded(
+            lambda sh, d: recurrent_engine.forward_utterances(model, x, offsets, out, sh[0], sh[1], ft=ft,
+                                                              ivectors=ivectors, timedelay=timedelay, device=d,
+                                                              fix_timedelay_tail=fix_timedelay_tail),
+            shards, devs)
+    else:
+        splice = int(winlen) // 2
+        shards = engine.partition_frames(n, len(devs))
+        engine.run_sharded(
+            lambda sh, d: engine.ff_forward_frames(model, x, ft, splice, out, sh[0], sh[1], ivectors=ivectors,
+                                                   device=d),
+            shards, devs)
+    return out
+
+
+def _activation(name):
+    if name not in ("sigmoid", "tanh", "relu"):
+        print("Wrong activation function specified")
+        sys.exit(1)
+    return F.resolve(name)
+
+
+def main(arg_list=None):
+    """predict_folds.py:97-246 -- same flags, same directory conventions, same outputs."""
+    parser = argparse.ArgumentParser(description="B200 network-output step (predict_folds drop-in)")
+    parser.add_argument("--network", "-n", default="ff")
+    parser.add_argument("--gpu", "-g", type=int, nargs="+", default=[0], help="GPU id(s); CPU (<0) is not supported")
+    parser.add_argument("--units", "-u", type=int, nargs="+", default=[1024])
+    parser.add_argument("--layers", "-l", type=int, default=2)
+    parser.add_argument("--activation", "-a", default="relu")
+    parser.add_argument("--tdnn-ksize", type=int, nargs="+", default=[5])
+    parser.add_argument("--timedelay", type=int, default=0)
+    parser.add_argument("--splice", type=int, default=0)
+    parser.add_argument("--dropout", "-d", type=float, nargs="+", default=[0])
+    parser.add_argument("--ft")
+    parser.add_argument("--tri", action="store_true")
+    parser.add_argument("--data-dir", default="data/fmllr")
+    parser.add_argument("--offset-dir", default="data")
+    parser.add_argument("--ivector-dir")
+    parser.add_argument("--data", default="data_{}.npy")
+    parser.add_argument("--offsets", default="offsets_{}.npy")
+    parser.add_argument("--ivectors", default="ivectors_{}.npy")
+    parser.add_argument("--fold-data-dir")
+    parser.add_argument("--fold-output-dir")
+    parser.add_argument("--fold-model-dir")
+    parser.add_argument("--fold-output-dev")
+    parser.add_argument("--fold-data-pattern", default="data_{}.npy")
+    parser.add_argument("--fold-offset-pattern", default="offsets_{}.npy")
+    parser.add_argument("--fold-ivector-pattern", default="ivectors_{}.npy")
+    parser.add_argument("--fold-output-pattern", default="data_{}.npy")
+    parser.add_argument("--fold-network-pattern", default="fold_{}.npz")
+    parser.add_argument("--no-progress", action="store_true")
+    parser.add_argument("--precision", default=None, choices=["fp32", "bf16"], help="extension: GEMM precision mode")
+    args = parser.parse_args(list(map(str, arg_list)) if arg_list is not None else None)
+
+    out_file = Path(args.fold_output_dir, args.fold_output_dev or args.fold_output_pattern)
+    out_file.parent.mkdir(exist_ok=True, parents=True)
+    num_classes = 1909 if args.tri else 39
+    model = get_nn(args.network, args.layers, args.units, num_classes, _activation(args.activation),
+                   args.tdnn_ksize, args.dropout)
+    if args.precision:
+        model.precision = args.precision
+    model_cls = Classifier(model)
+    recurrent = is_nn_recurrent(args.network)
+    splice = (sum(args.tdnn_ksize) - len(args.tdnn_ksize)) // 2 if args.network == "tdnn" else args.splice
+    winlen = 2 * splice + 1
+    ft = None
+    if args.ft is not None and args.ft != "-":
+        ft = adapt_transform(loadKaldiFeatureTransform(str(Path(args.data_dir, args.ft))), args.network, splice,
+                             recurrent)
+    gpu = args.gpu if len(args.gpu) > 1 else args.gpu[0]
+
+    def fold_models():
+        fold = 0
+        while True:
+            f = Path(args.fold_model_dir, args.fold_network_pattern.format(fold))
+            if not f.is_file():
+                return
+            load_npz(str(f), model_cls)
+            print("Predicting fold {} data".format(fold))
+            yield fold
+            fold += 1
+
+    n_folds = 0
+    if args.fold_output_dev is not None:
+        x = np.load(str(Path(args.data_dir, args.data.format("dev"))))
+        offsets = np.load(str(Path(args.offset_dir, args.offsets.format("dev")))) if recurrent else None
+        iv = np.load(str(Path(args.ivector_dir, args.ivectors.format("dev")))) if args.ivector_dir else None
+        y_out = 0
+        for _ in fold_models():
+            y_out = y_out + predict(model, x, offsets, num_classes, args.network, gpu, winlen, args.timedelay, ft,
+                                    not args.no_progress, ivectors=iv)
+            n_folds += 1
+        if n_folds == 0:
+            print("Error: No fold networks found")
+            sys.exit(2)
+        # predict_folds.py:217-219: mean of the fold LOG-SOFTMAX outputs, renormalised (quirk Q5)
+        y_out /= n_folds
+        mx = y_out.max(axis=1, keepdims=True)
+        y_out = y_out - (mx + np.log(np.exp(y_out - mx).sum(axis=1, keepdims=True)))
+        np.save(str(Path(args.fold_output_dir, args.fold_output_dev)), y_out.astype(np.float32))
+    else:
+        for fold in fold_models():
+            x = np.load(str(Path(args.fold_data_dir, args.fold_data_pattern.format(fold))))
+            offsets = np.load(str(Path(args.fold_data_dir, args.fold_offset_pattern.format(fold)))) if recurrent else None
+            iv = (np.load(str(Path(args.fold_data_dir, args.fold_ivector_pattern.format(fold))))
+                  if args.ivector_dir else None)
+            y = predict(model, x, offsets, num_classes, args.network, gpu, winlen, args.timedelay, ft,
+                        not args.no_progress, ivectors=iv)
+            np.save(str(Path(args.fold_output_dir, args.fold_output_pattern.format(fold))), y)
+            n_folds += 1
+        if n_folds == 0:
+            print("Error: No fold networks found")
+            sys.exit(2)
+
+
+if __name__ == "__main__":
+    main()

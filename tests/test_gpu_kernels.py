@@ -1,0 +1,203 @@
+"""Parity of the CUDA kernels (through the C ABI) against the oracle / golden vectors.  -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import nnam_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from nnacousticmodeling_b200 import ops as _ops
+    return _ops
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _bf16(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+# ----------------------------------------------------------------------------------------- K1
+def test_splice_golden_bit_exact(ops, dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "splice.npz"))
+    ft = O.load_kaldi_feature_transform(os.path.join(golden_dir, "final.feature_transform"))
+    x = _t(g["x"], dev)
+    add, mul = _t(ft["addShift"], dev), _t(ft["rescale"], dev)
+    assert np.array_equal(ops.splice_transform(x, len(x), 5)[0].cpu().numpy(), g["splice11"])
+    assert np.array_equal(ops.splice_transform(x, len(x), 5, add, mul)[0].cpu().numpy(), g["splice11_ft"])
+    xs = _t(g["x_small"], dev)  # 3 frames: both clamps active in one window
+    assert np.array_equal(ops.splice_transform(xs, 3, 5)[0].cpu().numpy(), g["splice11_small"])
+    assert np.array_equal(ops.splice_transform(x[:64].contiguous(), 64, 8)[0].cpu().numpy(), g["splice17"])
+    assert np.array_equal(ops.splice_transform(x[:8].contiguous(), 8, 0)[0].cpu().numpy(), g["splice1"])
+
+
+def test_splice_recurrent_middle_block(ops, dev, golden_dir):
+    g = np.load(os.path.join(golden_dir, "timedelay.npz"))
+    ft = O.select_transform_for_network(
+        O.load_kaldi_feature_transform(os.path.join(golden_dir, "final.feature_transform")), "lstm")
+    out, _ = ops.splice_transform(_t(g["x"], dev), len(g["x"]), 0, _t(ft["addShift"], dev), _t(ft["rescale"], dev))
+    assert np.array_equal(out.cpu().numpy(), g["x_mid_ft"])
+
+
+@pytest.mark.parametrize("n,dim,splice,ivd", [(1000, 40, 5, 100), (333, 40, 5, 0), (70, 13, 3, 5), (129, 40, 0, 100),
+                                              (1, 40, 5, 0), (5000, 40, 5, 100)])
+def test_splice_ivectors_shards_and_odd_dims(ops, dev, n, dim, splice, ivd):
+    rng = np.random.default_rng(n + dim)
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    iv = rng.standard_normal((n, ivd)).astype(np.float32) if ivd else None
+    w = 2 * splice + 1
+    ft = {"addShift": rng.standard_normal(w * dim).astype(np.float32),
+          "rescale": (1 + 0.1 * rng.standard_normal(w * dim)).astype(np.float32)}
+    want = O.apply_kaldi_feature_transform(O.splicing(x, range(-splice, splice + 1)), ft)
+    if iv is not None:
+        want = np.concatenate((want, iv), axis=1)
+    add, mul = _t(ft["addShift"], dev), _t(ft["rescale"], dev)
+    got = ops.splice_transform(_t(x, dev), n, splice, add, mul, None if iv is None else _t(iv, dev))[0]
+    assert np.array_equal(got.cpu().numpy(), want)
+    # shards: rows [f0, f1) from a buffer that only holds the halo'd slice, must equal the 1-shot output
+    for parts in (2, 3):
+        pieces = []
+        for i in range(parts):
+            f0, f1 = n * i // parts, n * (i + 1) // parts
+            if f1 == f0:
+                continue
+            lo, hi = max(f0 - splice, 0), min(f1 + splice, n)
+            o = ops.splice_transform(_t(x[lo:hi], dev), n, splice, add, mul,
+                                     None if iv is None else _t(iv[f0:f1], dev), f0=f0, f1=f1, x_row0=lo)[0]
+            pieces.append(o.cpu().numpy())
+        assert np.array_equal(np.concatenate(pieces), want)
+    # bf16 and bf16 hi/lo outputs: hi == bf16(fp32 value), hi + lo ~ fp32 value to 2^-16
+    hi, lo = ops.splice_transform(_t(x, dev), n, splice, add, mul, None if iv is None else _t(iv, dev),
+                                  out_kind=ops.OUT_BF16_SPLIT)
+    cols = want.shape[1]
+    assert np.array_equal(hi.float().cpu().numpy()[:, :cols], _bf16(want))
+    assert np.all(hi.float().cpu().numpy()[:, cols:] == 0)
+    rec = (hi.float() + lo.float()).cpu().numpy()[:, :cols]
+    assert np.abs(rec - want).max() <= 2.0 ** -15 * max(1.0, np.abs(want).max())
+
+
+def test_splice_rejects_bad_arguments(ops, dev):
+    from nnacousticmodeling_b200 import NnamError
+    x = torch.zeros(10, 40, device=dev)
+    with pytest.raises(NnamError):
+        ops.splice_transform(x, 100, 5, f0=50, f1=60, x_row0=0)  # buffer does not cover the halo
+    with pytest.raises(NnamError):
+        ops.splice_transform(torch.zeros(10, 40), 10, 5)  # host tensor: no CPU path
+    assert ops.splice_transform(x, 10, 5, f0=4, f1=4)[0].shape[0] == 0  # empty range is a no-op
+
+
+# ----------------------------------------------------------------------------------------- K4
+def test_head_golden(ops, dev, golden_dir):
+    h = np.load(os.path.join(golden_dir, "head.npz"))
+    ap = np.load(os.path.join(golden_dir, "log_ap_Kaldi1909.npy"))
+    y = _t(h["y"], dev)
+    assert np.abs(ops.head(y, 1909).cpu().numpy() - h["logsoftmax"]).max() < 1e-4
+    got = ops.head(y, 1909, prior=_t(ap.reshape(-1), dev)).cpu().numpy()
+    assert np.abs(got - h["head_ap"]).max() < 1e-4
+    got = ops.head(y, 1909, prior=_t(ap.reshape(-1), dev), prior_scale=0.5).cpu().numpy()
+    assert np.abs(got - O.head(h["y"], np.float32(0.5) * ap)).max() < 1e-4
+
+
+@pytest.mark.parametrize("c,rows,ld", [(39, 77, 48), (1909, 300, 1920), (1000, 17, 1000), (2048, 9, 2048), (7, 1, 7)])
+def test_head_ensembles_rpl_and_shapes(ops, dev, c, rows, ld):
+    rng = np.random.default_rng(c)
+    ys = [(2 * rng.standard_normal((rows, c))).astype(np.float32) for _ in range(3)]
+
+    def dv(a):
+        buf = torch.zeros(rows, ld, device=dev)
+        buf[:, :c] = _t(a, dev)
+        return buf
+
+    yd = [dv(a) for a in ys]
+    assert np.abs(ops.head(yd[0], c).cpu().numpy() - O.log_softmax(ys[0])).max() < 1e-4
+    # evaluate.py:35-51 master + folds: (K*master + sum folds) / (2K), then log-softmax
+    k = 2
+    want = O.log_softmax(O.nn_with_rpl(lambda v: ys[0], [lambda v: ys[1], lambda v: ys[2]], None, None))
+    got = ops.head(yd, c, weights=[k / (2 * k), 1 / (2 * k), 1 / (2 * k)]).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-4
+    # predict_folds dev mode: mean of log-softmax outputs, renormalised
+    want = O.log_softmax((O.log_softmax(ys[0]) + O.log_softmax(ys[1]) + O.log_softmax(ys[2])) / np.float32(3))
+    got = ops.head(yd, c, pre_normalize=True).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-4
+    # RPL4 then prior then log-softmax
+    prm = {"W": (0.1 * rng.standard_normal((1, c))).astype(np.float32),
+           "b": (0.1 * rng.standard_normal((1, c))).astype(np.float32), "lb": np.full((1, c), -6.0, np.float32)}
+    ap = (-3 + rng.standard_normal((1, c))).astype(np.float32)
+    want = O.head(O.rpl4(prm, ys[1]), ap)
+    got = ops.head(yd[1], c, rpl=tuple(_t(prm[n].reshape(-1), dev) for n in ("W", "b", "lb")),
+                   prior=_t(ap.reshape(-1), dev)).cpu().numpy()
+    assert np.abs(got - want).max() < 1e-4
+    # raw (un-normalised) ensemble mean
+    got = ops.head(yd[:2], c, final_normalize=False).cpu().numpy()
+    assert np.abs(got - (ys[0] + ys[1]) / 2).max() < 1e-5
+
+
+# ----------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1, 16, 8), (300, 1024, 544), (1000, 1909, 440), (77, 40, 40),
+                                   (2048, 2048, 2048), (513, 2048, 140), (129, 1909, 1024)])
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_linear_bias_act(ops, dev, m, n, k, mode):
+    rng = np.random.default_rng(m * 7 + n)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    split = mode == "fp32"
+    kind = ops.OUT_BF16_SPLIT if split else ops.OUT_BF16
+    a_hi, a_lo = ops.convert_f32(_t(a, dev), kind)
+    w_hi, w_lo = ops.convert_f32(_t(w, dev), kind)
+    for act in ("relu", "identity"):
+        got, _ = ops.linear_bias_act(a_hi, a_lo, w_hi, w_lo, _t(b, dev), m, n, k, act=act, out_kind=ops.OUT_F32,
+                                     nsplit=3 if split else 1)
+        got = got.cpu().numpy()[:, :n]
+        if split:
+            ref = a.astype(np.float64) @ w.astype(np.float64).T + b
+            tol = 2e-4  # bf16x3: 16 mantissa bits per operand
+        else:
+            ref = _bf16(a).astype(np.float64) @ _bf16(w).astype(np.float64).T + b
+            tol = 5e-5  # exact products of bf16 inputs, fp32 accumulation
+        ref = O.activation(act)(ref)
+        assert np.abs(got - ref).max() < tol * max(1.0, np.abs(ref).max())
+    # bf16 / split outputs of the hidden layers
+    hi, lo = ops.linear_bias_act(a_hi, a_lo, w_hi, w_lo, _t(b, dev), m, n, k, act="relu", out_kind=kind,
+                                 nsplit=3 if split else 1)
+    rec = hi.float() if lo is None else hi.float() + lo.float()
+    assert np.abs(rec.cpu().numpy()[:, :n] - ref * (ref > 0)).max() < (2e-4 if split else 2e-2) * max(1.0, np.abs(ref).max())
+
+
+def test_linear_activations_match_chainer_formulation(ops, dev):
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((256, 512)).astype(np.float32)
+    w = (rng.standard_normal((512, 512)) / np.sqrt(512)).astype(np.float32)
+    a_hi, a_lo = ops.convert_f32(_t(a, dev), ops.OUT_BF16_SPLIT)
+    w_hi, w_lo = ops.convert_f32(_t(w, dev), ops.OUT_BF16_SPLIT)
+    for act in ("sigmoid", "tanh"):
+        got, _ = ops.linear_bias_act(a_hi, a_lo, w_hi, w_lo, None, 256, 512, 512, act=act, out_kind=ops.OUT_F32, nsplit=3)
+        ref = O.activation(act)((a.astype(np.float64) @ w.astype(np.float64).T).astype(np.float32))
+        assert np.abs(got.cpu().numpy() - ref).max() < 1e-4
+
+
+def test_linear_rejects_bad_arguments(ops, dev):
+    from nnacousticmodeling_b200 import NnamError
+    a = torch.zeros(16, 24, dtype=torch.bfloat16, device=dev)
+    w = torch.zeros(16, 24, dtype=torch.bfloat16, device=dev)
+    with pytest.raises(NnamError):
+        ops.linear_bias_act(a, None, w, None, None, 16, 16, 24, nsplit=3)  # missing lo operands
+    with pytest.raises(NnamError):
+        ops.linear_bias_act(a, None, w, None, None, 16, 16, 24, nsplit=2)
+    with pytest.raises(NnamError):
+        a20 = torch.zeros(16, 20, dtype=torch.bfloat16, device=dev)
+        ops.linear_bias_act(a20, None, w, None, None, 16, 16, 20)  # lda = 20 elements: rows not 16-byte aligned

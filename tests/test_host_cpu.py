@@ -1,0 +1,99 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, host logic, CLI parsing."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import nnacousticmodeling_b200 as nn
+from nnacousticmodeling_b200 import _native
+from oracle import nnam_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    _native.build()
+    return _native.lib()
+
+
+def test_library_exports_every_symbol_in_header(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "nnam_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(nnam_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        assert hasattr(raw, sym), f"{sym} declared in include/nnam_b200.h but not exported"
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    assert built_lib.nnam_abi_version() == 1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(nn.NnamError, match="no CPU or PyTorch fallback"):
+        _native.lib()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "nnacousticmodeling_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "oracle" not in src, f"{f} must not reference the oracle"
+
+
+def test_feature_transform_parser_and_adaptation(golden_dir):
+    ft = nn.loadKaldiFeatureTransform(os.path.join(golden_dir, "final.feature_transform"))
+    ref = O.load_kaldi_feature_transform(os.path.join(golden_dir, "final.feature_transform"))
+    assert ft["shape"] == ref["shape"] and ft["shifts"] == ref["shifts"]
+    assert np.array_equal(ft["addShift"], ref["addShift"]) and np.array_equal(ft["rescale"], ref["rescale"])
+    for net, spl in (("lstm", 0), ("gru", 0), ("tdnn", 8), ("ff", 5)):
+        a = nn.adapt_transform(ft, net, spl, nn.is_nn_recurrent(net))
+        b = O.select_transform_for_network(ref, net, spl)
+        assert a["shape"] == b["shape"] and a["shifts"] == b["shifts"]
+        assert np.array_equal(a["addShift"], b["addShift"]) and np.array_equal(a["rescale"], b["rescale"])
+    assert ft["shape"] == [440, 40]  # adapt_transform must not modify its input
+
+
+def test_get_nn_dispatch_and_param_layout():
+    kinds = {"ff": nn.MLP, "lstm": nn.LSTM, "zoneoutlstm": nn.ZoneoutLSTM, "zoneoutdropoutlstm": nn.ZoneoutDropoutLSTM,
+             "peepholelstm": nn.PeepholeLSTM, "gru": nn.GRU, "mgrurelu": nn.NetMGRU, "mgrurelur": nn.NetMGRU}
+    for name, cls in kinds.items():
+        drop = [0.5, 0.5] if name == "zoneoutlstm" else ([0, 0.5, 0.5] if name == "zoneoutdropoutlstm" else [0])
+        m = nn.get_nn(name, 2, [16], 39, nn.F.relu, [5], drop)
+        assert type(m) is cls and m.network == name
+        assert nn.is_nn_recurrent(name) == m.recurrent
+        m.init_params(12)
+        ref = O.init_mlp(np.random.default_rng(0), 12, 16, 2, 39) if name == "ff" else \
+            O.init_recurrent(np.random.default_rng(0), name, 12, 16, 2, 39)
+        assert {k: v.shape for k, v in m.params.items()} == {k: v.shape for k, v in ref.items()}
+    assert np.all(nn.get_nn("lstm", 1, [4], 3, "relu", [5]).init_params(5).params["layer_0/upward/b"][2::4] == 1)
+    t = nn.get_nn("tdnn", 4, [8, 8, 8, 8], 39, nn.F.relu, [5, 5, 5, 5])
+    assert t.input_win_size == 17
+    with pytest.raises(SystemExit):
+        nn.get_nn("nope", 1, [4], 3, "relu", [5])
+    with pytest.raises(nn.NnamError):
+        nn.get_nn("ff", 2, [16], 39, "relu", [5]).load_params({"layer_0/W": np.zeros((16, 12))})
+
+
+def test_partitions_cover_everything():
+    off = O.synth_set(3, 57)[1]
+    for parts in (1, 2, 4, 8, 57, 64):
+        sh = nn.partition_utterances(off, parts)
+        assert sh[0][0] == 0 and sh[-1][1] == 57 and all(a[1] == b[0] for a, b in zip(sh, sh[1:]))
+        fr = nn.partition_frames(int(off[-1]), parts)
+        assert fr[0][0] == 0 and fr[-1][1] == off[-1] and all(a[1] == b[0] for a, b in zip(fr, fr[1:]))
+    loads = [off[b] - off[a] for a, b in nn.partition_utterances(off, 8)]
+    assert max(loads) < 1.3 * (off[-1] / 8)
+
+
+def test_lab_writer_matches_reference_format(golden_dir, tmp_path):
+    want = open(os.path.join(golden_dir, "sample.lab"), "rb").read()
+    y = np.load(os.path.join(golden_dir, "head.npz"))["logsoftmax"][:4]
+    nn.saveBin(str(tmp_path / "a.lab"), y)
+    assert (tmp_path / "a.lab").read_bytes() == want
+    assert np.array_equal(nn.loadBin(str(tmp_path / "a.lab")), y)
