@@ -101,6 +101,65 @@ int nnam_head(const float* const* logits_host, const float* weights_host, int n_
               float prior_scale, int final_normalize, float* out, long long ld_out, long long rows,
               int n_classes, void* stream);
 
+/* nnam_head with a scatter map: logits row r is written to out row out_row_map[r] (a negative entry drops the
+ * row).  Used by the recurrent path, whose rows are time-major "packed"; dropping rows reproduces the reference's
+ * unwritten last `timedelay` frames (predict_folds.py:50,60-61, quirk Q4).  */
+int nnam_head_scatter(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in,
+                      int pre_normalize, const float* rpl_w, const float* rpl_b, const float* rpl_lb,
+                      const float* prior, float prior_scale, int final_normalize, float* out, long long ld_out,
+                      long long rows, int n_classes, const int* out_row_map, void* stream);
+
+/* Row gather + feature transform (+ i-vector append) for recurrent nets: out[r] = transform(x[row_map[r]]) ++
+ * ivec[row_map[r]].  Replaces the per-utterance `np.pad(..., mode="edge")` + applyKaldiFeatureTransform + padded
+ * (U, Lmax+timedelay, D) batch assembly of predict_folds.py:34-43 / evaluateModelForTest.py:57-59: row_map lists,
+ * in time-major packed order, the source frame of every (utterance, step), repeating the last frame `timedelay`
+ * times.  add_shift/rescale have `dim` entries (the shift-0 block) or are NULL.  Output bf16 / bf16 split / f32.  */
+int nnam_gather_transform(const float* x, long long n_src, int dim, const float* add_shift, const float* rescale,
+                          const float* ivec, int ivec_dim, const int* row_map, long long n_rows, void* out_hi,
+                          void* out_lo, long long ldo, int out_kind, void* stream);
+
+/* K3 -- persistent recurrence kernel: one launch runs a whole layer (one or both directions) over a whole shard.
+ * Replaces the per-time-step Python loop around L.LSTM / F.lstm (chainer_networks.py:44-62 via
+ * predict_folds.py:49-61 and evaluateModelForTest.py:67-80).  See csrc/recurrent.cu for the data layout.  */
+typedef struct NnamRnnDesc {
+  int cell;    /* NNAM_CELL_* */
+  int hidden;  /* H (multiple of 64) */
+  int n_dirs;  /* 1, or 2 = bidirectional: direction 1 walks every utterance backwards */
+  int batch;   /* utterances per batch: 16, 32 or 64 */
+  int nsplit;  /* 1 = bf16 operands, 3 = bf16x3 (needs the _lo buffers) */
+  int flags;   /* GRU family: bit 0 = reset gate, bits 1-2 = candidate activation (NNAM_ACT_*) */
+  const float* gx[2];  /* per direction: input projection + bias for every packed row, (rows, gx_ld) fp32,
+                          columns gate-interleaved exactly like Chainer's upward/W rows */
+  long long gx_ld;
+  const void* w_hi[2]; /* per direction: lateral weights (gates*H, H) bf16 K-major (Chainer lateral/W layout) */
+  const void* w_lo[2];
+  long long w_ld;
+  const float* u_bias[2]; /* GRU family: hidden-side biases, applied from the second step on (MGRU.py:70-83) */
+  void* h_hi;          /* layer output (rows, h_ld) bf16; direction d writes columns [d*H, (d+1)*H) */
+  void* h_lo;          /* low halves (bf16x3) or NULL */
+  long long h_ld;
+  int n_items;                 /* work items = (batch, direction) pairs, grouped by CTA group */
+  const int* item_batch;       /* device arrays */
+  const int* item_dir;
+  int n_groups;
+  const int* group_item_start; /* n_groups + 1 */
+  const int* batch_row0;       /* first packed row of each batch */
+  const int* batch_steps;      /* steps (= longest utterance) of each batch */
+  const int* batch_nutt;       /* utterances in each batch (<= batch) */
+  const int* batch_base_off;   /* offset of each batch's prefix-sum table inside `base` */
+  const int* base;             /* per batch: base[t] = sum_{t' < t} active(t'), steps + 1 entries */
+  const int* utt_len;          /* steps of every utterance in sorted order; batch b owns [b*batch, ...) */
+  const void* h0_hi;           /* optional initial hidden state (n_utts, H*n_dirs) bf16 (+ lo), sorted order */
+  const void* h0_lo;
+  const float* c0;             /* optional initial cell state (n_utts, H*n_dirs) fp32 */
+  float* c_out;                /* optional final cell state, same shape */
+  unsigned int* counters;      /* n_groups words of scratch */
+} NnamRnnDesc;
+
+int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream);
+/* CTAs per group and the number of groups the current device can run for this cell configuration.  */
+int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups);
+
 #ifdef __cplusplus
 }
 #endif

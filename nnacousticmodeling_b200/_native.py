@@ -75,7 +75,33 @@ _SIGNATURES = {
                                      c_void_p]),
     "nnam_head": (c_int, [POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_float, c_int, c_void_p, c_longlong, c_longlong, c_int, c_void_p]),
+    "nnam_head_scatter": (c_int, [POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_float, c_int, c_void_p, c_longlong, c_longlong, c_int, c_void_p,
+                                  c_void_p]),
+    "nnam_gather_transform": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                      c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "nnam_rnn_seq": (c_int, [c_void_p, c_void_p]),
+    "nnam_rnn_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
 }
+
+
+class RnnDesc(ctypes.Structure):
+    """Mirror of ``NnamRnnDesc`` (include/nnam_b200.h)."""
+
+    _fields_ = [
+        ("cell", c_int), ("hidden", c_int), ("n_dirs", c_int), ("batch", c_int), ("nsplit", c_int), ("flags", c_int),
+        ("gx", c_void_p * 2), ("gx_ld", c_longlong),
+        ("w_hi", c_void_p * 2), ("w_lo", c_void_p * 2), ("w_ld", c_longlong),
+        ("u_bias", c_void_p * 2),
+        ("h_hi", c_void_p), ("h_lo", c_void_p), ("h_ld", c_longlong),
+        ("n_items", c_int), ("item_batch", c_void_p), ("item_dir", c_void_p),
+        ("n_groups", c_int), ("group_item_start", c_void_p),
+        ("batch_row0", c_void_p), ("batch_steps", c_void_p), ("batch_nutt", c_void_p), ("batch_base_off", c_void_p),
+        ("base", c_void_p), ("utt_len", c_void_p),
+        ("h0_hi", c_void_p), ("h0_lo", c_void_p), ("c0", c_void_p), ("c_out", c_void_p),
+        ("counters", c_void_p),
+    ]
+
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

@@ -76,7 +76,13 @@ int convert_f32(const float* src, long long rows, int cols, long long lds, void*
                 int out_kind, cudaStream_t stream);
 int head(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in, int pre_normalize,
          const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior, float prior_scale,
-         int final_normalize, float* out, long long ld_out, long long rows, int n_classes, cudaStream_t stream);
+         int final_normalize, float* out, long long ld_out, long long rows, int n_classes, const int* out_row_map,
+         cudaStream_t stream);
+int gather_transform(const float* x, long long n_src, int dim, const float* add_shift, const float* rescale,
+                     const float* ivec, int ivec_dim, const int* row_map, long long n_rows, void* out_hi, void* out_lo,
+                     long long ldo, int out_kind, cudaStream_t stream);
+int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream);
+int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups);
 
 }  // namespace nnam
 
@@ -116,7 +122,33 @@ int nnam_head(const float* const* logits_host, const float* weights_host, int n_
               float prior_scale, int final_normalize, float* out, long long ld_out, long long rows, int n_classes,
               void* stream) {
   return nnam::head(logits_host, weights_host, n_inputs, ld_in, pre_normalize, rpl_w, rpl_b, rpl_lb, prior,
-                    prior_scale, final_normalize, out, ld_out, rows, n_classes, static_cast<cudaStream_t>(stream));
+                    prior_scale, final_normalize, out, ld_out, rows, n_classes, nullptr,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int nnam_head_scatter(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in,
+                      int pre_normalize, const float* rpl_w, const float* rpl_b, const float* rpl_lb,
+                      const float* prior, float prior_scale, int final_normalize, float* out, long long ld_out,
+                      long long rows, int n_classes, const int* out_row_map, void* stream) {
+  return nnam::head(logits_host, weights_host, n_inputs, ld_in, pre_normalize, rpl_w, rpl_b, rpl_lb, prior,
+                    prior_scale, final_normalize, out, ld_out, rows, n_classes, out_row_map,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int nnam_gather_transform(const float* x, long long n_src, int dim, const float* add_shift, const float* rescale,
+                          const float* ivec, int ivec_dim, const int* row_map, long long n_rows, void* out_hi,
+                          void* out_lo, long long ldo, int out_kind, void* stream) {
+  return nnam::gather_transform(x, n_src, dim, add_shift, rescale, ivec, ivec_dim, row_map, n_rows, out_hi, out_lo,
+                                ldo, out_kind, static_cast<cudaStream_t>(stream));
+}
+
+int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream) {
+  return nnam::rnn_seq(desc, static_cast<cudaStream_t>(stream));
+}
+
+int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups) {
+  if (!group_ctas || !max_groups) return nnam::set_error(NNAM_ERR_ARG, "rnn_plan: NULL output");
+  return nnam::rnn_plan(cell, hidden, batch, nsplit, group_ctas, max_groups);
 }
 
 }  // extern "C"

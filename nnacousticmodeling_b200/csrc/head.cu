@@ -35,6 +35,7 @@ struct HeadParams {
   long long ld_out;
   long long rows;
   int n_classes;
+  const int* out_row_map;  // optional scatter: logits row r -> out row map[r] (negative: drop)
 };
 
 __device__ __forceinline__ float warp_max(float v) {
@@ -119,7 +120,12 @@ __global__ void __launch_bounds__(HEAD_THREADS, (MULTI || NV < 64) ? 1 : 2) head
       }
     }
     const float lse = p.final_normalize ? row_logsumexp<NV>(h, lane, C) : 0.0f;
-    float* dst = p.out + row * p.ld_out;
+    long long out_row = row;
+    if (p.out_row_map != nullptr) {
+      out_row = __ldg(p.out_row_map + row);
+      if (out_row < 0) continue;  // warp-uniform: one row per warp
+    }
+    float* dst = p.out + out_row * p.ld_out;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
@@ -130,7 +136,8 @@ __global__ void __launch_bounds__(HEAD_THREADS, (MULTI || NV < 64) ? 1 : 2) head
 
 int head(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in, int pre_normalize,
          const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior, float prior_scale,
-         int final_normalize, float* out, long long ld_out, long long rows, int n_classes, cudaStream_t stream) {
+         int final_normalize, float* out, long long ld_out, long long rows, int n_classes, const int* out_row_map,
+         cudaStream_t stream) {
   if (n_inputs < 1 || n_inputs > HEAD_MAX_INPUTS)
     return set_error(NNAM_ERR_ARG, "head: n_inputs must be in [1, %d]", HEAD_MAX_INPUTS);
   if (n_classes < 1 || n_classes > 2048) return set_error(NNAM_ERR_UNSUPPORTED, "head: n_classes must be in [1, 2048]");
@@ -158,6 +165,7 @@ int head(const float* const* logits_host, const float* weights_host, int n_input
   p.ld_out = ld_out;
   p.rows = rows;
   p.n_classes = n_classes;
+  p.out_row_map = out_row_map;
   const int warps_per_block = HEAD_THREADS / 32;
   long long blocks = (rows + warps_per_block - 1) / warps_per_block;
   const long long cap = static_cast<long long>(sm_count()) * 8;  // grid-stride beyond 8 resident blocks per SM

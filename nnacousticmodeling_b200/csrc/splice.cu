@@ -242,6 +242,92 @@ int splice_transform(const float* x, long long x_row0, long long x_rows, long lo
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Row gather + transform (+ i-vector) for the recurrent path: out[r] = (x[map[r]] + add) * mul ++ ivec[map[r]].
+// 8 output elements per thread, 16-byte stores (bf16) / two float4 stores (fp32).
+template <int OUT_KIND>
+__global__ void gather_transform_kernel(const float* __restrict__ x, int dim, const float* __restrict__ add,
+                                        const float* __restrict__ mul, const float* __restrict__ ivec, int ivec_dim,
+                                        const int* __restrict__ row_map, long long n_rows, void* out_hi_v,
+                                        void* out_lo_v, long long ldo) {
+  const long long vpr = ldo >> 3;
+  const long long total = n_rows * vpr;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vpr;
+    const int c = static_cast<int>(i - r * vpr) << 3;
+    const long long src = __ldg(row_map + r);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cc = c + j;
+      if (cc < dim) {
+        float t = __ldg(x + src * dim + cc);
+        if (add != nullptr) t = __fmul_rn(__fadd_rn(t, __ldg(add + cc)), __ldg(mul + cc));
+        v[j] = t;
+      } else if (cc < dim + ivec_dim) {
+        v[j] = __ldg(ivec + src * ivec_dim + (cc - dim));
+      } else {
+        v[j] = 0.0f;
+      }
+    }
+    if (OUT_KIND == NNAM_OUT_F32) {
+      float4* dst = reinterpret_cast<float4*>(static_cast<float*>(out_hi_v) + r * ldo + c);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint32_t h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out_hi_v) + r * ldo)[c >> 3] =
+          make_uint4(h[0], h[1], h[2], h[3]);
+      if (OUT_KIND == NNAM_OUT_BF16_SPLIT) {
+        uint32_t l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          l[j] = pack_bf16x2(v[2 * j] - bf16_round(v[2 * j]), v[2 * j + 1] - bf16_round(v[2 * j + 1]));
+        reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out_lo_v) + r * ldo)[c >> 3] =
+            make_uint4(l[0], l[1], l[2], l[3]);
+      }
+    }
+  }
+}
+
+int gather_transform(const float* x, long long n_src, int dim, const float* add_shift, const float* rescale,
+                     const float* ivec, int ivec_dim, const int* row_map, long long n_rows, void* out_hi, void* out_lo,
+                     long long ldo, int out_kind, cudaStream_t stream) {
+  if (n_rows < 0 || n_src <= 0 || dim <= 0 || ivec_dim < 0) return set_error(NNAM_ERR_ARG, "gather: bad shape");
+  if (n_rows == 0) return NNAM_OK;
+  if (!row_map) return set_error(NNAM_ERR_ARG, "gather: row_map is NULL");
+  if ((add_shift == nullptr) != (rescale == nullptr)) return set_error(NNAM_ERR_ARG, "gather: add_shift/rescale");
+  if (ivec_dim > 0 && !ivec) return set_error(NNAM_ERR_ARG, "gather: ivec is NULL");
+  if (ldo < dim + ivec_dim || ldo % 8) return set_error(NNAM_ERR_ARG, "gather: ldo must be >= columns and %% 8 == 0");
+  if (reinterpret_cast<uintptr_t>(out_hi) & 15) return set_error(NNAM_ERR_ARG, "gather: out_hi alignment");
+  const long long total = n_rows * (ldo >> 3);
+  long long blocks = (total + 255) / 256;
+  const long long cap = static_cast<long long>(sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  const unsigned g = static_cast<unsigned>(blocks);
+  switch (out_kind) {
+    case NNAM_OUT_F32:
+      gather_transform_kernel<NNAM_OUT_F32><<<g, 256, 0, stream>>>(x, dim, add_shift, rescale, ivec, ivec_dim, row_map,
+                                                                  n_rows, out_hi, out_lo, ldo);
+      break;
+    case NNAM_OUT_BF16:
+      gather_transform_kernel<NNAM_OUT_BF16><<<g, 256, 0, stream>>>(x, dim, add_shift, rescale, ivec, ivec_dim,
+                                                                   row_map, n_rows, out_hi, out_lo, ldo);
+      break;
+    case NNAM_OUT_BF16_SPLIT:
+      if (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 15)) return set_error(NNAM_ERR_ARG, "gather: out_lo");
+      gather_transform_kernel<NNAM_OUT_BF16_SPLIT><<<g, 256, 0, stream>>>(x, dim, add_shift, rescale, ivec, ivec_dim,
+                                                                         row_map, n_rows, out_hi, out_lo, ldo);
+      break;
+    default:
+      return set_error(NNAM_ERR_ARG, "gather: unknown out_kind %d", out_kind);
+  }
+  return check_launch("gather_transform_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // fp32 -> bf16 / bf16 split staging of weights and pre-spliced inputs (8 elements per thread).
 template <bool SPLIT>
 __global__ void convert_f32_kernel(const float* __restrict__ src, long long rows, int cols, long long lds,

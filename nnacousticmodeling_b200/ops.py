@@ -134,7 +134,7 @@ def linear_bias_act(a_hi, a_lo, w_hi, w_lo, bias, M, N, K, act="identity", out_k
 
 
 def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=None, prior=None, prior_scale=1.0,
-         final_normalize=True, out=None):
+         final_normalize=True, out=None, out_row_map=None):
     """K4.  logits: one (rows, ld) f32 tensor or a list of them (ensemble)."""
     if isinstance(logits, torch.Tensor):
         logits = [logits]
@@ -157,8 +157,53 @@ def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=No
         for t in (rw, rb, rlb):
             _req(t, torch.float32, "rpl")
     _req(prior, torch.float32, "prior")
+    _req(out_row_map, torch.int32, "out_row_map")
     with _Prof("head", rows * n_classes * 4 * (k + 1)):
-        check(_native.lib().nnam_head(ptrs, wts, k, ld_in, int(bool(pre_normalize)), _ptr(rw), _ptr(rb), _ptr(rlb),
-                                      _ptr(prior), float(prior_scale), int(bool(final_normalize)), _ptr(out),
-                                      out.stride(0), rows, n_classes, _stream()))
+        if out_row_map is None:
+            check(_native.lib().nnam_head(ptrs, wts, k, ld_in, int(bool(pre_normalize)), _ptr(rw), _ptr(rb),
+                                          _ptr(rlb), _ptr(prior), float(prior_scale), int(bool(final_normalize)),
+                                          _ptr(out), out.stride(0), rows, n_classes, _stream()))
+        else:
+            check(_native.lib().nnam_head_scatter(ptrs, wts, k, ld_in, int(bool(pre_normalize)), _ptr(rw), _ptr(rb),
+                                                  _ptr(rlb), _ptr(prior), float(prior_scale),
+                                                  int(bool(final_normalize)), _ptr(out), out.stride(0), rows,
+                                                  n_classes, _ptr(out_row_map), _stream()))
     return out
+
+
+def gather_transform(x, row_map, add_shift=None, rescale=None, ivec=None, out_kind=OUT_BF16, ldo=None, out=None):
+    """Recurrent-path feature prep: out[r] = transform(x[row_map[r]]) ++ ivec[row_map[r]]."""
+    _req(x, torch.float32, "x")
+    _req(ivec, torch.float32, "ivec")
+    _req(row_map, torch.int32, "row_map")
+    if not x.is_contiguous() or (ivec is not None and not ivec.is_contiguous()):
+        raise NnamError("gather: x and ivec must be contiguous")
+    n_src, dim = x.shape
+    ivec_dim = 0 if ivec is None else ivec.shape[1]
+    n_rows = row_map.numel()
+    if ldo is None:
+        ldo = round_up(dim + ivec_dim, 8)
+    dt = torch.float32 if out_kind == OUT_F32 else torch.bfloat16
+    if out is None:
+        hi = torch.empty((n_rows, ldo), dtype=dt, device=x.device)
+        lo = torch.empty((n_rows, ldo), dtype=dt, device=x.device) if out_kind == OUT_BF16_SPLIT else None
+    else:
+        hi, lo = out
+    with _Prof("splice", n_rows * ((dim + ivec_dim) * 4 + (dim + ivec_dim) * (4 if out_kind != OUT_BF16 else 2))):
+        check(_native.lib().nnam_gather_transform(_ptr(x), n_src, dim, _ptr(add_shift), _ptr(rescale), _ptr(ivec),
+                                                  ivec_dim, _ptr(row_map), n_rows, _ptr(hi), _ptr(lo), ldo, out_kind,
+                                                  _stream()))
+    return hi, lo
+
+
+def rnn_plan(cell, hidden, batch, nsplit):
+    """(CTAs per group, max groups on the current device) for a recurrent cell configuration."""
+    g, m = ctypes.c_int(0), ctypes.c_int(0)
+    check(_native.lib().nnam_rnn_plan(cell, hidden, batch, nsplit, ctypes.byref(g), ctypes.byref(m)))
+    return g.value, m.value
+
+
+def rnn_seq(desc, flops):
+    """K3: run one recurrent layer (all batches, one or both directions) described by an RnnDesc."""
+    with _Prof("rnn", flops):
+        check(_native.lib().nnam_rnn_seq(ctypes.addressof(desc), _stream()))

@@ -1,0 +1,279 @@
+"""Host side of the recurrent path (K3): weight packing, the packed time-major schedule, and
+``forward_utterances`` = feature gather -> per layer (input-projection GEMM over all frames, persistent
+recurrence kernel) -> output GEMM -> head with scatter back to frame order.
+
+Packed layout.  Utterances of a shard are sorted by step count (descending) and cut into batches of NB.
+Batch b occupies rows [row0_b, row0_b + sum(steps)) in time-major order: row(t, u) = row0_b + base_b[t] + u,
+where base_b[t] = number of (utterance, step) pairs of the batch with step < t.  No padding rows exist, so
+unlike the reference (predict_folds.py:34-64 computes ALL utterances at every t up to Lmax) no work is spent
+on finished utterances.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import ops
+from ._native import NnamError, RnnDesc
+from .engine import HeadSpec, LinearDev, _as_host_tensor, _dev_vec, _device, get_plan
+from .ops import OUT_BF16, OUT_BF16_SPLIT, OUT_F32, round_up
+
+CELL_LSTM, CELL_GRU, CELL_PEEPHOLE = 0, 1, 2
+DEFAULT_BATCH = 32
+
+
+# ------------------------------------------------------------------------------------------
+# plan: packed weights per layer
+# ------------------------------------------------------------------------------------------
+class RecLayer:
+    pass
+
+
+def build_plan(plan, model):
+    p, dev, split = model.params, plan.device, plan.split
+    if model.network not in ("lstm", "zoneoutlstm", "zoneoutdropoutlstm", "blstm"):
+        raise NnamError(f"network '{model.network}' is not implemented on the B200 path yet")
+    plan.cell = CELL_LSTM
+    plan.n_dirs = 2 if model.bidirectional else 1
+    plan.hidden = model.n_units
+    plan.rec_layers = []
+    kind = OUT_BF16_SPLIT if split else OUT_BF16
+    dirs = ("fwd/", "bwd/") if model.bidirectional else ("",)
+    for l in range(model.layers):
+        L = RecLayer()
+        up_w = np.concatenate([p[f"layer_{l}/{d}upward/W"] for d in dirs], axis=0)
+        up_b = np.concatenate([p[f"layer_{l}/{d}upward/b"] for d in dirs], axis=0)
+        L.upward = LinearDev(up_w, up_b, dev, split)  # gx for both directions in one GEMM
+        L.lat = []
+        for d in dirs:
+            w = torch.from_numpy(np.ascontiguousarray(p[f"layer_{l}/{d}lateral/W"], dtype=np.float32)).to(dev)
+            L.lat.append(ops.convert_f32(w, kind))
+        plan.rec_layers.append(L)
+    plan.out = LinearDev(p["out/W"], p["out/b"], dev, split)
+
+
+# ------------------------------------------------------------------------------------------
+# schedule
+# ------------------------------------------------------------------------------------------
+class Schedule:
+    """Packed time-major schedule of a set of utterances (host arrays + device copies)."""
+
+    def __init__(self, steps, nb, n_dirs, max_groups, device):
+        steps = np.asarray(steps, dtype=np.int64)
+        n_utt = len(steps)
+        self.nb, self.n_utt = nb, n_utt
+        self.order = np.argsort(-steps, kind="stable")  # sorted position -> original utterance
+        s_sorted = steps[self.order]
+        n_batches = (n_utt + nb - 1) // nb
+        row0 = np.zeros(n_batches, np.int32)
+        bsteps = np.zeros(n_batches, np.int32)
+        bnutt = np.zeros(n_batches, np.int32)
+        boff = np.zeros(n_batches, np.int32)
+        bases, utt_rows = [], []
+        # per packed row: sorted-utterance index and step
+        row_utt, row_step = [], []
+        r = 0
+        off = 0
+        for b in range(n_batches):
+            ls = s_sorted[b * nb:(b + 1) * nb]
+            t_max = int(ls[0])
+            active = (ls[None, :] > np.arange(t_max)[:, None])  # (T, nutt)
+            n_t = active.sum(axis=1)
+            base = np.concatenate([[0], np.cumsum(n_t)]).astype(np.int32)
+            row0[b], bsteps[b], bnutt[b], boff[b] = r, t_max, len(ls), off
+            bases.append(base)
+            tt, uu = np.nonzero(active)  # time-major order, u ascending within t  == packed order
+            row_utt.append(uu + b * nb)
+            row_step.append(tt)
+            r += int(base[-1])
+            off += len(base)
+        self.n_rows = r
+        self.n_batches = n_batches
+        self.row_sorted_utt = np.concatenate(row_utt) if row_utt else np.zeros(0, np.int64)
+        self.row_step = np.concatenate(row_step) if row_step else np.zeros(0, np.int64)
+        utt_len = np.zeros(n_batches * nb, np.int32)
+        utt_len[:n_utt] = s_sorted
+        # work items, longest first, greedily assigned to the least-loaded group (LPT)
+        items = [(int(bsteps[b]), b, d) for b in range(n_batches) for d in range(n_dirs)]
+        items.sort(key=lambda t: -t[0])
+        n_groups = max(1, min(max_groups, len(items)))
+        load = [0] * n_groups
+        per_group = [[] for _ in range(n_groups)]
+        for cost, b, d in items:
+            g = int(np.argmin(load))
+            load[g] += cost
+            per_group[g].append((b, d))
+        for g in range(n_groups):  # keep a group's items direction-sorted to avoid reloading weights
+            per_group[g].sort(key=lambda t: (t[1], -int(bsteps[t[0]])))
+        flat = [it for g in per_group for it in g]
+        starts = np.concatenate([[0], np.cumsum([len(g) for g in per_group])]).astype(np.int32)
+        self.n_items, self.n_groups = len(flat), n_groups
+        self.max_group_steps = max(load) if load else 0
+        self.total_steps = int(sum(c for c, _, _ in items))
+
+        def dv(a):
+            return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
+
+        self.d_item_batch = dv([b for b, _ in flat])
+        self.d_item_dir = dv([d for _, d in flat])
+        self.d_group_start = dv(starts)
+        self.d_row0, self.d_steps, self.d_nutt, self.d_boff = dv(row0), dv(bsteps), dv(bnutt), dv(boff)
+        self.d_base = dv(np.concatenate(bases) if bases else np.zeros(1, np.int32))
+        self.d_utt_len = dv(utt_len)
+        self.d_counters = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)
+
+
+def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=None):
+    H, nd = plan.hidden, plan.n_dirs
+    d = RnnDesc()
+    d.cell, d.hidden, d.n_dirs, d.batch, d.nsplit, d.flags = plan.cell, H, nd, nb, 3 if plan.split else 1, 0
+    for k in range(nd):
+        d.gx[k] = gx.data_ptr() + 4 * k * 4 * H
+        d.w_hi[k] = layer.lat[k][0].data_ptr()
+        d.w_lo[k] = layer.lat[k][1].data_ptr() if plan.split else None
+    d.gx_ld = gx.stride(0)
+    d.w_ld = layer.lat[0][0].stride(0)
+    d.h_hi, d.h_lo, d.h_ld = h_hi.data_ptr(), (h_lo.data_ptr() if h_lo is not None else None), h_hi.stride(0)
+    d.n_items, d.item_batch, d.item_dir = sched.n_items, sched.d_item_batch.data_ptr(), sched.d_item_dir.data_ptr()
+    d.n_groups, d.group_item_start = sched.n_groups, sched.d_group_start.data_ptr()
+    d.batch_row0, d.batch_steps = sched.d_row0.data_ptr(), sched.d_steps.data_ptr()
+    d.batch_nutt, d.batch_base_off = sched.d_nutt.data_ptr(), sched.d_boff.data_ptr()
+    d.base, d.utt_len = sched.d_base.data_ptr(), sched.d_utt_len.data_ptr()
+    if h0 is not None:
+        d.h0_hi = h0[0].data_ptr()
+        d.h0_lo = h0[1].data_ptr() if h0[1] is not None else None
+    d.c0 = c0.data_ptr() if c0 is not None else None
+    d.c_out = c_out.data_ptr() if c_out is not None else None
+    d.counters = sched.d_counters.data_ptr()
+    return d
+
+
+def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_state=False, tag="rnn"):
+    """All recurrent layers on packed rows; returns (h_hi, h_lo) of the last layer and the new state."""
+    ws = plan.ws
+    H, nd = plan.hidden, plan.n_dirs
+    state_out = []
+    for l, layer in enumerate(plan.rec_layers):
+        gx = ws.get(f"{tag}.gx", rows, nd * 4 * H, torch.float32)
+        layer.upward(a_hi, a_lo, rows, "identity", OUT_F32, out=(gx, None))
+        slot = l if want_state else l % 2  # a carried state needs every layer's h kept
+        h_hi = ws.get(f"{tag}.h{slot}.hi", rows, nd * H, torch.bfloat16)
+        h_lo = ws.get(f"{tag}.h{slot}.lo", rows, nd * H, torch.bfloat16) if plan.split else None
+        h0 = c0 = c_out = None
+        if state_in is not None:
+            h0, c0 = state_in[l]
+        if want_state:
+            c_out = torch.zeros((sched.n_batches * nb, nd * H), dtype=torch.float32, device=plan.device)
+        desc = _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0, c0, c_out)
+        ops.rnn_seq(desc, 2.0 * rows * nd * 4 * H * H)
+        if want_state:
+            state_out.append(((h_hi, h_lo), c_out))
+        a_hi, a_lo = h_hi, h_lo
+    return a_hi, a_lo, state_out
+
+
+def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, timedelay=0, device=0, head=None,
+                       fix_timedelay_tail=False, nb=DEFAULT_BATCH):
+    """Recurrent hot path on ONE device for utterances [u0, u1) (predict_folds.py:28-68 semantics).
+
+    x / ivectors: (N, dim) / (N, I) float32, host arrays or CUDA tensors; out: (N, C) float32 host array or CUDA
+    tensor, rows [offsets[u0], offsets[u1]) are written.  Output frame f of an utterance is the network output at
+    step f + timedelay; like the reference, the last ``timedelay`` frames stay 0 unless fix_timedelay_tail.
+    """
+    device = _device(device)
+    head = head or HeadSpec()
+    offsets = np.asarray(offsets, dtype=np.int64)
+    if u1 <= u0:
+        return out
+    f_lo, f_hi = int(offsets[u0]), int(offsets[u1])
+    lens = (offsets[u0 + 1:u1 + 1] - offsets[u0:u1]).astype(np.int64)
+    if np.any(lens <= 0):
+        raise NnamError("forward_utterances: empty utterance in offsets")
+    with torch.cuda.device(device):
+        plan = get_plan(model, device)
+        ws = plan.ws
+        split = plan.split
+        g_ctas, max_groups = ops.rnn_plan(plan.cell, plan.hidden, nb, 3 if split else 1)
+        sched = Schedule(lens + timedelay, nb, plan.n_dirs, max_groups, device)
+        rows = sched.n_rows
+        # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1)
+        utt = sched.order[sched.row_sorted_utt]  # original utterance (shard-relative)
+        step = sched.row_step
+        l_row = lens[utt]
+        start = offsets[u0:u1][utt] - f_lo
+        src = start + np.minimum(step, l_row - 1)
+        dst = start + step - timedelay
+        keep = step >= timedelay
+        if not fix_timedelay_tail:
+            keep &= step < l_row  # predict_folds.py:50,60-61: rows are written only while utt_len > t (quirk Q4)
+        dst = np.where(keep, dst, -1)
+        d_src = torch.from_numpy(src.astype(np.int32)).to(device)
+        d_dst = torch.from_numpy(dst.astype(np.int32)).to(device)
+
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            x_dev = x[f_lo:f_hi]
+        else:
+            x_dev = ws.get("rnn.x", f_hi - f_lo, x.shape[1], torch.float32)
+            x_dev.copy_(_as_host_tensor(x)[f_lo:f_hi], non_blocking=True)
+        iv_dev = None
+        if ivectors is not None:
+            if isinstance(ivectors, torch.Tensor) and ivectors.is_cuda:
+                iv_dev = ivectors[f_lo:f_hi]
+            else:
+                iv_dev = ws.get("rnn.iv", f_hi - f_lo, ivectors.shape[1], torch.float32)
+                iv_dev.copy_(_as_host_tensor(ivectors)[f_lo:f_hi], non_blocking=True)
+        add = mul = None
+        if ft is not None:
+            add, mul = _dev_vec(ft["addShift"], device), _dev_vec(ft["rescale"], device)
+            if add.numel() != x.shape[1]:
+                raise NnamError("forward_utterances: recurrent nets take the shift-0 transform block (adapt_transform)")
+        d_in = model.in_size
+        if d_in != x.shape[1] + (0 if ivectors is None else ivectors.shape[1]):
+            raise NnamError(f"forward_utterances: model expects {d_in} inputs, data provides "
+                            f"{x.shape[1] + (0 if ivectors is None else ivectors.shape[1])}")
+        ld_in = round_up(d_in, 8)
+        a_hi = ws.get("rnn.a.hi", rows, ld_in, torch.bfloat16)
+        a_lo = ws.get("rnn.a.lo", rows, ld_in, torch.bfloat16) if split else None
+        ops.gather_transform(x_dev, d_src, add, mul, iv_dev, out_kind=plan.act_kind, ldo=ld_in, out=(a_hi, a_lo))
+        h_hi, h_lo, _ = run_layers(model, plan, sched, a_hi, a_lo, rows, nb)
+        n_out = model.n_out
+        logits = ws.get("rnn.logits", rows, round_up(n_out, 16), torch.float32)
+        plan.out(h_hi, h_lo, rows, "identity", OUT_F32, out=(logits, None))
+        on_dev = isinstance(out, torch.Tensor) and out.is_cuda
+        out_dev = out[f_lo:f_hi] if on_dev else ws.get("rnn.out", f_hi - f_lo, n_out, torch.float32)
+        out_dev.zero_()
+        prior = _dev_vec(head.prior, device)
+        rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
+        ops.head(logits, n_out, rows=rows, rpl=rpl, prior=prior, prior_scale=head.prior_scale,
+                 final_normalize=head.final_normalize, out=out_dev, out_row_map=d_dst)
+        if not on_dev:
+            _as_host_tensor(out)[f_lo:f_hi].copy_(out_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    return out
+
+
+def step(model, plan, xd):
+    """Stateful ``model(x)`` for recurrent specs: one time step for a batch of B rows
+    (chainer_networks.py:58-62); ``reset_state()`` clears the carried (h, c)."""
+    B = xd.shape[0]
+    nb = DEFAULT_BATCH
+    split = plan.split
+    if model.bidirectional:
+        raise NnamError("bidirectional models have no per-step form; use predict()/forward_utterances()")
+    g_ctas, max_groups = ops.rnn_plan(plan.cell, plan.hidden, nb, 3 if split else 1)
+    st = model._state
+    if st is not None and st["B"] != B:
+        raise NnamError("model(x): batch size changed between steps; call reset_state() first")
+    sched = st["sched"] if st is not None else Schedule(np.ones(B, np.int64), nb, 1, max_groups, plan.device)
+    a_hi, a_lo = ops.convert_f32(xd.contiguous(), plan.act_kind)
+    h_hi, h_lo, new = run_layers(model, plan, sched, a_hi, a_lo, B, nb, state_in=None if st is None else st["s"],
+                                 want_state=True, tag="step")
+    # carry state: all lengths are 1 and the sort is stable, so packed rows == sorted order == input order.
+    # The h buffers are workspace memory that the next call overwrites while reading -> keep private copies.
+    new_state = [((hh.clone(), None if hl is None else hl.clone()), c) for (hh, hl), c in new]
+    model._state = {"B": B, "sched": sched, "s": new_state}
+    logits = plan.ws.get("step.logits", B, round_up(model.n_out, 16), torch.float32)
+    plan.out(h_hi, h_lo, B, "identity", OUT_F32, out=(logits, None))
+    return logits[:B, :model.n_out].clone()

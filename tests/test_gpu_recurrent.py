@@ -1,0 +1,125 @@
+"""Recurrent path (K3 + schedule) against the oracle.  -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import nnam_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def nn():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import nnacousticmodeling_b200 as _nn
+    return _nn
+
+
+def _lstm(nn, seed, network, in_dim, units, layers, n_out, precision="fp32", bidirectional=False):
+    p = O.init_recurrent(np.random.default_rng(seed), "lstm" if network == "blstm" else network, in_dim, units, layers,
+                         n_out, bidirectional=bidirectional)
+    rng = np.random.default_rng(seed + 100)
+    for k in p:
+        if k.endswith("upward/b") or k == "out/b":
+            p[k] = p[k] + (0.1 * rng.standard_normal(p[k].shape)).astype(np.float32)
+    m = nn.get_nn(network, layers, [units], n_out, nn.F.relu, [5])
+    m.load_params(p)
+    m.precision = precision
+    return m, p
+
+
+def _offsets(lens):
+    return np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+
+
+@pytest.mark.parametrize("units,layers,lens,td", [
+    (64, 1, [5], 0),
+    (64, 2, [7, 3, 12, 1, 9], 0),
+    (128, 2, [30, 41, 17, 25, 33, 8] * 7, 3),   # 42 utterances: more than one batch of 32
+    (512, 4, [90, 120, 75, 101], 5),            # BASELINE config 3 geometry (40 -> 4x512 -> 1909), timedelay 5
+])
+def test_predict_lstm_fp32_mode(nn, golden_dir, units, layers, lens, td):
+    off = _offsets(lens)
+    rng = np.random.default_rng(sum(lens))
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    n_out = 1909 if units == 512 else 39
+    m, p = _lstm(nn, units + layers, "lstm", 40, units, layers, n_out)
+    ft = nn.adapt_transform(nn.loadKaldiFeatureTransform(os.path.join(golden_dir, "final.feature_transform")),
+                            "lstm", 0, True)
+    want = O.predict(O.RecurrentNet(p, "lstm", layers), x, off, "lstm", 1, td, ft)
+    got = nn.predict(m, x, off, n_out, "lstm", 0, 1, td, ft, progress=False)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 1e-3
+    if td:
+        for u in range(len(lens)):  # quirk Q4: the reference leaves the last `timedelay` frames at 0
+            assert np.all(got[off[u + 1] - min(td, lens[u]):off[u + 1]] == 0)
+        fixed = nn.predict(m, x, off, n_out, "lstm", 0, 1, td, ft, progress=False, fix_timedelay_tail=True)
+        assert np.all(np.abs(fixed).sum(axis=1) > 0)
+
+
+def test_predict_lstm_bf16_mode(nn):
+    lens = [60, 85, 44, 70, 52, 66, 91, 38]
+    off = _offsets(lens)
+    x = np.random.default_rng(1).standard_normal((off[-1], 40)).astype(np.float32)
+    m, p = _lstm(nn, 3, "lstm", 40, 512, 4, 1909, precision="bf16")
+    want = O.predict(O.RecurrentNet(p, "lstm", 4), x, off, "lstm", 1, 0, None)
+    got = nn.predict(m, x, off, 1909, "lstm", 0, 1, 0, None, progress=False)
+    assert np.abs(got - want).max() < 5e-2
+    rows = np.arange(len(want))
+    assert np.mean(want[rows, got.argmax(axis=1)] >= want.max(axis=1) - 1e-2) >= 0.995
+
+
+def test_zoneout_lstm_is_lstm_arithmetic(nn):
+    lens = [9, 4, 6]
+    off = _offsets(lens)
+    x = np.random.default_rng(2).standard_normal((off[-1], 40)).astype(np.float32)
+    m, p = _lstm(nn, 4, "zoneoutlstm", 40, 64, 2, 39)
+    want = O.predict(O.RecurrentNet(p, "zoneoutlstm", 2), x, off, "zoneoutlstm", 1, 0, None)
+    got = nn.predict(m, x, off, 39, "zoneoutlstm", 0, 1, 0, None, progress=False)
+    assert np.abs(got - want).max() < 1e-3
+
+
+def test_blstm_with_ivectors(nn, golden_dir):
+    """BASELINE config 4 geometry at small scale: bidirectional LSTM on 40 fMLLR + 100 i-vector."""
+    lens = [33, 20, 41, 12, 27]
+    off = _offsets(lens)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    iv = np.repeat((0.5 * rng.standard_normal((len(lens), 100))).astype(np.float32), lens, axis=0)
+    m, p = _lstm(nn, 6, "blstm", 140, 128, 2, 1909, bidirectional=True)
+    ft = nn.adapt_transform(nn.loadKaldiFeatureTransform(os.path.join(golden_dir, "final.feature_transform")),
+                            "blstm", 0, True)
+    feats = np.concatenate((O.apply_kaldi_feature_transform(x, ft), iv), axis=1)
+    want = np.concatenate([O.log_softmax(O.birnn_forward_utterance(p, "lstm", 2, feats[off[u]:off[u + 1]]))
+                           for u in range(len(lens))])
+    got = nn.predict(m, x, off, 1909, "blstm", 0, 1, 0, ft, progress=False, ivectors=iv)
+    assert np.abs(got - want).max() < 1e-3
+
+
+def test_stateful_call_and_reset(nn):
+    m, p = _lstm(nn, 7, "lstm", 40, 64, 3, 39)
+    ref = O.RecurrentNet(p, "lstm", 3)
+    rng = np.random.default_rng(8)
+    xs = rng.standard_normal((6, 5, 40)).astype(np.float32)
+    m.reset_state()
+    for t in range(6):
+        assert np.abs(m(xs[t]) - ref(xs[t])).max() < 1e-3
+    m.reset_state()
+    ref.reset_state()
+    assert np.abs(m(xs[0]) - ref(xs[0])).max() < 1e-3
+
+
+def test_multi_shard_equals_single(nn):
+    from nnacousticmodeling_b200 import recurrent_engine
+    lens = [15, 22, 9, 31, 18, 12, 27, 20, 11]
+    off = _offsets(lens)
+    x = np.random.default_rng(9).standard_normal((off[-1], 40)).astype(np.float32)
+    m, p = _lstm(nn, 10, "lstm", 40, 64, 2, 39)
+    full = nn.predict(m, x, off, 39, "lstm", 0, 1, 2, None, progress=False)
+    parts = np.zeros_like(full)
+    for u0, u1 in nn.partition_utterances(off, 3):
+        recurrent_engine.forward_utterances(m, x, off, parts, u0, u1, timedelay=2, device=0)
+    assert np.array_equal(full, parts)

@@ -1,0 +1,37 @@
+"""The packed time-major schedule of the recurrent path (host logic, runs on CPU)."""
+import numpy as np
+import torch
+
+from nnacousticmodeling_b200.recurrent_engine import Schedule
+
+
+def test_schedule_covers_every_utterance_step_once():
+    rng = np.random.default_rng(0)
+    steps = rng.integers(1, 40, size=77)
+    s = Schedule(steps, 32, 2, 4, torch.device("cpu"))
+    assert s.n_rows == steps.sum() and s.n_batches == 3
+    utt = s.order[s.row_sorted_utt]
+    seen = set(zip(utt.tolist(), s.row_step.tolist()))
+    assert len(seen) == s.n_rows
+    assert seen == {(u, t) for u in range(77) for t in range(steps[u])}
+    # device tables reproduce row(t, u) = row0 + base[t] + u
+    row0, boff = s.d_row0.numpy(), s.d_boff.numpy()
+    base, ulen = s.d_base.numpy(), s.d_utt_len.numpy()
+    for r in rng.integers(0, s.n_rows, size=200):
+        su, t = int(s.row_sorted_utt[r]), int(s.row_step[r])
+        b, u = divmod(su, 32)
+        assert row0[b] + base[boff[b] + t] + u == r
+        assert ulen[su] == steps[s.order[su]] > t
+    # every (batch, direction) item is scheduled exactly once, groups are balanced by LPT
+    items = sorted(zip(s.d_item_batch.tolist(), s.d_item_dir.tolist()))
+    assert items == [(b, d) for b in range(3) for d in range(2)]
+    gs = s.d_group_start.tolist()
+    assert gs[0] == 0 and gs[-1] == 6 and len(gs) == s.n_groups + 1
+
+
+def test_schedule_single_and_equal_lengths():
+    s = Schedule([5], 32, 1, 9, torch.device("cpu"))
+    assert s.n_rows == 5 and s.n_groups == 1 and s.d_base.tolist() == [0, 1, 2, 3, 4, 5]
+    s = Schedule([1] * 40, 32, 1, 9, torch.device("cpu"))
+    assert s.n_rows == 40 and np.array_equal(s.order, np.arange(40))  # stable sort keeps input order
+    assert s.d_row0.tolist() == [0, 32]
