@@ -125,7 +125,7 @@ typedef struct NnamRnnDesc {
   int cell;    /* NNAM_CELL_* */
   int hidden;  /* H (multiple of 64) */
   int n_dirs;  /* 1, or 2 = bidirectional: direction 1 walks every utterance backwards */
-  int batch;   /* utterances per batch: 16, 32 or 64 */
+  int batch;   /* utterances per batch: 32 or 64 */
   int nsplit;  /* 1 = bf16 operands, 3 = bf16x3 (needs the _lo buffers) */
   int flags;   /* GRU family: bit 0 = reset gate, bits 1-2 = candidate activation (NNAM_ACT_*) */
   const float* gx[2];  /* per direction: input projection + bias for every packed row, (rows, gx_ld) fp32,
@@ -154,6 +154,7 @@ typedef struct NnamRnnDesc {
   const float* c0;             /* optional initial cell state (n_utts, H*n_dirs) fp32 */
   float* c_out;                /* optional final cell state, same shape */
   unsigned int* counters;      /* n_groups words of scratch */
+  void* debug_cycles;          /* optional: int64[8] per CTA, per-phase SM cycle totals (profiling builds/tests) */
 } NnamRnnDesc;
 
 int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream);

@@ -46,15 +46,31 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA translation unit for sm_100a into ``libnnam_b200.so`` (in-tree)."""
+    """Compile every CUDA translation unit for sm_100a into ``libnnam_b200.so`` (in-tree).
+    Objects are compiled in parallel (one nvcc per .cu) and linked with ``nvcc -shared``."""
     if not force and not needs_build():
         return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(PKG_DIR, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [_nvcc()] + flags + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise NnamError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+        objs = list(pool.map(compile_one, _sources()))
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
-        raise NnamError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise NnamError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 
@@ -99,7 +115,7 @@ class RnnDesc(ctypes.Structure):
         ("batch_row0", c_void_p), ("batch_steps", c_void_p), ("batch_nutt", c_void_p), ("batch_base_off", c_void_p),
         ("base", c_void_p), ("utt_len", c_void_p),
         ("h0_hi", c_void_p), ("h0_lo", c_void_p), ("c0", c_void_p), ("c_out", c_void_p),
-        ("counters", c_void_p),
+        ("counters", c_void_p), ("debug_cycles", c_void_p),
     ]
 
 

@@ -27,7 +27,7 @@
 
 namespace nnam {
 
-constexpr int RNN_THREADS = 128;
+constexpr int RNN_THREADS = 256;
 
 struct RnnTmaps {
   CUtensorMap w_hi[2];
@@ -59,6 +59,7 @@ struct RnnParams {
   float* c_out;                // optional final cell state, same shape
   unsigned int* counters;      // one per group, zero on entry
   int gru_flags;
+  long long* prof;             // optional: 8 cycle accumulators per CTA (thread 0), phases of a step
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -79,6 +80,13 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+constexpr int RNN_BASE_SMEM = 2048;  // steps of a batch whose prefix-sum table is mirrored in shared memory
 
 // 4x4 transpose inside a lane quad: on entry thread k of the quad holds x[i] = (gate k, utterance i); on exit it
 // holds x[g] = (gate g, utterance k).
@@ -104,7 +112,9 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c16) {
   return static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
 }
 
-template <int M_ROWS, int NB, int NSPLIT, bool FAST_TANH>
+// KBT: compile-time number of 64-element k-blocks (H / 64) so that the MMA issue loop fully unrolls with
+// immediate descriptor offsets; KBT = 0 selects the generic runtime-H variant.
+template <int M_ROWS, int NB, int NSPLIT, bool FAST_TANH, int KBT>
 __global__ void __launch_bounds__(RNN_THREADS, 1)
     lstm_seq_kernel(const __grid_constant__ RnnTmaps tmaps, const RnnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -112,10 +122,11 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
   const int rank = blockIdx.x % p.group_ctas;
   if (group >= p.n_groups) return;
 
-  const int H = p.hidden;
-  const int KB = H >> 6;  // 64-element k-blocks
+  const int H = KBT > 0 ? KBT * 64 : p.hidden;
+  const int KB = KBT > 0 ? KBT : (H >> 6);  // 64-element k-blocks
   constexpr int W_BLOCK = M_ROWS * 128;
   constexpr int H_BLOCK = NB * 128;
+  constexpr int NBH = NB / 2;  // utterance slots per thread: warps 0-3 own slots [0, NBH), warps 4-7 [NBH, NB)
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* w_hi_s = smem;
@@ -127,10 +138,14 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
   uint64_t* bar_mma = bar_w + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
   int* s_len = reinterpret_cast<int*>(tmem_slot + 2);  // NB ints
+  int* s_base = s_len + NB;                            // RNN_BASE_SMEM + 1 ints
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+  const int half = warp >> 2;    // which half of the utterance slots (TMEM columns) this warp owns
+  const int u_lo = half * NBH;
   constexpr int TMEM_COLS = NB < 32 ? 32 : NB;
 
   if (tid == 0) {
@@ -147,16 +162,20 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // TMEM lane <-> gate row of this CTA's slice.  M_ROWS = 128: lane = tid.  M_ROWS = 64: rows 16q..16q+15 sit in
-  // lanes 32q..32q+15 (the upper half of every subpartition is unused).
+  // TMEM lane <-> gate row of this CTA's slice.  M_ROWS = 128: lane index = row.  M_ROWS = 64: rows 16q..16q+15
+  // sit in lanes 32q..32q+15 (the upper half of every subpartition is unused).
   const bool row_valid = (M_ROWS == 128) || (lane < 16);
-  const int my_row = (M_ROWS == 128) ? tid : (warp * 16 + (lane & 15));
-  const int gate = my_row & 3;                        // a, i, f, o
+  const int my_row = (M_ROWS == 128) ? (quarter * 32 + lane) : (quarter * 16 + (lane & 15));
+  const int gate = my_row & 3;                           // a, i, f, o
   const int unit = rank * (M_ROWS / 4) + (my_row >> 2);  // hidden unit index in [0, H)
-  const int gate_col = rank * M_ROWS + my_row;        // column of gx / row of W_lat
-  const uint32_t tmem_lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const int gate_col = rank * M_ROWS + my_row;           // column of gx / row of W_lat
+  const uint32_t tmem_lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + u_lo;
   const uint32_t idesc = make_idesc_bf16_f32(M_ROWS, NB);
 
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_t = 0;
+#define PROF_START() do { if (p.prof != nullptr && tid == 0) prof_t = clock64(); } while (0)
+#define PROF_MARK(i) do { if (p.prof != nullptr && tid == 0) { const long long now = clock64(); prof_acc[i] += now - prof_t; prof_t = now; } } while (0)
   unsigned int steps_done = 0;
   uint32_t w_phase = 0, mma_phase = 0;
   int cur_dir = -1;
@@ -184,17 +203,21 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
     const int nutt = p.batch_nutt[b];
     const int* base = p.base + p.batch_base_off[b];
     const int* len = p.utt_len + b * NB;
-    const float* gx = p.gx[d];
+    const float* gx = p.gx[d] + gate_col;
     const int h_col0 = d * H;
-    __syncthreads();  // previous item's readers of s_len are done
+    __syncthreads();  // previous item's readers of s_len / s_base are done
     if (tid < NB) s_len[tid] = tid < nutt ? len[tid] : 0;
+    const bool base_in_smem = T <= RNN_BASE_SMEM;
+    if (base_in_smem)
+      for (int i = tid; i <= T; i += RNN_THREADS) s_base[i] = __ldg(base + i);
     __syncthreads();
+    const int* bp = base_in_smem ? s_base : base;  // prefix sums: shared-memory mirror when it fits
 
-    // cell state of (utterance 4m + gate, unit) lives in this thread for the whole item
-    float c_reg[NB / 4];
+    // cell state of (utterance u_lo + 4m + gate, unit) lives in this thread for the whole item
+    float c_reg[NBH / 4];
 #pragma unroll
-    for (int m = 0; m < NB / 4; ++m) {
-      const int u = 4 * m + gate;
+    for (int m = 0; m < NBH / 4; ++m) {
+      const int u = u_lo + 4 * m + gate;
       c_reg[m] = (p.c0 != nullptr && row_valid && u < nutt)
                      ? p.c0[(static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0 + unit]
                      : 0.0f;
@@ -202,22 +225,23 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
     const bool has_h0 = p.h0_hi != nullptr;
 
     for (int s = 0; s < T; ++s) {
-      const int base_s = __ldg(base + s);
-      const int n_s = __ldg(base + s + 1) - base_s;  // active utterances (prefix of the batch)
+      PROF_START();
+      const int base_s = bp[s];
+      const int n_s = bp[s + 1] - base_s;  // active utterances (prefix of the batch), >= 1
 
-      // ---- prefetch the input projection of my gate row for every active utterance
-      float gxr[NB];
+      // ---- prefetch the input projection of my gate row for my utterance slots: independent loads
+      // (slots beyond n_s re-read the last active row, so no load is predicated or dependent on another)
+      float gxr[NBH];
 #pragma unroll
-      for (int u = 0; u < NB; ++u) {
-        gxr[u] = 0.0f;
-        if (u < n_s) {
-          const long long row = row0 + (bwd ? __ldg(base + (s_len[u] - 1 - s)) : base_s) + u;
-          if (row_valid) gxr[u] = __ldg(gx + row * p.gx_ld + gate_col);
-        }
+      for (int j = 0; j < NBH; ++j) {
+        const int u = u_lo + j;
+        const int uu = u < n_s ? u : n_s - 1;
+        const long long row = row0 + (bwd ? bp[s_len[uu] - 1 - s] : base_s) + uu;
+        gxr[j] = __ldg(gx + row * p.gx_ld);
       }
-
+      PROF_MARK(0);  // gx prefetch issue
       const bool do_mma = (s > 0) || has_h0;
-      float acc[NB];
+      float acc[NBH];
       if (do_mma) {
         if (s > 0) {
           if (tid == 0) {
@@ -227,42 +251,63 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
           }
           __syncthreads();
         }
-        // ---- h_{s-1} rows of the active utterances -> swizzled smem (B operand)
+        PROF_MARK(1);  // wait for the group
+        // ---- h_{s-1} rows of the active utterances -> swizzled smem (B operand): one warp per row, 16-byte
+        // cp.async chunks, all in flight at once
         const int chunks_per_row = H >> 3;
-        const int prev_base = s > 0 ? (bwd ? 0 : __ldg(base + s - 1)) : 0;
-        for (int idx = tid; idx < n_s * chunks_per_row; idx += RNN_THREADS) {
-          const int u = idx / chunks_per_row;
-          const int c = idx - u * chunks_per_row;
-          const __nv_bfloat16 *src_hi, *src_lo = nullptr;
+        const uint32_t h_hi_sa = smem_u32(h_hi_s), h_lo_sa = smem_u32(h_lo_s);
+        for (int u = warp; u < n_s; u += RNN_THREADS / 32) {
+          long long off;
+          const __nv_bfloat16 *src_hi, *src_lo;
           if (s == 0) {
-            const long long off = (static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0 + c * 8;
-            src_hi = p.h0_hi + off;
-            if (NSPLIT == 3) src_lo = p.h0_lo + off;
+            off = (static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0;
+            src_hi = p.h0_hi;
+            src_lo = p.h0_lo;
           } else {
-            const long long row = row0 + (bwd ? __ldg(base + (s_len[u] - s)) : prev_base) + u;
-            const long long off = row * p.h_ld + h_col0 + c * 8;
-            src_hi = p.h_hi + off;
-            if (NSPLIT == 3) src_lo = p.h_lo + off;
+            off = (row0 + bp[bwd ? (s_len[u] - s) : (s - 1)] + u) * p.h_ld + h_col0;
+            src_hi = p.h_hi;
+            src_lo = p.h_lo;
           }
-          const uint32_t so = static_cast<uint32_t>((c >> 3) * H_BLOCK) + sw128_offset(u, c & 7);
-          *reinterpret_cast<uint4*>(h_hi_s + so) = __ldcg(reinterpret_cast<const uint4*>(src_hi));
-          if (NSPLIT == 3) *reinterpret_cast<uint4*>(h_lo_s + so) = __ldcg(reinterpret_cast<const uint4*>(src_lo));
+          const uint32_t row_so = static_cast<uint32_t>((u >> 3) * 1024 + (u & 7) * 128);
+          for (int c = lane; c < chunks_per_row; c += 32) {
+            const uint32_t so = static_cast<uint32_t>((c >> 3) * H_BLOCK) + row_so + (((c & 7) ^ (u & 7)) << 4);
+            cp_async_16(h_hi_sa + so, src_hi + off + c * 8);
+            if (NSPLIT == 3) cp_async_16(h_lo_sa + so, src_lo + off + c * 8);
+          }
         }
+        cp_async_wait_all();
         fence_proxy_async_smem();
         __syncthreads();
+        PROF_MARK(2);  // h load
         if (tid == 0) {
           tc_fence_after();
+          const uint64_t wd_hi = make_sw128_kmajor_desc(smem_u32(w_hi_s));
+          const uint64_t wd_lo = make_sw128_kmajor_desc(smem_u32(w_lo_s));
+          const uint64_t hd_hi = make_sw128_kmajor_desc(smem_u32(h_hi_s));
+          const uint64_t hd_lo = make_sw128_kmajor_desc(smem_u32(h_lo_s));
           uint32_t accum = 0;
-#pragma unroll 1
-          for (int pass = 0; pass < NSPLIT; ++pass) {
-            const uint32_t wa = smem_u32(pass == 2 ? w_lo_s : w_hi_s);
-            const uint32_t ha = smem_u32(pass == 1 ? h_lo_s : h_hi_s);
-            for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16(tmem_base, make_sw128_kmajor_desc(wa + kb * W_BLOCK + k * 32),
-                          make_sw128_kmajor_desc(ha + kb * H_BLOCK + k * 32), idesc, accum);
-                accum = 1;
+          for (int pass = 0; pass < NSPLIT; ++pass) {
+            const uint64_t wa = pass == 2 ? wd_lo : wd_hi;
+            const uint64_t ha = pass == 1 ? hd_lo : hd_hi;
+            if (KBT > 0) {
+#pragma unroll
+              for (int kb = 0; kb < KBT; ++kb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc,
+                            accum);
+                  accum = 1;
+                }
+              }
+            } else {
+              for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc,
+                            accum);
+                  accum = 1;
+                }
               }
             }
           }
@@ -271,8 +316,9 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
         mbar_wait(bar_mma, mma_phase);
         mma_phase ^= 1;
         tc_fence_after();
+        PROF_MARK(3);  // MMA issue + completion
 #pragma unroll
-        for (int c0 = 0; c0 < NB; c0 += 16) {
+        for (int c0 = 0; c0 < NBH; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(tmem_lane_addr + c0, r);
           tmem_ld_wait();
@@ -280,15 +326,16 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
           for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(r[j]);
         }
         tc_fence_before();
+        PROF_MARK(4);  // TMEM -> registers
       } else {
 #pragma unroll
-        for (int u = 0; u < NB; ++u) acc[u] = 0.0f;
+        for (int j = 0; j < NBH; ++j) acc[j] = 0.0f;
       }
 
       // ---- gates, quad transpose, cell update, write h
 #pragma unroll
-      for (int m = 0; m < NB / 4; ++m) {
-        if (4 * m >= n_s) break;  // warp-uniform
+      for (int m = 0; m < NBH / 4; ++m) {
+        if (u_lo + 4 * m >= n_s) break;  // warp-uniform
         float x[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -296,29 +343,36 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
           const float t = tanh_sel<FAST_TANH>(gate == 0 ? v : 0.5f * v);
           x[i] = gate == 0 ? t : fmaf(t, 0.5f, 0.5f);
         }
-        quad_transpose(x, gate);  // x = {a, i, f, o} of utterance u = 4m + gate
-        const int u = 4 * m + gate;
+        quad_transpose(x, gate);  // x = {a, i, f, o} of utterance u = u_lo + 4m + gate
+        const int u = u_lo + 4 * m + gate;
         const float c_new = fmaf(x[0], x[1], x[2] * c_reg[m]);
         const float h_new = x[3] * tanh_sel<FAST_TANH>(c_new);
         if (row_valid && u < n_s) {
           c_reg[m] = c_new;
           const int t_idx = bwd ? (s_len[u] - 1 - s) : s;
-          const long long row = row0 + __ldg(base + t_idx) + u;
-          const long long off = row * p.h_ld + h_col0 + unit;
+          const long long off = (row0 + bp[t_idx] + u) * p.h_ld + h_col0 + unit;
           const __nv_bfloat16 hb = __float2bfloat16_rn(h_new);
           p.h_hi[off] = hb;
-          if (p.h_lo != nullptr) p.h_lo[off] = __float2bfloat16_rn(h_new - __bfloat162float(hb));
+          if (NSPLIT == 3) p.h_lo[off] = __float2bfloat16_rn(h_new - __bfloat162float(hb));
           if (p.c_out != nullptr && s == s_len[u] - 1)
             p.c_out[(static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0 + unit] = c_new;
         }
       }
+      PROF_MARK(5);  // gates, cell update, h stores
       __threadfence();
       __syncthreads();
       if (tid == 0) red_release_gpu_add(counter, 1u);
+      PROF_MARK(6);  // fence + publish
       ++steps_done;
     }
   }
 
+  if (p.prof != nullptr && tid == 0) {
+    prof_acc[7] = steps_done;
+    for (int i = 0; i < 8; ++i) p.prof[blockIdx.x * 8 + i] = prof_acc[i];
+  }
+#undef PROF_START
+#undef PROF_MARK
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -328,9 +382,9 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------ host side
-template <int M_ROWS, int NB, int NSPLIT, bool FAST>
+template <int M_ROWS, int NB, int NSPLIT, bool FAST, int KBT>
 static int launch_lstm(const RnnTmaps& tm, const RnnParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = lstm_seq_kernel<M_ROWS, NB, NSPLIT, FAST>;
+  auto kern = lstm_seq_kernel<M_ROWS, NB, NSPLIT, FAST, KBT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaFuncSetAttribute");
   void* args[] = {const_cast<RnnTmaps*>(&tm), const_cast<RnnParams*>(&p)};
@@ -343,7 +397,8 @@ static int launch_lstm(const RnnTmaps& tm, const RnnParams& p, int grid, size_t 
 size_t rnn_smem_bytes(int m_rows, int nb, int hidden, int nsplit) {
   const size_t kb = hidden / 64;
   const size_t mult = nsplit == 3 ? 2 : 1;
-  return kb * (static_cast<size_t>(m_rows) * 128 + static_cast<size_t>(nb) * 128) * mult + 64 + nb * 4 + 1024;
+  return kb * (static_cast<size_t>(m_rows) * 128 + static_cast<size_t>(nb) * 128) * mult + 64 + nb * 4 +
+         (RNN_BASE_SMEM + 1) * 4 + 1024;
 }
 
 // Pick the CTA slice height: 128 gate rows when the weights fit in shared memory, else 64.
@@ -361,8 +416,7 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   const int H = d->hidden;
   if (H <= 0 || H % 64) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: hidden size must be a multiple of 64 (got %d)", H);
   if (d->n_dirs != 1 && d->n_dirs != 2) return set_error(NNAM_ERR_ARG, "rnn: n_dirs must be 1 or 2");
-  if (d->batch != 16 && d->batch != 32 && d->batch != 64)
-    return set_error(NNAM_ERR_ARG, "rnn: batch must be 16, 32 or 64");
+  if (d->batch != 32 && d->batch != 64) return set_error(NNAM_ERR_ARG, "rnn: batch must be 32 or 64");
   if (d->nsplit != 1 && d->nsplit != 3) return set_error(NNAM_ERR_ARG, "rnn: nsplit must be 1 or 3");
   if (d->n_items <= 0) return NNAM_OK;
   if (d->nsplit == 3 && (d->h_lo == nullptr)) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs h_lo");
@@ -421,6 +475,7 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   p.c_out = d->c_out;
   p.counters = d->counters;
   p.gru_flags = d->flags;
+  p.prof = static_cast<long long*>(d->debug_cycles);
   if (p.h0_hi && d->nsplit == 3 && !p.h0_lo) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs h0_lo with h0_hi");
 
   cudaError_t e = cudaMemsetAsync(d->counters, 0, sizeof(unsigned int) * d->n_groups, stream);
@@ -429,21 +484,26 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   const size_t smem = rnn_smem_bytes(m_rows, d->batch, H, d->nsplit);
   const bool fast = d->nsplit == 1;  // bf16 mode: MUFU tanh; fp32-accurate mode: tanhf
 
-#define NNAM_RNN_CASE(M, NBV, NS, F)                                   \
-  if (m_rows == M && d->batch == NBV && d->nsplit == NS && fast == F)  \
-  return launch_lstm<M, NBV, NS, F>(tm, p, grid, smem, stream)
-  NNAM_RNN_CASE(128, 16, 1, true);
-  NNAM_RNN_CASE(128, 32, 1, true);
-  NNAM_RNN_CASE(128, 64, 1, true);
-  NNAM_RNN_CASE(64, 16, 1, true);
-  NNAM_RNN_CASE(64, 32, 1, true);
-  NNAM_RNN_CASE(64, 64, 1, true);
-  NNAM_RNN_CASE(128, 16, 3, false);
-  NNAM_RNN_CASE(128, 32, 3, false);
-  NNAM_RNN_CASE(128, 64, 3, false);
-  NNAM_RNN_CASE(64, 16, 3, false);
-  NNAM_RNN_CASE(64, 32, 3, false);
-  NNAM_RNN_CASE(64, 64, 3, false);
+  const int kbt = H / 64;
+#define NNAM_RNN_CASE(M, NBV, NS, F, KBTV)                                                                 \
+  if (m_rows == M && d->batch == NBV && d->nsplit == NS && fast == F && (KBTV == 0 || KBTV == kbt))      \
+  return launch_lstm<M, NBV, NS, F, KBTV>(tm, p, grid, smem, stream)
+  // tuned instances (compile-time H): the BASELINE geometries
+  NNAM_RNN_CASE(128, 32, 1, true, 8);   // H = 512, bf16
+  NNAM_RNN_CASE(128, 64, 1, true, 8);
+  NNAM_RNN_CASE(64, 32, 3, false, 8);   // H = 512, bf16x3
+  NNAM_RNN_CASE(64, 32, 1, true, 16);   // H = 1024, bf16
+  NNAM_RNN_CASE(128, 32, 1, true, 4);   // H = 256
+  NNAM_RNN_CASE(128, 32, 3, false, 4);
+  // generic instances (runtime H)
+  NNAM_RNN_CASE(128, 32, 1, true, 0);
+  NNAM_RNN_CASE(128, 64, 1, true, 0);
+  NNAM_RNN_CASE(64, 32, 1, true, 0);
+  NNAM_RNN_CASE(64, 64, 1, true, 0);
+  NNAM_RNN_CASE(128, 32, 3, false, 0);
+  NNAM_RNN_CASE(128, 64, 3, false, 0);
+  NNAM_RNN_CASE(64, 32, 3, false, 0);
+  NNAM_RNN_CASE(64, 64, 3, false, 0);
 #undef NNAM_RNN_CASE
   return set_error(NNAM_ERR_UNSUPPORTED, "rnn: no kernel instance for this configuration");
 }

@@ -21,7 +21,11 @@ from .engine import HeadSpec, LinearDev, _as_host_tensor, _dev_vec, _device, get
 from .ops import OUT_BF16, OUT_BF16_SPLIT, OUT_F32, round_up
 
 CELL_LSTM, CELL_GRU, CELL_PEEPHOLE = 0, 1, 2
-DEFAULT_BATCH = 32
+PROFILE_CYCLES = None  # set to a list to collect per-CTA phase cycle counters of every K3 launch
+DEFAULT_BATCH = None  # None: pick 32 or 64 utterances per batch from a cost model of the schedule
+# measured SM cycles per recurrence step (profiles/r01_k3_phase_cycles.md): the step cost grows sub-linearly in the
+# batch width, but fewer/larger work items balance worse over the CTA groups
+_STEP_CYCLES = {32: 8200.0, 64: 11900.0}
 
 
 # ------------------------------------------------------------------------------------------
@@ -125,6 +129,28 @@ class Schedule:
         self.d_counters = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)
 
 
+def pick_schedule(plan, steps, device, nb=None):
+    """Build the packed schedule; with nb=None choose the batch width that minimises the critical path
+    (longest group) under the measured per-step cost."""
+    nsplit = 3 if plan.split else 1
+    cands = [nb] if nb else [64, 32]
+    best = None
+    for cand in cands:
+        try:
+            _, max_groups = ops.rnn_plan(plan.cell, plan.hidden, cand, nsplit)
+        except NnamError:
+            if len(cands) == 1:
+                raise
+            continue
+        sc = Schedule(steps, cand, plan.n_dirs, max_groups, device)
+        cost = sc.max_group_steps * _STEP_CYCLES[cand]
+        if best is None or cost < best[0]:
+            best = (cost, sc, cand)
+    if best is None:
+        raise NnamError("no recurrent kernel configuration fits this layer size / precision")
+    return best[1], best[2]
+
+
 def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=None):
     H, nd = plan.hidden, plan.n_dirs
     d = RnnDesc()
@@ -147,6 +173,10 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
     d.c0 = c0.data_ptr() if c0 is not None else None
     d.c_out = c_out.data_ptr() if c_out is not None else None
     d.counters = sched.d_counters.data_ptr()
+    if PROFILE_CYCLES is not None:
+        buf = torch.zeros(148 * 8, dtype=torch.int64, device=plan.device)
+        PROFILE_CYCLES.append(buf)
+        d.debug_cycles = buf.data_ptr()
     return d
 
 
@@ -195,8 +225,7 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         plan = get_plan(model, device)
         ws = plan.ws
         split = plan.split
-        g_ctas, max_groups = ops.rnn_plan(plan.cell, plan.hidden, nb, 3 if split else 1)
-        sched = Schedule(lens + timedelay, nb, plan.n_dirs, max_groups, device)
+        sched, nb = pick_schedule(plan, lens + timedelay, device, nb)
         rows = sched.n_rows
         # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1)
         utt = sched.order[sched.row_sorted_utt]  # original utterance (shard-relative)
@@ -258,7 +287,7 @@ def step(model, plan, xd):
     """Stateful ``model(x)`` for recurrent specs: one time step for a batch of B rows
     (chainer_networks.py:58-62); ``reset_state()`` clears the carried (h, c)."""
     B = xd.shape[0]
-    nb = DEFAULT_BATCH
+    nb = 32
     split = plan.split
     if model.bidirectional:
         raise NnamError("bidirectional models have no per-step form; use predict()/forward_utterances()")
