@@ -131,13 +131,16 @@ typedef struct NnamRnnDesc {
   const float* gx[2];  /* per direction: input projection + bias for every packed row, (rows, gx_ld) fp32,
                           columns gate-interleaved exactly like Chainer's upward/W rows */
   long long gx_ld;
-  const void* w_hi[2]; /* per direction: lateral weights (gates*H, H) bf16 K-major (Chainer lateral/W layout) */
+  const void* w_hi[2]; /* per direction: lateral weights (4H, H) bf16 K-major.  LSTM: Chainer lateral/W as is.
+                          GRU family: rows interleaved per unit [U_z, U_r (or 0), U, 0]; gx and u_bias likewise */
   const void* w_lo[2];
   long long w_ld;
   const float* u_bias[2]; /* GRU family: hidden-side biases, applied from the second step on (MGRU.py:70-83) */
   void* h_hi;          /* layer output (rows, h_ld) bf16; direction d writes columns [d*H, (d+1)*H) */
   void* h_lo;          /* low halves (bf16x3) or NULL */
   long long h_ld;
+  void* aux_hi;        /* GRU with reset gate: scratch (rows, h_ld) bf16 for the r*h exchange (+ aux_lo in bf16x3) */
+  void* aux_lo;
   int n_items;                 /* work items = (batch, direction) pairs, grouped by CTA group */
   const int* item_batch;       /* device arrays */
   const int* item_dir;

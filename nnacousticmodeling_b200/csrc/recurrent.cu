@@ -44,6 +44,8 @@ struct RnnParams {
   const float* u_bias[2]; // GRU family only
   __nv_bfloat16* h_hi;    // (rows, h_ld); direction d owns columns [d*H, (d+1)*H)
   __nv_bfloat16* h_lo;
+  __nv_bfloat16* aux_hi;  // GRU reset-gate variants: r*h exchange buffer, same shape as h
+  __nv_bfloat16* aux_lo;
   const int* item_batch;
   const int* item_dir;
   const int* group_item_start;  // n_groups + 1
@@ -381,10 +383,313 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
   }
 }
 
+// =====================================================================================================
+// GRU family (scripts/common/MGRU.py:67-85; Chainer's L.GRU is the reset-gate + tanh instance).
+//
+// Same decomposition as the LSTM kernel.  The three hidden-side matrices are interleaved 4 rows per unit,
+// row 4j+0 = U_z[j], 4j+1 = U_r[j] (zero without reset gate), 4j+2 = U[j], 4j+3 = zero padding, so a CTA slice again
+// holds whole units and the quad transpose applies unchanged; gx holds [W_z x + b, W_r x + b, W x + b, 0] the same
+// way and u_bias the hidden-side biases, which -- like every U term -- only exist from the second step on
+// (MGRU.py:70-83: h is None on the first step).
+//   no reset gate : one exchange per step:  z, hbar from [U_z; U] h
+//   reset gate    : r = s(W_r x + U_r h) must be applied BEFORE the candidate matmul (MGRU.py:73-74), so a step has
+//                   two phases: (1) [U_z; U_r] h -> r, publish r*h;  (2) U (r*h) -> hbar, publish h.
+// h itself stays in fp32 registers for the interpolation h' = z*hbar + (1-z)*h.
+template <int M_ROWS, int NB, int NSPLIT, bool FAST_TANH, int KBT>
+__global__ void __launch_bounds__(RNN_THREADS, 1)
+    gru_seq_kernel(const __grid_constant__ RnnTmaps tmaps, const RnnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int group = blockIdx.x / p.group_ctas;
+  const int rank = blockIdx.x % p.group_ctas;
+  if (group >= p.n_groups) return;
+
+  const int H = KBT > 0 ? KBT * 64 : p.hidden;
+  const int KB = KBT > 0 ? KBT : (H >> 6);
+  constexpr int W_BLOCK = M_ROWS * 128;
+  constexpr int H_BLOCK = NB * 128;
+  constexpr int NBH = NB / 2;
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* w_hi_s = smem;
+  uint8_t* w_lo_s = w_hi_s + (NSPLIT == 3 ? KB * W_BLOCK : 0);
+  uint8_t* h_hi_s = w_lo_s + KB * W_BLOCK;
+  uint8_t* h_lo_s = h_hi_s + (NSPLIT == 3 ? KB * H_BLOCK : 0);
+  uint8_t* tail = h_lo_s + KB * H_BLOCK;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* bar_mma = bar_w + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  int* s_len = reinterpret_cast<int*>(tmem_slot + 2);
+  int* s_base = s_len + NB;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int quarter = warp & 3;
+  const int half = warp >> 2;
+  const int u_lo = half * NBH;
+  constexpr int TMEM_COLS = NB < 32 ? 32 : NB;
+  const bool reset = (p.gru_flags & 1) != 0;
+  const int act = (p.gru_flags >> 1) & 3;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const bool row_valid = (M_ROWS == 128) || (lane < 16);
+  const int my_row = (M_ROWS == 128) ? (quarter * 32 + lane) : (quarter * 16 + (lane & 15));
+  const int gate = my_row & 3;  // z, r, candidate, pad
+  const int unit = rank * (M_ROWS / 4) + (my_row >> 2);
+  const int gate_col = rank * M_ROWS + my_row;
+  const uint32_t tmem_lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + u_lo;
+  const uint32_t idesc = make_idesc_bf16_f32(M_ROWS, NB);
+
+  unsigned int steps_done = 0;  // arrivals on the group counter so far
+  uint32_t w_phase = 0, mma_phase = 0;
+  int cur_dir = -1;
+  unsigned int* counter = p.counters + group;
+  const uint32_t h_hi_sa = smem_u32(h_hi_s), h_lo_sa = smem_u32(h_lo_s);
+
+  auto group_wait = [&]() {
+    if (tid == 0) {
+      const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
+      while (ld_acquire_gpu(counter) < target) {
+      }
+    }
+    __syncthreads();
+  };
+  auto group_publish = [&]() {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) red_release_gpu_add(counter, 1u);
+    ++steps_done;
+  };
+  // D[M_ROWS x NB] = W_slice . tile^T, result of my (row, slots) in acc[]
+  auto mma_tile = [&](float (&acc)[NBH]) {
+    cp_async_wait_all();
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t wd_hi = make_sw128_kmajor_desc(smem_u32(w_hi_s));
+      const uint64_t wd_lo = make_sw128_kmajor_desc(smem_u32(w_lo_s));
+      const uint64_t hd_hi = make_sw128_kmajor_desc(h_hi_sa);
+      const uint64_t hd_lo = make_sw128_kmajor_desc(h_lo_sa);
+      uint32_t accum = 0;
+#pragma unroll
+      for (int pass = 0; pass < NSPLIT; ++pass) {
+        const uint64_t wa = pass == 2 ? wd_lo : wd_hi;
+        const uint64_t ha = pass == 1 ? hd_lo : hd_hi;
+        if (KBT > 0) {
+#pragma unroll
+          for (int kb = 0; kb < KBT; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
+              accum = 1;
+            }
+        } else {
+          for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
+              accum = 1;
+            }
+        }
+      }
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < NBH; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_lane_addr + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+  };
+
+  for (int it = p.group_item_start[group]; it < p.group_item_start[group + 1]; ++it) {
+    const int b = p.item_batch[it];
+    const int d = p.item_dir[it];
+    const bool bwd = d == 1;
+    if (d != cur_dir) {
+      __syncthreads();
+      if (tid == 0) {
+        mbar_expect_tx(bar_w, static_cast<uint32_t>(KB * W_BLOCK * (NSPLIT == 3 ? 2 : 1)));
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_2d(w_hi_s + kb * W_BLOCK, &tmaps.w_hi[d], bar_w, kb * 64, rank * M_ROWS);
+          if (NSPLIT == 3) tma_load_2d(w_lo_s + kb * W_BLOCK, &tmaps.w_lo[d], bar_w, kb * 64, rank * M_ROWS);
+        }
+      }
+      mbar_wait(bar_w, w_phase);
+      w_phase ^= 1;
+      cur_dir = d;
+    }
+    const long long row0 = p.batch_row0[b];
+    const int T = p.batch_steps[b];
+    const int nutt = p.batch_nutt[b];
+    const int* base = p.base + p.batch_base_off[b];
+    const int* len = p.utt_len + b * NB;
+    const float* gx = p.gx[d] + gate_col;
+    const float ub = row_valid ? __ldg(p.u_bias[d] + gate_col) : 0.0f;
+    const int h_col0 = d * H;
+    __syncthreads();
+    if (tid < NB) s_len[tid] = tid < nutt ? len[tid] : 0;
+    const bool base_in_smem = T <= RNN_BASE_SMEM;
+    if (base_in_smem)
+      for (int i = tid; i <= T; i += RNN_THREADS) s_base[i] = __ldg(base + i);
+    __syncthreads();
+    const int* bp = base_in_smem ? s_base : base;
+    const bool has_h0 = p.h0_hi != nullptr;
+
+    // fp32 hidden state of (utterance u_lo + 4m + gate, unit)
+    float h_reg[NBH / 4];
+#pragma unroll
+    for (int m = 0; m < NBH / 4; ++m) {
+      const int u = u_lo + 4 * m + gate;
+      h_reg[m] = 0.0f;
+      if (has_h0 && row_valid && u < nutt) {
+        const long long o = (static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0 + unit;
+        h_reg[m] = __bfloat162float(p.h0_hi[o]) + (NSPLIT == 3 ? __bfloat162float(p.h0_lo[o]) : 0.0f);
+      }
+    }
+    const int chunks_per_row = H >> 3;
+    // stage rows of `src` (hi/lo) for the active utterances into the swizzled B-operand tile
+    auto load_tile = [&](const __nv_bfloat16* src_hi, const __nv_bfloat16* src_lo, int n_act, int s, int mode) {
+      // mode 0: initial state rows; 1: rows of the previous step; 2: rows of the current step
+      for (int u = warp; u < n_act; u += RNN_THREADS / 32) {
+        long long off;
+        if (mode == 0) {
+          off = (static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0;
+        } else {
+          const int t_idx = mode == 1 ? (bwd ? (s_len[u] - s) : (s - 1)) : (bwd ? (s_len[u] - 1 - s) : s);
+          off = (row0 + bp[t_idx] + u) * p.h_ld + h_col0;
+        }
+        const uint32_t row_so = static_cast<uint32_t>((u >> 3) * 1024 + (u & 7) * 128);
+        for (int c = lane; c < chunks_per_row; c += 32) {
+          const uint32_t so = static_cast<uint32_t>((c >> 3) * H_BLOCK) + row_so + (((c & 7) ^ (u & 7)) << 4);
+          cp_async_16(h_hi_sa + so, src_hi + off + c * 8);
+          if (NSPLIT == 3) cp_async_16(h_lo_sa + so, src_lo + off + c * 8);
+        }
+      }
+    };
+
+    for (int s = 0; s < T; ++s) {
+      const int base_s = bp[s];
+      const int n_s = bp[s + 1] - base_s;
+      float gxr[NBH];
+#pragma unroll
+      for (int j = 0; j < NBH; ++j) {
+        const int u = u_lo + j;
+        const int uu = u < n_s ? u : n_s - 1;
+        const long long row = row0 + (bwd ? bp[s_len[uu] - 1 - s] : base_s) + uu;
+        gxr[j] = __ldg(gx + row * p.gx_ld);
+      }
+      const bool have_h = (s > 0) || has_h0;
+      float acc[NBH];
+      if (have_h) {
+        if (s > 0) group_wait();
+        if (s == 0)
+          load_tile(p.h0_hi, p.h0_lo, n_s, s, 0);
+        else
+          load_tile(p.h_hi, p.h_lo, n_s, s, 1);
+        mma_tile(acc);
+      } else {
+#pragma unroll
+        for (int j = 0; j < NBH; ++j) acc[j] = 0.0f;
+      }
+      const float ubs = have_h ? ub : 0.0f;  // U biases exist only when h does (MGRU.py:70-83)
+      const bool two_phase = reset && have_h;
+
+      float zp[NBH / 4], hp[NBH / 4];
+#pragma unroll
+      for (int m = 0; m < NBH / 4; ++m) {
+        zp[m] = hp[m] = 0.0f;
+        if (u_lo + 4 * m >= n_s) break;
+        float x[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          x[i] = gxr[4 * m + i] + ubs + ((two_phase && gate == 2) ? 0.0f : acc[4 * m + i]);
+        quad_transpose(x, gate);  // x = {z_pre, r_pre, cand_pre, pad} of utterance u_lo + 4m + gate
+        zp[m] = x[0];
+        hp[m] = x[2];
+        if (two_phase) {
+          const int u = u_lo + 4 * m + gate;
+          const float r = fmaf(tanh_sel<FAST_TANH>(0.5f * x[1]), 0.5f, 0.5f);
+          const float rh = r * h_reg[m];
+          if (row_valid && u < n_s) {
+            const int t_idx = bwd ? (s_len[u] - 1 - s) : s;
+            const long long off = (row0 + bp[t_idx] + u) * p.h_ld + h_col0 + unit;
+            const __nv_bfloat16 hb = __float2bfloat16_rn(rh);
+            p.aux_hi[off] = hb;
+            if (NSPLIT == 3) p.aux_lo[off] = __float2bfloat16_rn(rh - __bfloat162float(hb));
+          }
+        }
+      }
+      if (two_phase) {
+        group_publish();  // r*h slices are out
+        group_wait();
+        load_tile(p.aux_hi, p.aux_lo, n_s, s, 2);
+        mma_tile(acc);    // row 4j+2 now holds U (r*h)
+      }
+#pragma unroll
+      for (int m = 0; m < NBH / 4; ++m) {
+        if (u_lo + 4 * m >= n_s) break;
+        float cand = hp[m];
+        if (two_phase) {
+          float y[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) y[i] = gate == 2 ? acc[4 * m + i] : 0.0f;
+          quad_transpose(y, gate);
+          cand += y[2];
+        }
+        const int u = u_lo + 4 * m + gate;
+        const float z = fmaf(tanh_sel<FAST_TANH>(0.5f * zp[m]), 0.5f, 0.5f);
+        const float hb = act == NNAM_ACT_RELU ? fmaxf(cand, 0.0f)
+                                              : (act == NNAM_ACT_SIGMOID
+                                                     ? fmaf(tanh_sel<FAST_TANH>(0.5f * cand), 0.5f, 0.5f)
+                                                     : (act == NNAM_ACT_TANH ? tanh_sel<FAST_TANH>(cand) : cand));
+        const float h_new = have_h ? fmaf(z, hb, (1.0f - z) * h_reg[m]) : z * hb;
+        if (row_valid && u < n_s) {
+          h_reg[m] = h_new;
+          const int t_idx = bwd ? (s_len[u] - 1 - s) : s;
+          const long long off = (row0 + bp[t_idx] + u) * p.h_ld + h_col0 + unit;
+          const __nv_bfloat16 hbf = __float2bfloat16_rn(h_new);
+          p.h_hi[off] = hbf;
+          if (NSPLIT == 3) p.h_lo[off] = __float2bfloat16_rn(h_new - __bfloat162float(hbf));
+        }
+      }
+      group_publish();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------ host side
 template <int M_ROWS, int NB, int NSPLIT, bool FAST, int KBT>
-static int launch_lstm(const RnnTmaps& tm, const RnnParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = lstm_seq_kernel<M_ROWS, NB, NSPLIT, FAST, KBT>;
+static int launch_rnn(int cell, const RnnTmaps& tm, const RnnParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = cell == NNAM_CELL_GRU ? gru_seq_kernel<M_ROWS, NB, NSPLIT, FAST, KBT>
+                                    : lstm_seq_kernel<M_ROWS, NB, NSPLIT, FAST, KBT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaFuncSetAttribute");
   void* args[] = {const_cast<RnnTmaps*>(&tm), const_cast<RnnParams*>(&p)};
@@ -412,7 +717,8 @@ int rnn_pick_m_rows(int gate_rows_total, int hidden, int nb, int nsplit) {
 
 int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   if (d == nullptr) return set_error(NNAM_ERR_ARG, "rnn: NULL descriptor");
-  if (d->cell != NNAM_CELL_LSTM) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: cell kind %d not implemented", d->cell);
+  if (d->cell != NNAM_CELL_LSTM && d->cell != NNAM_CELL_GRU)
+    return set_error(NNAM_ERR_UNSUPPORTED, "rnn: cell kind %d not implemented", d->cell);
   const int H = d->hidden;
   if (H <= 0 || H % 64) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: hidden size must be a multiple of 64 (got %d)", H);
   if (d->n_dirs != 1 && d->n_dirs != 2) return set_error(NNAM_ERR_ARG, "rnn: n_dirs must be 1 or 2");
@@ -460,6 +766,14 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   }
   p.h_hi = static_cast<__nv_bfloat16*>(d->h_hi);
   p.h_lo = static_cast<__nv_bfloat16*>(d->h_lo);
+  p.aux_hi = static_cast<__nv_bfloat16*>(d->aux_hi);
+  p.aux_lo = static_cast<__nv_bfloat16*>(d->aux_lo);
+  if (d->cell == NNAM_CELL_GRU) {
+    for (int k = 0; k < d->n_dirs; ++k)
+      if (!d->u_bias[k]) return set_error(NNAM_ERR_ARG, "rnn: GRU cells need u_bias");
+    if ((d->flags & 1) && (!d->aux_hi || (d->nsplit == 3 && !d->aux_lo)))
+      return set_error(NNAM_ERR_ARG, "rnn: reset-gate GRU needs the aux (r*h) exchange buffer");
+  }
   p.item_batch = d->item_batch;
   p.item_dir = d->item_dir;
   p.group_item_start = d->group_item_start;
@@ -487,7 +801,7 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   const int kbt = H / 64;
 #define NNAM_RNN_CASE(M, NBV, NS, F, KBTV)                                                                 \
   if (m_rows == M && d->batch == NBV && d->nsplit == NS && fast == F && (KBTV == 0 || KBTV == kbt))      \
-  return launch_lstm<M, NBV, NS, F, KBTV>(tm, p, grid, smem, stream)
+  return launch_rnn<M, NBV, NS, F, KBTV>(d->cell, tm, p, grid, smem, stream)
   // tuned instances (compile-time H): the BASELINE geometries
   NNAM_RNN_CASE(128, 32, 1, true, 8);   // H = 512, bf16
   NNAM_RNN_CASE(128, 64, 1, true, 8);
@@ -509,7 +823,8 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
 }
 
 int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups) {
-  if (cell != NNAM_CELL_LSTM) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: cell kind %d not implemented", cell);
+  if (cell != NNAM_CELL_LSTM && cell != NNAM_CELL_GRU)
+    return set_error(NNAM_ERR_UNSUPPORTED, "rnn: cell kind %d not implemented", cell);
   if (hidden <= 0 || hidden % 64) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: hidden size must be a multiple of 64");
   const int m_rows = rnn_pick_m_rows(4 * hidden, hidden, batch, nsplit);
   if (!m_rows)

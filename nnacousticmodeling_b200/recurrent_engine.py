@@ -35,26 +35,65 @@ class RecLayer:
     pass
 
 
+_ACT_CODE = {"identity": 0, "relu": 1, "sigmoid": 2, "tanh": 3}
+
+
+def _interleave4(blocks, h, cols):
+    """Stack up to three (h, cols) blocks as rows 4j+k (k = 0,1,2), row 4j+3 and missing blocks are zero."""
+    out = np.zeros((4 * h, cols), dtype=np.float32)
+    for k, blk in enumerate(blocks):
+        if blk is not None:
+            out[k::4] = blk
+    return out
+
+
 def build_plan(plan, model):
     p, dev, split = model.params, plan.device, plan.split
-    if model.network not in ("lstm", "zoneoutlstm", "zoneoutdropoutlstm", "blstm"):
-        raise NnamError(f"network '{model.network}' is not implemented on the B200 path yet")
-    plan.cell = CELL_LSTM
+    net = model.network
     plan.n_dirs = 2 if model.bidirectional else 1
-    plan.hidden = model.n_units
+    plan.hidden = h = model.n_units
     plan.rec_layers = []
+    plan.gru_flags = 0
     kind = OUT_BF16_SPLIT if split else OUT_BF16
     dirs = ("fwd/", "bwd/") if model.bidirectional else ("",)
-    for l in range(model.layers):
-        L = RecLayer()
-        up_w = np.concatenate([p[f"layer_{l}/{d}upward/W"] for d in dirs], axis=0)
-        up_b = np.concatenate([p[f"layer_{l}/{d}upward/b"] for d in dirs], axis=0)
-        L.upward = LinearDev(up_w, up_b, dev, split)  # gx for both directions in one GEMM
-        L.lat = []
-        for d in dirs:
-            w = torch.from_numpy(np.ascontiguousarray(p[f"layer_{l}/{d}lateral/W"], dtype=np.float32)).to(dev)
-            L.lat.append(ops.convert_f32(w, kind))
-        plan.rec_layers.append(L)
+
+    def to_dev_bf16(w):
+        return ops.convert_f32(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)).to(dev), kind)
+
+    if net in ("lstm", "zoneoutlstm", "zoneoutdropoutlstm", "blstm"):
+        plan.cell = CELL_LSTM
+        for l in range(model.layers):
+            L = RecLayer()
+            up_w = np.concatenate([p[f"layer_{l}/{d}upward/W"] for d in dirs], axis=0)
+            up_b = np.concatenate([p[f"layer_{l}/{d}upward/b"] for d in dirs], axis=0)
+            L.upward = LinearDev(up_w, up_b, dev, split)  # gx for both directions in one GEMM
+            L.lat = [to_dev_bf16(p[f"layer_{l}/{d}lateral/W"]) for d in dirs]
+            L.u_bias = [None for _ in dirs]
+            plan.rec_layers.append(L)
+    elif net in ("gru", "mgrurelu", "mgrurelur", "mgru", "bgru"):
+        # MGRU.py: W_* act on x (folded into the gx GEMM), U_* on h (resident in K3); rows interleaved per unit
+        # as [z, r, candidate, pad] so that the LSTM kernel's slice/quad structure carries over.
+        plan.cell = CELL_GRU
+        reset = model.use_reset_gate
+        plan.gru_flags = (1 if reset else 0) | (_ACT_CODE[model.activation.name] << 1)
+        for l in range(model.layers):
+            L = RecLayer()
+            ups, upb, L.lat, L.u_bias = [], [], [], []
+            for d in dirs:
+                pre = f"layer_{l}/{d}"
+                d_in = p[pre + "W_z/W"].shape[1]
+                ups.append(_interleave4([p[pre + "W_z/W"], p[pre + "W_r/W"] if reset else None, p[pre + "W/W"]], h, d_in))
+                upb.append(_interleave4([p[pre + "W_z/b"][:, None], p[pre + "W_r/b"][:, None] if reset else None,
+                                         p[pre + "W/b"][:, None]], h, 1)[:, 0])
+                L.lat.append(to_dev_bf16(_interleave4([p[pre + "U_z/W"], p[pre + "U_r/W"] if reset else None,
+                                                       p[pre + "U/W"]], h, h)))
+                ub = _interleave4([p[pre + "U_z/b"][:, None], p[pre + "U_r/b"][:, None] if reset else None,
+                                   p[pre + "U/b"][:, None]], h, 1)[:, 0]
+                L.u_bias.append(torch.from_numpy(np.ascontiguousarray(ub)).to(dev))
+            L.upward = LinearDev(np.concatenate(ups, axis=0), np.concatenate(upb, axis=0), dev, split)
+            plan.rec_layers.append(L)
+    else:
+        raise NnamError(f"network '{net}' is not implemented on the B200 path yet (peephole LSTM is planned)")
     plan.out = LinearDev(p["out/W"], p["out/b"], dev, split)
 
 
@@ -151,14 +190,19 @@ def pick_schedule(plan, steps, device, nb=None):
     return best[1], best[2]
 
 
-def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=None):
+def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=None, aux=None):
     H, nd = plan.hidden, plan.n_dirs
     d = RnnDesc()
-    d.cell, d.hidden, d.n_dirs, d.batch, d.nsplit, d.flags = plan.cell, H, nd, nb, 3 if plan.split else 1, 0
+    d.cell, d.hidden, d.n_dirs, d.batch, d.nsplit = plan.cell, H, nd, nb, 3 if plan.split else 1
+    d.flags = plan.gru_flags
     for k in range(nd):
         d.gx[k] = gx.data_ptr() + 4 * k * 4 * H
         d.w_hi[k] = layer.lat[k][0].data_ptr()
         d.w_lo[k] = layer.lat[k][1].data_ptr() if plan.split else None
+        d.u_bias[k] = layer.u_bias[k].data_ptr() if layer.u_bias[k] is not None else None
+    if aux is not None:
+        d.aux_hi = aux[0].data_ptr()
+        d.aux_lo = aux[1].data_ptr() if aux[1] is not None else None
     d.gx_ld = gx.stride(0)
     d.w_ld = layer.lat[0][0].stride(0)
     d.h_hi, d.h_lo, d.h_ld = h_hi.data_ptr(), (h_lo.data_ptr() if h_lo is not None else None), h_hi.stride(0)
@@ -194,10 +238,16 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
         h0 = c0 = c_out = None
         if state_in is not None:
             h0, c0 = state_in[l]
-        if want_state:
+        if want_state and plan.cell == CELL_LSTM:
             c_out = torch.zeros((sched.n_batches * nb, nd * H), dtype=torch.float32, device=plan.device)
-        desc = _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0, c0, c_out)
-        ops.rnn_seq(desc, 2.0 * rows * nd * 4 * H * H)
+        aux = None
+        if plan.cell == CELL_GRU and (plan.gru_flags & 1):  # r*h exchange scratch, same shape as h
+            aux = (ws.get(f"{tag}.aux.hi", rows, nd * H, torch.bfloat16),
+                   ws.get(f"{tag}.aux.lo", rows, nd * H, torch.bfloat16) if plan.split else None)
+        desc = _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0, c0, c_out, aux)
+        # algorithmic lateral flops: LSTM 4 gates, GRU 3 (2 without reset gate) H x H products per frame
+        n_mats = 4 if plan.cell == CELL_LSTM else (3 if plan.gru_flags & 1 else 2)
+        ops.rnn_seq(desc, 2.0 * rows * nd * n_mats * H * H)
         if want_state:
             state_out.append(((h_hi, h_lo), c_out))
         a_hi, a_lo = h_hi, h_lo

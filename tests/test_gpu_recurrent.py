@@ -123,3 +123,52 @@ def test_multi_shard_equals_single(nn):
     for u0, u1 in nn.partition_utterances(off, 3):
         recurrent_engine.forward_utterances(m, x, off, parts, u0, u1, timedelay=2, device=0)
     assert np.array_equal(full, parts)
+
+
+def _gru(nn, seed, network, in_dim, units, layers, n_out, precision="fp32", bidirectional=False):
+    base = "gru" if network == "bgru" else network
+    p = O.init_recurrent(np.random.default_rng(seed), base, in_dim, units, layers, n_out, bidirectional=bidirectional,
+                         bias_scale=0.3)  # non-zero U biases: the "first step has no U terms" rule is observable
+    m = nn.get_nn(network, layers, [units], n_out, nn.F.relu, [5])
+    m.load_params(p)
+    m.precision = precision
+    return m, p
+
+
+@pytest.mark.parametrize("network", ["gru", "mgrurelu", "mgrurelur"])
+@pytest.mark.parametrize("units,layers,lens,td", [(64, 2, [7, 3, 12, 1, 9], 0), (128, 2, [30, 41, 17, 25, 33, 8] * 7, 3),
+                                                  (512, 4, [60, 75, 44, 58], 5)])
+def test_predict_gru_family_fp32_mode(nn, golden_dir, network, units, layers, lens, td):
+    off = _offsets(lens)
+    x = np.random.default_rng(sum(lens) + 1).standard_normal((off[-1], 40)).astype(np.float32)
+    n_out = 1909 if units == 512 else 39
+    m, p = _gru(nn, units + layers, network, 40, units, layers, n_out)
+    ft = nn.adapt_transform(nn.loadKaldiFeatureTransform(os.path.join(golden_dir, "final.feature_transform")),
+                            network, 0, True)
+    want = O.predict(O.RecurrentNet(p, network, layers), x, off, network, 1, td, ft)
+    got = nn.predict(m, x, off, n_out, network, 0, 1, td, ft, progress=False)
+    assert np.abs(got - want).max() < 1e-3
+
+
+def test_gru_bf16_mode_and_bidirectional(nn):
+    lens = [40, 55, 31, 47, 62, 28]
+    off = _offsets(lens)
+    x = np.random.default_rng(11).standard_normal((off[-1], 40)).astype(np.float32)
+    m, p = _gru(nn, 12, "gru", 40, 512, 4, 1909, precision="bf16")
+    want = O.predict(O.RecurrentNet(p, "gru", 4), x, off, "gru", 1, 0, None)
+    got = nn.predict(m, x, off, 1909, "gru", 0, 1, 0, None, progress=False)
+    assert np.abs(got - want).max() < 5e-2
+    mb, pb = _gru(nn, 13, "bgru", 40, 128, 2, 39, bidirectional=True)
+    want = np.concatenate([O.log_softmax(O.birnn_forward_utterance(pb, "gru", 2, x[off[u]:off[u + 1]]))
+                           for u in range(len(lens))])
+    got = nn.predict(mb, x, off, 39, "bgru", 0, 1, 0, None, progress=False)
+    assert np.abs(got - want).max() < 1e-3
+
+
+def test_gru_stateful_call(nn):
+    m, p = _gru(nn, 14, "gru", 40, 64, 2, 39)
+    ref = O.RecurrentNet(p, "gru", 2)
+    xs = np.random.default_rng(15).standard_normal((5, 4, 40)).astype(np.float32)
+    m.reset_state()
+    for t in range(5):
+        assert np.abs(m(xs[t]) - ref(xs[t])).max() < 1e-3
