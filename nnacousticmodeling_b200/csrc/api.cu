@@ -52,21 +52,26 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-int encode_tmap_bf16_2d(CUtensorMap* m, const void* ptr, unsigned long long inner, unsigned long long rows,
-                        unsigned long long ld_elems, unsigned box_inner, unsigned box_rows) {
+int encode_tmap_2d(CUtensorMap* m, const void* ptr, bool f32, unsigned long long inner, unsigned long long rows,
+                   unsigned long long ld_elems, unsigned box_inner, unsigned box_rows) {
   auto fn = get_encode_fn();
   if (!fn) return set_error(NNAM_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {inner, rows};
-  cuuint64_t strides[1] = {ld_elems * 2ull};
+  cuuint64_t strides[1] = {ld_elems * (f32 ? 4ull : 2ull)};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return set_error(NNAM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%llu rows=%llu ld=%llu box=%ux%u",
                      static_cast<int>(r), inner, rows, ld_elems, box_inner, box_rows);
   return NNAM_OK;
+}
+
+int encode_tmap_bf16_2d(CUtensorMap* m, const void* ptr, unsigned long long inner, unsigned long long rows,
+                        unsigned long long ld_elems, unsigned box_inner, unsigned box_rows) {
+  return encode_tmap_2d(m, ptr, false, inner, rows, ld_elems, box_inner, box_rows);
 }
 
 int splice_transform(const float* x, long long x_row0, long long x_rows, long long n_total, int dim, int splice,

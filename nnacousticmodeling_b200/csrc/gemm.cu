@@ -33,66 +33,66 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;      // 16 KiB
 constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;  // 32 KiB
 constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 + 1024;  // + barriers + align slack
+constexpr int EPI_BOX_BYTES = 32 * 128;         // one epilogue warp's store box: 32 rows x 128 B, SWIZZLE_128B
+constexpr int EPI_BYTES = 4 * 2 * EPI_BOX_BYTES;  // 4 epilogue warps x 2 alternating boxes
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_BYTES + 256 + 1024;
 constexpr int TMEM_COLS = 512;
 
 struct GemmParams {
   int M, N, K;
-  int bn;         // tile width, multiple of 16, <= 256
+  int bn;         // tile width: a multiple of the store box width (64 bf16 / 32 fp32 columns), <= 256
   int tiles_m, tiles_n;
   int k_blocks;   // ceil(K / 64)
   int nsplit;     // 1 or 3
   int act;        // NNAM_ACT_*
-  int out_kind;   // NNAM_OUT_*
   const float* bias;
-  void* out_hi;
-  void* out_lo;
-  long long ldo;  // elements
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case NNAM_ACT_RELU: return fmaxf(v, 0.0f);
-    case NNAM_ACT_SIGMOID: return tanhf(v * 0.5f) * 0.5f + 0.5f;  // Chainer's sigmoid formulation
-    case NNAM_ACT_TANH: return tanhf(v);
-    default: return v;
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+  if (ACT == NNAM_ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == NNAM_ACT_SIGMOID) return tanhf(v * 0.5f) * 0.5f + 0.5f;  // Chainer's sigmoid formulation
+  if (ACT == NNAM_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void apply_act(float (&v)[NV], int act) {  // warp-uniform switch hoisted out of the loop
+  if (act == NNAM_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = act_fn<NNAM_ACT_RELU>(v[j]);
+  } else if (act == NNAM_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = act_fn<NNAM_ACT_SIGMOID>(v[j]);
+  } else if (act == NNAM_ACT_TANH) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = act_fn<NNAM_ACT_TANH>(v[j]);
   }
 }
 
-__device__ __forceinline__ void store_chunk16(const GemmParams& p, long long row, int col, const float (&v)[16]) {
-  if (p.out_kind == NNAM_OUT_F32) {
-    float4* dst = reinterpret_cast<float4*>(static_cast<float*>(p.out_hi) + row * p.ldo + col);
+// Output tile staging: the warp's 32 rows x 128 B go to shared memory in the SWIZZLE_128B pattern (16-byte chunk j of
+// row r lives at chunk position j ^ (r & 7): conflict-free for 8 consecutive lanes), then ONE lane hands the box to
+// the TMA store engine, which clips rows >= M and columns >= N.  Replaces per-thread row-strided global stores, whose
+// 32 separate lines per instruction had the L1/LSU pipe at ~73 % (profiles/r01_cfg2_gemm_before.md).
+__device__ __forceinline__ void stage_row_128B(uint8_t* box, int lane, const uint4 (&chunks)[8]) {
+  uint8_t* row = box + lane * 128;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else {
-    uint32_t h[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-    uint4* dh = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_hi) + row * p.ldo + col);
-    dh[0] = make_uint4(h[0], h[1], h[2], h[3]);
-    dh[1] = make_uint4(h[4], h[5], h[6], h[7]);
-    if (p.out_kind == NNAM_OUT_BF16_SPLIT) {
-      uint32_t l[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        l[j] = pack_bf16x2(v[2 * j] - bf16_round(v[2 * j]), v[2 * j + 1] - bf16_round(v[2 * j + 1]));
-      uint4* dl = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_lo) + row * p.ldo + col);
-      dl[0] = make_uint4(l[0], l[1], l[2], l[3]);
-      dl[1] = make_uint4(l[4], l[5], l[6], l[7]);
-    }
-  }
+  for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(row + ((j ^ (lane & 7)) << 4)) = chunks[j];
 }
 
+template <int OUT_KIND>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
     gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                         const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                          const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_STAGE_BYTES);
+  uint8_t* smem_epi = smem_b + STAGES * B_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -106,10 +106,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
     prefetch_tmap(&tm_w_hi);
+    prefetch_tmap(&tm_o_hi);
     if (p.nsplit > 1) {
       prefetch_tmap(&tm_a_lo);
       prefetch_tmap(&tm_w_lo);
     }
+    if (OUT_KIND == NNAM_OUT_BF16_SPLIT) prefetch_tmap(&tm_o_lo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -192,7 +194,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
     }
   } else if (warp >= 4) {
     // -------------------------------------------------------------- epilogue
+    // TMEM -> registers (tcgen05.ld 32x32b.x32) -> + bias, activation, (hi/lo split) -> swizzled smem box -> TMA store
+    constexpr int BOX_COLS = OUT_KIND == NNAM_OUT_F32 ? 32 : 64;  // 128 B of output per row and box
     const int q = warp & 3;  // TMEM lane quarter this warp may read
+    uint8_t* boxes = smem_epi + q * 2 * EPI_BOX_BYTES;
+    int box_sel = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -201,42 +207,71 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * MAX_BN);
-      const long long row = static_cast<long long>(m_blk) * BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      for (int c0 = 0; c0 < p.bn; c0 += 32) {
-        uint32_t r0[16], r1[16];
-        const bool second = (c0 + 16) < p.bn;  // warp-uniform
-        tmem_ld16(taddr + c0, r0);
-        if (second) tmem_ld16(taddr + c0 + 16, r1);
-        tmem_ld_wait();
+      const int row0 = m_blk * BM + q * 32;
+      for (int c0 = 0; c0 < p.bn; c0 += BOX_COLS) {
+        const int col = n_blk * p.bn + c0;
+        if (col >= p.N || row0 >= p.M) break;  // warp-uniform; the TMA store clips partial boxes
+        float v[BOX_COLS];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (half == 1 && !second) break;
-          const int col = n_blk * p.bn + c0 + half * 16;
-          if (col >= p.N) break;  // warp-uniform
-          float v[16];
+        for (int j0 = 0; j0 < BOX_COLS; j0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0 + j0, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(half == 0 ? r0[j] : r1[j]);
-          if (p.bias != nullptr) {
-            if (col + 16 <= p.N) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          for (int j = 0; j < 32; ++j) v[j0 + j] = __uint_as_float(r[j]);
+        }
+        if (p.bias != nullptr) {
+          if (col + BOX_COLS <= p.N) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float4 b = __ldg(b4 + j);
-                v[4 * j] += b.x;
-                v[4 * j + 1] += b.y;
-                v[4 * j + 2] += b.z;
-                v[4 * j + 3] += b.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (col + j < p.N) v[j] += __ldg(p.bias + col + j);
+            for (int j = 0; j < BOX_COLS / 4; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j] += b.x;
+              v[4 * j + 1] += b.y;
+              v[4 * j + 2] += b.z;
+              v[4 * j + 3] += b.w;
             }
-          }
+          } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], p.act);
-          if (row_ok) store_chunk16(p, row, col, v);
+            for (int j = 0; j < BOX_COLS; ++j)
+              if (col + j < p.N) v[j] += __ldg(p.bias + col + j);
+          }
+        }
+        apply_act<BOX_COLS>(v, p.act);
+
+        constexpr int N_OUT = OUT_KIND == NNAM_OUT_BF16_SPLIT ? 2 : 1;
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o) {
+          uint4 chunks[8];
+          if (OUT_KIND == NNAM_OUT_F32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              chunks[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else if (o == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              chunks[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < BOX_COLS; ++j) v[j] -= bf16_round(v[j]);  // low half of the hi/lo split
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              chunks[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+          uint8_t* box = boxes + box_sel * EPI_BOX_BYTES;
+          if (lane == 0) tma_store_wait_read<1>();  // the store issued from this box two boxes ago has read it
+          __syncwarp();
+          stage_row_128B(box, lane, chunks);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(o == 0 ? &tm_o_hi : &tm_o_lo, box, col, row0);
+            tma_store_commit();
+          }
+          box_sel ^= 1;
         }
       }
       tc_fence_before();
@@ -245,6 +280,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (lane == 0) tma_store_wait<0>();  // all output boxes written before the CTA retires
   }
 
   tc_fence_before();
@@ -256,11 +292,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------ host side
-static int pick_bn(int n) {
+// Tile width: the narrowest multiple of the store box width that covers N in ceil(N / 256) tiles, or -- when that
+// would pad N by more than ~3 % (N = 1909 -> 8 x 256) -- the best of the box multiples >= 128 (N = 1909 -> 10 x 192).
+static int pick_bn(int n, int box_cols) {
   const int tiles = (n + MAX_BN - 1) / MAX_BN;
   int bn = (n + tiles - 1) / tiles;
-  bn = (bn + 15) / 16 * 16;
-  return bn < 16 ? 16 : bn;
+  bn = (bn + box_cols - 1) / box_cols * box_cols;
+  long long best_pad = static_cast<long long>((n + bn - 1) / bn) * bn;
+  if (best_pad * 100 > static_cast<long long>(n) * 103) {
+    for (int cand = MAX_BN - box_cols; cand >= 128; cand -= box_cols) {
+      const long long pad = static_cast<long long>((n + cand - 1) / cand) * cand;
+      if (pad < best_pad) {
+        best_pad = pad;
+        bn = cand;
+      }
+    }
+  }
+  return bn;
+}
+
+template <int OUT_KIND>
+static int launch_gemm(const CUtensorMap (&tm)[6], const GemmParams& p, int grid, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel<OUT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GEMM_SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute");
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  gemm_bias_act_kernel<OUT_KIND><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
+                                                                                  tm[5], p);
+  return check_launch("gemm_bias_act_kernel");
 }
 
 int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
@@ -281,47 +345,48 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
        reinterpret_cast<uintptr_t>(bias)) & 15)
     return set_error(NNAM_ERR_ARG, "gemm: pointers must be 16-byte aligned");
 
+  if (out_kind != NNAM_OUT_F32 && out_kind != NNAM_OUT_BF16 && out_kind != NNAM_OUT_BF16_SPLIT)
+    return set_error(NNAM_ERR_ARG, "gemm: unknown out_kind %d", out_kind);
+  const bool f32_out = out_kind == NNAM_OUT_F32;
+  const int box_cols = f32_out ? 32 : 64;
   GemmParams p;
   p.M = M;
   p.N = N;
   p.K = K;
-  p.bn = pick_bn(N);
+  p.bn = pick_bn(N, box_cols);
   p.tiles_m = (M + BM - 1) / BM;
   p.tiles_n = (N + p.bn - 1) / p.bn;
   p.k_blocks = (K + BK - 1) / BK;
   p.nsplit = nsplit;
   p.act = act;
-  p.out_kind = out_kind;
   p.bias = bias;
-  p.out_hi = out_hi;
-  p.out_lo = out_lo;
-  p.ldo = ldo;
 
-  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  // tm[0..3] = A hi/lo, W hi/lo (loads); tm[4..5] = output hi/lo (stores: 32-row x 128-byte boxes, clipped at M x N)
+  CUtensorMap tm[6];
   int rc;
-  if ((rc = encode_tmap_bf16_2d(&ta_hi, a_hi, K, M, lda, BK, BM))) return rc;
-  if ((rc = encode_tmap_bf16_2d(&tw_hi, w_hi, K, N, ldw, BK, p.bn))) return rc;
+  if ((rc = encode_tmap_bf16_2d(&tm[0], a_hi, K, M, lda, BK, BM))) return rc;
+  if ((rc = encode_tmap_bf16_2d(&tm[2], w_hi, K, N, ldw, BK, p.bn))) return rc;
   if (nsplit == 3) {
-    if ((rc = encode_tmap_bf16_2d(&ta_lo, a_lo, K, M, lda, BK, BM))) return rc;
-    if ((rc = encode_tmap_bf16_2d(&tw_lo, w_lo, K, N, ldw, BK, p.bn))) return rc;
+    if ((rc = encode_tmap_bf16_2d(&tm[1], a_lo, K, M, lda, BK, BM))) return rc;
+    if ((rc = encode_tmap_bf16_2d(&tm[3], w_lo, K, N, ldw, BK, p.bn))) return rc;
   } else {
-    ta_lo = ta_hi;
-    tw_lo = tw_hi;
+    tm[1] = tm[0];
+    tm[3] = tm[2];
+  }
+  if ((rc = encode_tmap_2d(&tm[4], out_hi, f32_out, N, M, ldo, box_cols, 32))) return rc;
+  if (out_kind == NNAM_OUT_BF16_SPLIT) {
+    if ((rc = encode_tmap_2d(&tm[5], out_lo, false, N, M, ldo, box_cols, 32))) return rc;
+  } else {
+    tm[5] = tm[4];
   }
 
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 64 && !attr_set[dev]) {
-    cudaError_t e =
-        cudaFuncSetAttribute(gemm_bias_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES);
-    if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute");
-    attr_set[dev] = true;
-  }
   const int total = p.tiles_m * p.tiles_n;
   const int grid = total < sm_count() ? total : sm_count();
-  gemm_bias_act_kernel<<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(ta_hi, ta_lo, tw_hi, tw_lo, p);
-  return check_launch("gemm_bias_act_kernel");
+  switch (out_kind) {
+    case NNAM_OUT_F32: return launch_gemm<NNAM_OUT_F32>(tm, p, grid, stream);
+    case NNAM_OUT_BF16: return launch_gemm<NNAM_OUT_BF16>(tm, p, grid, stream);
+    default: return launch_gemm<NNAM_OUT_BF16_SPLIT>(tm, p, grid, stream);
+  }
 }
 
 }  // namespace nnam

@@ -15,6 +15,10 @@ int sm_count();
 int encode_tmap_bf16_2d(CUtensorMap* m, const void* ptr, unsigned long long inner, unsigned long long rows,
                         unsigned long long ld_elems, unsigned box_inner, unsigned box_rows);
 
+// Same for bf16 or fp32 elements (box_inner * element size must be <= 128 B).
+int encode_tmap_2d(CUtensorMap* m, const void* ptr, bool f32, unsigned long long inner, unsigned long long rows,
+                   unsigned long long ld_elems, unsigned box_inner, unsigned box_rows);
+
 int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
                   long long ldw, const float* bias, void* out_hi, void* out_lo, long long ldo, int M, int N, int K,
                   int act, int out_kind, int nsplit, cudaStream_t stream);
