@@ -79,7 +79,9 @@ int nnam_convert_f32(const float* src, long long rows, int cols, long long lds, 
 /* K2 -- out = act(A . W^T + bias): every L.Linear of chainer_networks.py (F.linear: x.dot(W.T) + b) and the
  * batched `upward` / `W_*` projections of the recurrent links.  A [M,K] (lda), W [N,K] (ldw) bf16 K-major.
  * nsplit 1: bf16; nsplit 3: bf16x3 fp32-accurate mode (needs a_lo, w_lo).  bias may be NULL.
- * out_kind selects bf16 / bf16 split / fp32 output with leading dimension ldo >= roundup(N,16).  */
+ * out_kind selects bf16 / bf16 split / fp32 output with leading dimension ldo >= N (rows 16-byte aligned); only
+ * columns [0, N) are written.  A may be a column slice of a wider matrix (pointer offset + lda): that is how the
+ * TDNN's valid 1 x k convolutions (chainer_networks.py:38-42) run on this kernel without an im2col copy.  */
 int nnam_linear_bias_act(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
                          long long ldw, const float* bias, void* out_hi, void* out_lo, long long ldo, int M,
                          int N, int K, int act, int out_kind, int nsplit, void* stream);

@@ -15,6 +15,9 @@ from .features import (  # noqa: F401
     adapt_transform, loadBin, loadKaldiFeatureTransform, saveBin, splice_and_transform, splicing,
 )
 from .engine import empty_pinned, partition_frames, partition_utterances  # noqa: F401
+from .engine import HeadSpec  # noqa: F401
 from .predict import predict  # noqa: F401
+from . import evaluate  # noqa: F401
+from .evaluate import NNWithRPL, evaluateModelTestTri  # noqa: F401
 
 __version__ = "0.1.0"

@@ -336,8 +336,7 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
   if (lda < K || ldw < K) return set_error(NNAM_ERR_ARG, "gemm: leading dimension smaller than K");
   if (nsplit == 3 && (!a_lo || !w_lo)) return set_error(NNAM_ERR_ARG, "gemm: bf16x3 needs lo operands");
   if (out_kind == NNAM_OUT_BF16_SPLIT && !out_lo) return set_error(NNAM_ERR_ARG, "gemm: split output needs out_lo");
-  const int n16 = (N + 15) / 16 * 16;
-  if (ldo < n16) return set_error(NNAM_ERR_ARG, "gemm: ldo must be >= N rounded up to 16");
+  if (ldo < N) return set_error(NNAM_ERR_ARG, "gemm: ldo must be >= N");
   if (out_kind == NNAM_OUT_F32 ? (ldo % 4) : (ldo % 8))
     return set_error(NNAM_ERR_ARG, "gemm: ldo must keep rows 16-byte aligned");
   if ((reinterpret_cast<uintptr_t>(a_hi) | reinterpret_cast<uintptr_t>(w_hi) | reinterpret_cast<uintptr_t>(a_lo) |

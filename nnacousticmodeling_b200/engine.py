@@ -95,6 +95,9 @@ class Plan:
                 self.layers = [LinearDev(p[f"layer_{l}/W"], p[f"layer_{l}/b"], device, self.split)
                                for l in range(model.layers)]
                 self.out = LinearDev(p["out/W"], p["out/b"], device, self.split)
+            elif model.network == "tdnn":
+                from . import tdnn_engine
+                tdnn_engine.build_plan(self, model)
             else:
                 from . import recurrent_engine
                 recurrent_engine.build_plan(self, model)
@@ -117,21 +120,30 @@ def get_plan(model, device):
 # ------------------------------------------------------------------------------------------
 # MLP stack on already-staged bf16 inputs
 # ------------------------------------------------------------------------------------------
-def mlp_logits(model, plan, a_hi, a_lo, rows, tag="mlp"):
-    """Run the Linear stack; returns fp32 logits (rows, roundup(C, 16)) in workspace memory."""
-    ws = plan.ws
+def mlp_logits(model, plan, a_hi, a_lo, rows, tag="mlp", ws=None):
+    """Run the Linear stack; returns fp32 logits (rows, roundup(C, 16)) in workspace memory (``ws``: the
+    workspace to use -- ensemble members share the first member's activation buffers)."""
+    ws = ws or plan.ws
     act = model.activation.name
     cap = a_hi.shape[0]
     for l, lin in enumerate(plan.layers):
         ld = round_up(lin.n, 16)
-        hi = ws.get(f"{tag}.h{l % 2}.hi", cap, ld, torch.bfloat16)
-        lo = ws.get(f"{tag}.h{l % 2}.lo", cap, ld, torch.bfloat16) if plan.split else None
+        hi = ws.get(f"act.h{l % 2}.hi", cap, ld, torch.bfloat16)
+        lo = ws.get(f"act.h{l % 2}.lo", cap, ld, torch.bfloat16) if plan.split else None
         lin(a_hi, a_lo, rows, act, plan.act_kind, out=(hi, lo))
         a_hi, a_lo = hi, lo
     ldc = round_up(plan.out.n, 16)
     logits = ws.get(f"{tag}.logits", cap, ldc, torch.float32)
     plan.out(a_hi, a_lo, rows, "identity", OUT_F32, out=(logits, None))
     return logits
+
+
+def ff_logits(model, plan, a_hi, a_lo, rows, tag, ws=None):
+    """Frame-independent nets on staged inputs: MLP Linear stack or TDNN conv-as-GEMM stack."""
+    if model.network == "tdnn":
+        from . import tdnn_engine
+        return tdnn_engine.logits(model, plan, a_hi, a_lo, rows, tag=tag, ws=ws)
+    return mlp_logits(model, plan, a_hi, a_lo, rows, tag=tag, ws=ws)
 
 
 def call_model(model, x):
@@ -157,11 +169,7 @@ def call_model(model, x):
         else:
             rows = xd.shape[0]
             a_hi, a_lo = ops.convert_f32(xd.contiguous(), plan.act_kind)
-            if model.network == "tdnn":
-                from . import tdnn_engine
-                logits = tdnn_engine.logits(model, plan, a_hi, a_lo, rows)
-            else:
-                logits = mlp_logits(model, plan, a_hi, a_lo, rows, tag="call")
+            logits = ff_logits(model, plan, a_hi, a_lo, rows, "call")
             logits = logits[:rows, :model.n_out].clone()
         if is_np:
             return logits.cpu().numpy()
@@ -259,6 +267,11 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         out_h = None if out_on_device else _as_host_tensor(out)
         chunk = min(chunk, f1 - f0)
         d_in = models[0].in_size
+        if any(m.in_size != d_in or m.n_out != n_out for m in models):
+            raise NnamError("ensemble members must share input and output sizes")
+        have = x.shape[1] if presliced else (2 * splice + 1) * x.shape[1] + (0 if ivectors is None else ivectors.shape[1])
+        if have != d_in:
+            raise NnamError(f"model expects {d_in} inputs per frame, the data provides {have}")
         ld_in = round_up(d_in, 8)
         a_hi = ws.get("ff.a.hi", chunk, ld_in, torch.bfloat16)
         a_lo = ws.get("ff.a.lo", chunk, ld_in, torch.bfloat16) if plan0.split else None
@@ -273,7 +286,7 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
                 ops.splice_transform(x_dev, n_total, splice, add, mul,
                                      None if iv_dev is None else iv_dev[c0 - iv0:c1 - iv0], f0=c0, f1=c1, x_row0=lo,
                                      out_kind=plan0.act_kind, ldo=ld_in, out=(a_hi, a_lo))
-            logits = [mlp_logits(m, p, a_hi, a_lo, rows, tag=f"ff{k}") for k, (m, p) in enumerate(zip(models, plans))]
+            logits = [ff_logits(m, p, a_hi, a_lo, rows, f"ff{k}", ws) for k, (m, p) in enumerate(zip(models, plans))]
             hkw = dict(rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
                        prior_scale=head.prior_scale, final_normalize=head.final_normalize)
             if out_on_device:

@@ -119,7 +119,7 @@ def linear_bias_act(a_hi, a_lo, w_hi, w_lo, bias, M, N, K, act="identity", out_k
         _req(t, torch.bfloat16, n)
     _req(bias, torch.float32, "bias")
     if ldo is None:
-        ldo = round_up(N, 16)
+        ldo = round_up(N, 16) if out is None else out[0].stride(0)
     dt = torch.float32 if out_kind == OUT_F32 else torch.bfloat16
     if out is None:
         hi = torch.empty((M, ldo), dtype=dt, device=a_hi.device)

@@ -23,12 +23,15 @@ def _devices(gpu):
 
 
 def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft, progress=True, ivectors=None,
-            out=None, fix_timedelay_tail=False):
+            out=None, fix_timedelay_tail=False, head=None, presliced=False):
     """predict_folds.py:27-95.  Returns (N, num_classes) float32 log-softmax outputs.
 
     Extensions: ``ivectors`` (N, I) are appended AFTER splice + transform (train.py:255-258 /
     evaluate.py:169-171 order; see SURVEY quirk Q2); ``out`` may be a caller-owned (pinned) array;
-    ``fix_timedelay_tail`` fills the last ``timedelay`` frames that the reference leaves 0 (quirk Q4).
+    ``fix_timedelay_tail`` fills the last ``timedelay`` frames that the reference leaves 0 (quirk Q4);
+    ``model`` may be a list of same-shaped nets whose outputs are combined on the device by ``head``
+    (an ``engine.HeadSpec``: logit mean of evaluate.py:35-51, log-prob mean of predict_folds.py:199-219, RPL4,
+    prior); ``presliced`` says ``x`` is already spliced/transformed (the evaluate.py data flow).
     """
     devs = _devices(gpu)
     x = np.ascontiguousarray(x, dtype=np.float32)
@@ -48,14 +51,14 @@ def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft,
         engine.run_sharded(
             lambda sh, d: recurrent_engine.forward_utterances(model, x, offsets, out, sh[0], sh[1], ft=ft,
                                                               ivectors=ivectors, timedelay=timedelay, device=d,
-                                                              fix_timedelay_tail=fix_timedelay_tail),
+                                                              fix_timedelay_tail=fix_timedelay_tail, head=head),
             shards, devs)
     else:
         splice = int(winlen) // 2
         shards = engine.partition_frames(n, len(devs))
         engine.run_sharded(
             lambda sh, d: engine.ff_forward_frames(model, x, ft, splice, out, sh[0], sh[1], ivectors=ivectors,
-                                                   device=d),
+                                                   device=d, head=head, presliced=presliced),
             shards, devs)
     return out
 
@@ -133,19 +136,33 @@ def main(arg_list=None):
         x = np.load(str(Path(args.data_dir, args.data.format("dev"))))
         offsets = np.load(str(Path(args.offset_dir, args.offsets.format("dev")))) if recurrent else None
         iv = np.load(str(Path(args.ivector_dir, args.ivectors.format("dev")))) if args.ivector_dir else None
-        y_out = 0
-        for _ in fold_models():
-            y_out = y_out + predict(model, x, offsets, num_classes, args.network, gpu, winlen, args.timedelay, ft,
-                                    not args.no_progress, ivectors=iv)
-            n_folds += 1
+        folds = []
+        while True:
+            f = Path(args.fold_model_dir, args.fold_network_pattern.format(len(folds)))
+            if not f.is_file():
+                break
+            m = get_nn(args.network, args.layers, args.units, num_classes, _activation(args.activation),
+                       args.tdnn_ksize, args.dropout)
+            if args.precision:
+                m.precision = args.precision
+            load_npz(str(f), Classifier(m))
+            print("Predicting fold {} data".format(len(folds)))
+            folds.append(m)
+        n_folds = len(folds)
         if n_folds == 0:
             print("Error: No fold networks found")
             sys.exit(2)
-        # predict_folds.py:217-219: mean of the fold LOG-SOFTMAX outputs, renormalised (quirk Q5)
-        y_out /= n_folds
-        mx = y_out.max(axis=1, keepdims=True)
-        y_out = y_out - (mx + np.log(np.exp(y_out - mx).sum(axis=1, keepdims=True)))
-        np.save(str(Path(args.fold_output_dir, args.fold_output_dev)), y_out.astype(np.float32))
+        # predict_folds.py:199-219: mean of the fold LOG-SOFTMAX outputs, renormalised (quirk Q5) -- one pass on the
+        # device: K4 normalises every member, averages, and normalises again
+        y_out = predict(folds, x, offsets, num_classes, args.network, gpu, winlen, args.timedelay, ft,
+                        not args.no_progress, ivectors=iv, head=engine.HeadSpec(pre_normalize=True))
+        if recurrent and args.timedelay > 0:
+            # quirk Q4 through the reference's averaging: the unwritten (all-zero) tail rows of every fold average to
+            # zero and are then renormalised to -log(C) (predict_folds.py:217-219)
+            for u in range(len(offsets) - 1):
+                y_out[max(int(offsets[u + 1]) - args.timedelay, int(offsets[u])):int(offsets[u + 1])] = -np.log(
+                    np.float32(num_classes))
+        np.save(str(Path(args.fold_output_dir, args.fold_output_dev)), y_out)
     else:
         for fold in fold_models():
             x = np.load(str(Path(args.fold_data_dir, args.fold_data_pattern.format(fold))))

@@ -224,9 +224,10 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
     return d
 
 
-def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_state=False, tag="rnn"):
-    """All recurrent layers on packed rows; returns (h_hi, h_lo) of the last layer and the new state."""
-    ws = plan.ws
+def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_state=False, tag="rnn", ws=None):
+    """All recurrent layers on packed rows; returns (h_hi, h_lo) of the last layer and the new state.
+    ``ws``: workspace to use (ensembles share the first member's buffers; launches are stream-ordered)."""
+    ws = ws or plan.ws
     H, nd = plan.hidden, plan.n_dirs
     state_out = []
     for l, layer in enumerate(plan.rec_layers):
@@ -258,10 +259,12 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
                        fix_timedelay_tail=False, nb=DEFAULT_BATCH):
     """Recurrent hot path on ONE device for utterances [u0, u1) (predict_folds.py:28-68 semantics).
 
+    model: one recurrent spec or a list of them (ensemble: the logits are combined in the head, evaluate.py:35-51).
     x / ivectors: (N, dim) / (N, I) float32, host arrays or CUDA tensors; out: (N, C) float32 host array or CUDA
     tensor, rows [offsets[u0], offsets[u1]) are written.  Output frame f of an utterance is the network output at
     step f + timedelay; like the reference, the last ``timedelay`` frames stay 0 unless fix_timedelay_tail.
     """
+    models = list(model) if isinstance(model, (list, tuple)) else [model]
     device = _device(device)
     head = head or HeadSpec()
     offsets = np.asarray(offsets, dtype=np.int64)
@@ -272,10 +275,14 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
     if np.any(lens <= 0):
         raise NnamError("forward_utterances: empty utterance in offsets")
     with torch.cuda.device(device):
-        plan = get_plan(model, device)
+        plans = [get_plan(m, device) for m in models]
+        plan = plans[0]
         ws = plan.ws
         split = plan.split
+        if any(p.split != split for p in plans):
+            raise NnamError("forward_utterances: all ensemble members must use the same precision mode")
         sched, nb = pick_schedule(plan, lens + timedelay, device, nb)
+        scheds = {(plan.cell, plan.hidden, plan.n_dirs): sched}
         rows = sched.n_rows
         # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1)
         utt = sched.order[sched.row_sorted_utt]  # original utterance (shard-relative)
@@ -308,7 +315,7 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
             add, mul = _dev_vec(ft["addShift"], device), _dev_vec(ft["rescale"], device)
             if add.numel() != x.shape[1]:
                 raise NnamError("forward_utterances: recurrent nets take the shift-0 transform block (adapt_transform)")
-        d_in = model.in_size
+        d_in = models[0].in_size
         if d_in != x.shape[1] + (0 if ivectors is None else ivectors.shape[1]):
             raise NnamError(f"forward_utterances: model expects {d_in} inputs, data provides "
                             f"{x.shape[1] + (0 if ivectors is None else ivectors.shape[1])}")
@@ -316,17 +323,25 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         a_hi = ws.get("rnn.a.hi", rows, ld_in, torch.bfloat16)
         a_lo = ws.get("rnn.a.lo", rows, ld_in, torch.bfloat16) if split else None
         ops.gather_transform(x_dev, d_src, add, mul, iv_dev, out_kind=plan.act_kind, ldo=ld_in, out=(a_hi, a_lo))
-        h_hi, h_lo, _ = run_layers(model, plan, sched, a_hi, a_lo, rows, nb)
-        n_out = model.n_out
-        logits = ws.get("rnn.logits", rows, round_up(n_out, 16), torch.float32)
-        plan.out(h_hi, h_lo, rows, "identity", OUT_F32, out=(logits, None))
+        n_out = models[0].n_out
+        logits = []
+        for k, (m, pl) in enumerate(zip(models, plans)):
+            if m.in_size != d_in or m.n_out != n_out:
+                raise NnamError("forward_utterances: ensemble members must share input and output sizes")
+            key = (pl.cell, pl.hidden, pl.n_dirs)
+            if key not in scheds:  # same utterances and batch width => same packed row order, other grouping
+                scheds[key], _ = pick_schedule(pl, lens + timedelay, device, nb)
+            h_hi, h_lo, _ = run_layers(m, pl, scheds[key], a_hi, a_lo, rows, nb, ws=ws)
+            lg = ws.get(f"rnn.logits{k}", rows, round_up(n_out, 16), torch.float32)
+            pl.out(h_hi, h_lo, rows, "identity", OUT_F32, out=(lg, None))
+            logits.append(lg)
         on_dev = isinstance(out, torch.Tensor) and out.is_cuda
         out_dev = out[f_lo:f_hi] if on_dev else ws.get("rnn.out", f_hi - f_lo, n_out, torch.float32)
         out_dev.zero_()
         prior = _dev_vec(head.prior, device)
         rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
-        ops.head(logits, n_out, rows=rows, rpl=rpl, prior=prior, prior_scale=head.prior_scale,
-                 final_normalize=head.final_normalize, out=out_dev, out_row_map=d_dst)
+        ops.head(logits, n_out, rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
+                 prior_scale=head.prior_scale, final_normalize=head.final_normalize, out=out_dev, out_row_map=d_dst)
         if not on_dev:
             _as_host_tensor(out)[f_lo:f_hi].copy_(out_dev, non_blocking=True)
         torch.cuda.current_stream().synchronize()
