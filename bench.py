@@ -202,18 +202,14 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
-    import torch.distributed as dist
-
     import nnacousticmodeling_b200 as nn
     from nnacousticmodeling_b200 import engine, ops
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from nnacousticmodeling_b200 import dist_util
+    world, rank, local = dist_util.env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    dist_util.init("nccl", dev)
     peaks = load_peaks()
 
     w, x, offsets, iv = make_workload(args.workload, rank)
@@ -256,16 +252,11 @@ def run_ours(args):
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        dist_util.barrier()
         torch.cuda.synchronize()
 
     def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return dist_util.max_over_ranks(v, dev)
 
     # ---- device-resident leg ("value"): inputs in HBM, outputs left in HBM, CUDA events
     for _ in range(max(args.warmup, 3)):
@@ -358,8 +349,7 @@ def run_ours(args):
         line["cpu_baseline"] = None
     if rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    dist_util.finalize()
     return 0
 
 

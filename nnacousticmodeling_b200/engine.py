@@ -238,8 +238,8 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
     if f1 <= f0:
         return out
     n_out = models[0].n_out
-    halo = 0 if presliced else splice
-    lo, hi = max(f0 - halo, 0), min(f1 + halo, n_total)
+    from .dist_util import halo_range
+    lo, hi = halo_range(f0, f1, 0 if presliced else splice, n_total)
     with torch.cuda.device(device):
         plans = [get_plan(m, device) for m in models]
         plan0 = plans[0]
