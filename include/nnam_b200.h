@@ -163,8 +163,11 @@ typedef struct NnamRnnDesc {
 } NnamRnnDesc;
 
 int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream);
-/* CTAs per group and the number of groups the current device can run for this cell configuration.  */
-int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups);
+/* CTAs per group, the number of groups the current device can run concurrently for this cell configuration, and
+ * (optional, may be NULL) the measured SM cycles per recurrence step, from which the host picks the batch width.
+ * NNAM_RNN_CLUSTER=1 in the environment opts LSTM / bf16 / batch 32 into the experimental thread-block-cluster variant
+ * (h exchanged through distributed shared memory; measured slower than the L2 exchange on B200).  */
+int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles);
 
 #ifdef __cplusplus
 }

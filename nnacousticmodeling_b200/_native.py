@@ -97,7 +97,7 @@ _SIGNATURES = {
     "nnam_gather_transform": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                       c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "nnam_rnn_seq": (c_int, [c_void_p, c_void_p]),
-    "nnam_rnn_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "nnam_rnn_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
 }
 
 

@@ -87,7 +87,7 @@ int gather_transform(const float* x, long long n_src, int dim, const float* add_
                      const float* ivec, int ivec_dim, const int* row_map, long long n_rows, void* out_hi, void* out_lo,
                      long long ldo, int out_kind, cudaStream_t stream);
 int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream);
-int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups);
+int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles);
 
 }  // namespace nnam
 
@@ -151,9 +151,9 @@ int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream) {
   return nnam::rnn_seq(desc, static_cast<cudaStream_t>(stream));
 }
 
-int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups) {
+int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles) {
   if (!group_ctas || !max_groups) return nnam::set_error(NNAM_ERR_ARG, "rnn_plan: NULL output");
-  return nnam::rnn_plan(cell, hidden, batch, nsplit, group_ctas, max_groups);
+  return nnam::rnn_plan(cell, hidden, batch, nsplit, group_ctas, max_groups, step_cycles);
 }
 
 }  // extern "C"

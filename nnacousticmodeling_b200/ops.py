@@ -196,11 +196,12 @@ def gather_transform(x, row_map, add_shift=None, rescale=None, ivec=None, out_ki
     return hi, lo
 
 
-def rnn_plan(cell, hidden, batch, nsplit):
-    """(CTAs per group, max groups on the current device) for a recurrent cell configuration."""
-    g, m = ctypes.c_int(0), ctypes.c_int(0)
-    check(_native.lib().nnam_rnn_plan(cell, hidden, batch, nsplit, ctypes.byref(g), ctypes.byref(m)))
-    return g.value, m.value
+def rnn_plan(cell, hidden, batch, nsplit, with_cycles=False):
+    """(CTAs per group, max concurrent groups on the current device[, SM cycles per step]) for a recurrent cell
+    configuration."""
+    g, m, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    check(_native.lib().nnam_rnn_plan(cell, hidden, batch, nsplit, ctypes.byref(g), ctypes.byref(m), ctypes.byref(c)))
+    return (g.value, m.value, c.value) if with_cycles else (g.value, m.value)
 
 
 def rnn_seq(desc, flops):

@@ -25,7 +25,6 @@ PROFILE_CYCLES = None  # set to a list to collect per-CTA phase cycle counters o
 DEFAULT_BATCH = None  # None: pick 32 or 64 utterances per batch from a cost model of the schedule
 # measured SM cycles per recurrence step (profiles/r01_k3_phase_cycles.md): the step cost grows sub-linearly in the
 # batch width, but fewer/larger work items balance worse over the CTA groups
-_STEP_CYCLES = {32: 8200.0, 64: 11900.0}
 
 
 # ------------------------------------------------------------------------------------------
@@ -176,13 +175,13 @@ def pick_schedule(plan, steps, device, nb=None):
     best = None
     for cand in cands:
         try:
-            _, max_groups = ops.rnn_plan(plan.cell, plan.hidden, cand, nsplit)
+            _, max_groups, cycles = ops.rnn_plan(plan.cell, plan.hidden, cand, nsplit, with_cycles=True)
         except NnamError:
             if len(cands) == 1:
                 raise
             continue
         sc = Schedule(steps, cand, plan.n_dirs, max_groups, device)
-        cost = sc.max_group_steps * _STEP_CYCLES[cand]
+        cost = sc.max_group_steps * cycles
         if best is None or cost < best[0]:
             best = (cost, sc, cand)
     if best is None:
