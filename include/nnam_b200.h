@@ -120,6 +120,18 @@ int nnam_gather_transform(const float* x, long long n_src, int dim, const float*
                           const float* ivec, int ivec_dim, const int* row_map, long long n_rows, void* out_hi,
                           void* out_lo, long long ldo, int out_kind, void* stream);
 
+/* Peephole-LSTM gate arithmetic for ONE time step on n packed rows (L.StatefulPeepholeLSTM via PeepholeLSTM,
+ * chainer_networks.py:103-121).  The matrix products around it are nnam_linear_bias_act calls:
+ *   g1 = [h | c] . [lateral/W | P]^T   with P rows [0, peep_i, peep_f, 0] per unit (gate-interleaved like lateral/W)
+ *   phase 0:  c' = tanh(gx_a + g1_a) s(gx_i + g1_i) + s(gx_f + g1_f) c      -> c_new (fp32) and columns [H, 2H) of out
+ *   p2 = c' . peep_o^T
+ *   phase 1:  h' = s(gx_o + g1_o + p2) tanh(c')                              -> columns [0, H) of out
+ * out_hi/out_lo are the bf16 (hi/lo) [h | c] rows of this step, (n, out_ld >= 2H).  g1 / c_prev may be NULL on the
+ * first step (h = None, c = 0).  fast_tanh: 1 = tanh.approx (bf16 mode), 0 = tanhf (fp32-accurate mode).  */
+int nnam_peephole_cell(int phase, const float* gx, long long gx_ld, const float* g1, long long g1_ld, const float* p2,
+                       long long p2_ld, const float* c_prev, float* c_new, void* out_hi, void* out_lo,
+                       long long out_ld, int n, int hidden, int fast_tanh, void* stream);
+
 /* K3 -- persistent recurrence kernel: one launch runs a whole layer (one or both directions) over a whole shard.
  * Replaces the per-time-step Python loop around L.LSTM / F.lstm (chainer_networks.py:44-62 via
  * predict_folds.py:49-61 and evaluateModelForTest.py:67-80).  See csrc/recurrent.cu for the data layout.  */
@@ -127,7 +139,8 @@ typedef struct NnamRnnDesc {
   int cell;    /* NNAM_CELL_* */
   int hidden;  /* H (multiple of 64) */
   int n_dirs;  /* 1, or 2 = bidirectional: direction 1 walks every utterance backwards */
-  int batch;   /* utterances per batch: 32 or 64 */
+  int batch;   /* utterance slots per batch (= per stream): 16, 32 or 64 */
+  int streams; /* independent batches a CTA group runs concurrently (from nnam_rnn_plan) */
   int nsplit;  /* 1 = bf16 operands, 3 = bf16x3 (needs the _lo buffers) */
   int flags;   /* GRU family: bit 0 = reset gate, bits 1-2 = candidate activation (NNAM_ACT_*) */
   const float* gx[2];  /* per direction: input projection + bias for every packed row, (rows, gx_ld) fp32,
@@ -143,11 +156,12 @@ typedef struct NnamRnnDesc {
   long long h_ld;
   void* aux_hi;        /* GRU with reset gate: scratch (rows, h_ld) bf16 for the r*h exchange (+ aux_lo in bf16x3) */
   void* aux_lo;
-  int n_items;                 /* work items = (batch, direction) pairs, grouped by CTA group */
+  int n_items;                 /* work items = (batch, direction) pairs, grouped by lane = (CTA group, stream);
+                                  inside a lane the items are sorted by direction */
   const int* item_batch;       /* device arrays */
   const int* item_dir;
   int n_groups;
-  const int* group_item_start; /* n_groups + 1 */
+  const int* group_item_start; /* n_groups * streams + 1: first item of lane g * streams + s */
   const int* batch_row0;       /* first packed row of each batch */
   const int* batch_steps;      /* steps (= longest utterance) of each batch */
   const int* batch_nutt;       /* utterances in each batch (<= batch) */
@@ -158,16 +172,18 @@ typedef struct NnamRnnDesc {
   const void* h0_lo;
   const float* c0;             /* optional initial cell state (n_utts, H*n_dirs) fp32 */
   float* c_out;                /* optional final cell state, same shape */
-  unsigned int* counters;      /* n_groups words of scratch */
+  unsigned int* counters;      /* n_groups * streams words of scratch */
   void* debug_cycles;          /* optional: int64[8] per CTA, per-phase SM cycle totals (profiling builds/tests) */
 } NnamRnnDesc;
 
 int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream);
 /* CTAs per group, the number of groups the current device can run concurrently for this cell configuration, and
- * (optional, may be NULL) the measured SM cycles per recurrence step, from which the host picks the batch width.
+ * (optional, may be NULL) the measured SM cycles per recurrence step, from which the host picks the batch width, and
+ * the number of streams (concurrent batches per group) the kernel instance for `batch` slots runs.
  * NNAM_RNN_CLUSTER=1 in the environment opts LSTM / bf16 / batch 32 into the experimental thread-block-cluster variant
  * (h exchanged through distributed shared memory; measured slower than the L2 exchange on B200).  */
-int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles);
+int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles,
+                  int* streams);
 
 #ifdef __cplusplus
 }

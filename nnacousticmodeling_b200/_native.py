@@ -14,7 +14,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libnnam_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu"]
+SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_cluster.cu", "peephole.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -96,8 +96,11 @@ _SIGNATURES = {
                                   c_void_p]),
     "nnam_gather_transform": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                       c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "nnam_peephole_cell": (c_int, [c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p]),
     "nnam_rnn_seq": (c_int, [c_void_p, c_void_p]),
-    "nnam_rnn_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "nnam_rnn_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int),
+                              POINTER(c_int)]),
 }
 
 
@@ -105,7 +108,8 @@ class RnnDesc(ctypes.Structure):
     """Mirror of ``NnamRnnDesc`` (include/nnam_b200.h)."""
 
     _fields_ = [
-        ("cell", c_int), ("hidden", c_int), ("n_dirs", c_int), ("batch", c_int), ("nsplit", c_int), ("flags", c_int),
+        ("cell", c_int), ("hidden", c_int), ("n_dirs", c_int), ("batch", c_int), ("streams", c_int), ("nsplit", c_int),
+        ("flags", c_int),
         ("gx", c_void_p * 2), ("gx_ld", c_longlong),
         ("w_hi", c_void_p * 2), ("w_lo", c_void_p * 2), ("w_ld", c_longlong),
         ("u_bias", c_void_p * 2),

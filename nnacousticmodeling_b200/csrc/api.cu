@@ -86,8 +86,12 @@ int head(const float* const* logits_host, const float* weights_host, int n_input
 int gather_transform(const float* x, long long n_src, int dim, const float* add_shift, const float* rescale,
                      const float* ivec, int ivec_dim, const int* row_map, long long n_rows, void* out_hi, void* out_lo,
                      long long ldo, int out_kind, cudaStream_t stream);
+int peephole_cell(int phase, const float* gx, long long gx_ld, const float* g1, long long g1_ld, const float* p2,
+                  long long p2_ld, const float* c_prev, float* c_new, void* out_hi, void* out_lo, long long out_ld, int n,
+                  int H, int fast, cudaStream_t stream);
 int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream);
-int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles);
+int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles,
+             int* streams);
 
 }  // namespace nnam
 
@@ -147,13 +151,21 @@ int nnam_gather_transform(const float* x, long long n_src, int dim, const float*
                                 ldo, out_kind, static_cast<cudaStream_t>(stream));
 }
 
+int nnam_peephole_cell(int phase, const float* gx, long long gx_ld, const float* g1, long long g1_ld, const float* p2,
+                       long long p2_ld, const float* c_prev, float* c_new, void* out_hi, void* out_lo,
+                       long long out_ld, int n, int hidden, int fast_tanh, void* stream) {
+  return nnam::peephole_cell(phase, gx, gx_ld, g1, g1_ld, p2, p2_ld, c_prev, c_new, out_hi, out_lo, out_ld, n, hidden,
+                             fast_tanh, static_cast<cudaStream_t>(stream));
+}
+
 int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream) {
   return nnam::rnn_seq(desc, static_cast<cudaStream_t>(stream));
 }
 
-int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles) {
+int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles,
+                  int* streams) {
   if (!group_ctas || !max_groups) return nnam::set_error(NNAM_ERR_ARG, "rnn_plan: NULL output");
-  return nnam::rnn_plan(cell, hidden, batch, nsplit, group_ctas, max_groups, step_cycles);
+  return nnam::rnn_plan(cell, hidden, batch, nsplit, group_ctas, max_groups, step_cycles, streams);
 }
 
 }  // extern "C"

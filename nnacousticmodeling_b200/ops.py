@@ -14,7 +14,7 @@ OUT_BF16, OUT_BF16_SPLIT, OUT_F32 = 0, 1, 2
 
 
 # launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing for the roofline block)
-LAUNCHES = {"splice": 0, "convert": 0, "gemm": 0, "head": 0, "rnn": 0}
+LAUNCHES = {"splice": 0, "convert": 0, "gemm": 0, "head": 0, "rnn": 0, "cell": 0}
 PROFILE = None  # set to a list to record (kernel, start_event, end_event, work) per launch
 
 
@@ -196,15 +196,25 @@ def gather_transform(x, row_map, add_shift=None, rescale=None, ivec=None, out_ki
     return hi, lo
 
 
-def rnn_plan(cell, hidden, batch, nsplit, with_cycles=False):
-    """(CTAs per group, max concurrent groups on the current device[, SM cycles per step]) for a recurrent cell
-    configuration."""
-    g, m, c = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
-    check(_native.lib().nnam_rnn_plan(cell, hidden, batch, nsplit, ctypes.byref(g), ctypes.byref(m), ctypes.byref(c)))
-    return (g.value, m.value, c.value) if with_cycles else (g.value, m.value)
+def rnn_plan(cell, hidden, batch, nsplit):
+    """(CTAs per group, max concurrent groups on the current device, SM cycles per stream step, streams per group)
+    for a recurrent cell configuration with ``batch`` utterance slots per stream."""
+    g, m, c, s = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    check(_native.lib().nnam_rnn_plan(cell, hidden, batch, nsplit, ctypes.byref(g), ctypes.byref(m), ctypes.byref(c),
+                                      ctypes.byref(s)))
+    return g.value, m.value, c.value, s.value
 
 
 def rnn_seq(desc, flops):
     """K3: run one recurrent layer (all batches, one or both directions) described by an RnnDesc."""
     with _Prof("rnn", flops):
         check(_native.lib().nnam_rnn_seq(ctypes.addressof(desc), _stream()))
+
+
+def peephole_cell(phase, gx, g1, p2, c_prev, c_new, out_hi, out_lo, n, hidden, fast):
+    """One phase of the peephole-LSTM gate arithmetic on n packed rows (see include/nnam_b200.h)."""
+    with _Prof("cell", n * hidden * 4 * 8):
+        check(_native.lib().nnam_peephole_cell(
+            phase, _ptr(gx), gx.stride(0), _ptr(g1), 0 if g1 is None else g1.stride(0), _ptr(p2),
+            0 if p2 is None else p2.stride(0), _ptr(c_prev), _ptr(c_new), _ptr(out_hi), _ptr(out_lo), out_hi.stride(0),
+            n, hidden, int(bool(fast)), _stream()))

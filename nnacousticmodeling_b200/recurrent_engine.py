@@ -59,6 +59,8 @@ def build_plan(plan, model):
     def to_dev_bf16(w):
         return ops.convert_f32(torch.from_numpy(np.ascontiguousarray(w, dtype=np.float32)).to(dev), kind)
 
+    if model.bidirectional and net == "peepholelstm":
+        raise NnamError("bidirectional peephole LSTM is not defined (SURVEY A9 covers LSTM and GRU)")
     if net in ("lstm", "zoneoutlstm", "zoneoutdropoutlstm", "blstm"):
         plan.cell = CELL_LSTM
         for l in range(model.layers):
@@ -91,21 +93,50 @@ def build_plan(plan, model):
                 L.u_bias.append(torch.from_numpy(np.ascontiguousarray(ub)).to(dev))
             L.upward = LinearDev(np.concatenate(ups, axis=0), np.concatenate(upb, axis=0), dev, split)
             plan.rec_layers.append(L)
+    elif net == "peepholelstm":
+        from . import peephole_engine
+        plan.cell = CELL_PEEPHOLE
+        peephole_engine.build_plan(plan, model)
+        return
     else:
-        raise NnamError(f"network '{net}' is not implemented on the B200 path yet (peephole LSTM is planned)")
+        raise NnamError(f"network '{net}' is not implemented on the B200 path")
     plan.out = LinearDev(p["out/W"], p["out/b"], dev, split)
 
 
 # ------------------------------------------------------------------------------------------
 # schedule
 # ------------------------------------------------------------------------------------------
-class Schedule:
-    """Packed time-major schedule of a set of utterances (host arrays + device copies)."""
+def assign_lanes(bsteps, n_dirs, max_groups, streams):
+    """Spread the (batch, direction) work items over lanes = (CTA group, stream): per direction, batches longest
+    first, each to the least-loaded lane (LPT).  Returns (items per lane, groups used, critical path in steps); the
+    critical path accounts for a group switching direction only when all of its streams are done with the current
+    one."""
+    n_batches = len(bsteps)
+    n_groups = max(1, min(max_groups, (n_batches + streams - 1) // streams))
+    n_lanes = n_groups * streams
+    per_lane = [[] for _ in range(n_lanes)]
+    load = np.zeros((n_lanes, n_dirs), np.int64)
+    by_len = np.argsort(-np.asarray(bsteps), kind="stable")
+    for d in range(n_dirs):
+        for b in by_len:
+            ln = int(np.argmin(load[:, d]))
+            load[ln, d] += int(bsteps[b])
+            per_lane[ln].append((int(b), d))  # direction-sorted by construction
+    per_group = load.reshape(n_groups, streams, n_dirs).max(axis=1).sum(axis=1)
+    return per_lane, n_groups, (int(per_group.max()) if n_batches else 0)
 
-    def __init__(self, steps, nb, n_dirs, max_groups, device):
+
+class Schedule:
+    """Packed time-major schedule of a set of utterances (host arrays + device copies).
+
+    Utterances are sorted by length and cut into batches of ``nb`` slots.  Work items are (batch, direction) pairs;
+    they are spread over LANES = (CTA group, stream): a group runs ``streams`` batches concurrently against one
+    resident weight slice, so all streams of a group work on the same direction at a time (direction 0 first)."""
+
+    def __init__(self, steps, nb, n_dirs, max_groups, device, streams=1):
         steps = np.asarray(steps, dtype=np.int64)
         n_utt = len(steps)
-        self.nb, self.n_utt = nb, n_utt
+        self.nb, self.n_utt, self.streams = nb, n_utt, streams
         self.order = np.argsort(-steps, kind="stable")  # sorted position -> original utterance
         s_sorted = steps[self.order]
         n_batches = (n_utt + nb - 1) // nb
@@ -113,7 +144,7 @@ class Schedule:
         bsteps = np.zeros(n_batches, np.int32)
         bnutt = np.zeros(n_batches, np.int32)
         boff = np.zeros(n_batches, np.int32)
-        bases, utt_rows = [], []
+        bases = []
         # per packed row: sorted-utterance index and step
         row_utt, row_step = [], []
         r = 0
@@ -133,27 +164,17 @@ class Schedule:
             off += len(base)
         self.n_rows = r
         self.n_batches = n_batches
+        self.h_base = bases  # host copies of the per-batch prefix-sum tables
         self.row_sorted_utt = np.concatenate(row_utt) if row_utt else np.zeros(0, np.int64)
         self.row_step = np.concatenate(row_step) if row_step else np.zeros(0, np.int64)
         utt_len = np.zeros(n_batches * nb, np.int32)
         utt_len[:n_utt] = s_sorted
-        # work items, longest first, greedily assigned to the least-loaded group (LPT)
-        items = [(int(bsteps[b]), b, d) for b in range(n_batches) for d in range(n_dirs)]
-        items.sort(key=lambda t: -t[0])
-        n_groups = max(1, min(max_groups, len(items)))
-        load = [0] * n_groups
-        per_group = [[] for _ in range(n_groups)]
-        for cost, b, d in items:
-            g = int(np.argmin(load))
-            load[g] += cost
-            per_group[g].append((b, d))
-        for g in range(n_groups):  # keep a group's items direction-sorted to avoid reloading weights
-            per_group[g].sort(key=lambda t: (t[1], -int(bsteps[t[0]])))
-        flat = [it for g in per_group for it in g]
-        starts = np.concatenate([[0], np.cumsum([len(g) for g in per_group])]).astype(np.int32)
-        self.n_items, self.n_groups = len(flat), n_groups
-        self.max_group_steps = max(load) if load else 0
-        self.total_steps = int(sum(c for c, _, _ in items))
+        per_lane, self.n_groups, self.max_group_steps = assign_lanes(bsteps, n_dirs, max_groups, streams)
+        n_lanes = self.n_groups * streams
+        flat = [it for ln in per_lane for it in ln]
+        starts = np.concatenate([[0], np.cumsum([len(ln) for ln in per_lane])]).astype(np.int32)
+        self.n_items, self.n_lanes = len(flat), n_lanes
+        self.total_steps = int(bsteps.sum()) * n_dirs
 
         def dv(a):
             return torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(device)
@@ -164,35 +185,49 @@ class Schedule:
         self.d_row0, self.d_steps, self.d_nutt, self.d_boff = dv(row0), dv(bsteps), dv(bnutt), dv(boff)
         self.d_base = dv(np.concatenate(bases) if bases else np.zeros(1, np.int32))
         self.d_utt_len = dv(utt_len)
-        self.d_counters = torch.zeros(max(n_groups, 1), dtype=torch.int32, device=device)
+        self.d_counters = torch.zeros(max(n_lanes, 1), dtype=torch.int32, device=device)
 
 
 def pick_schedule(plan, steps, device, nb=None):
-    """Build the packed schedule; with nb=None choose the batch width that minimises the critical path
-    (longest group) under the measured per-step cost."""
+    """Build the packed schedule; with nb=None choose the slots-per-stream (16 x 4 streams, 32 x 2, 64 x 1) that
+    minimises the critical path (longest group) under the measured per-step cost.  The schedule depends only on the
+    utterance lengths, so it is cached on the plan (a repeated call on the same data set re-uses it)."""
+    steps = np.asarray(steps, dtype=np.int64)
+    key = (steps.tobytes(), nb, plan.n_dirs)
+    cache = plan.__dict__.setdefault("_sched_cache", {})
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
     nsplit = 3 if plan.split else 1
-    cands = [nb] if nb else [64, 32]
+    cands = [nb] if nb else [16, 32, 64]
+    s_sorted = -np.sort(-steps, kind="stable")
     best = None
     for cand in cands:
         try:
-            _, max_groups, cycles = ops.rnn_plan(plan.cell, plan.hidden, cand, nsplit, with_cycles=True)
+            _, max_groups, cycles, streams = ops.rnn_plan(plan.cell, plan.hidden, cand, nsplit)
         except NnamError:
             if len(cands) == 1:
                 raise
             continue
-        sc = Schedule(steps, cand, plan.n_dirs, max_groups, device)
-        cost = sc.max_group_steps * cycles
+        _, _, crit = assign_lanes(s_sorted[::cand], plan.n_dirs, max_groups, streams)  # a batch runs as long as its
+        cost = crit * cycles                                                           # longest utterance
         if best is None or cost < best[0]:
-            best = (cost, sc, cand)
+            best = (cost, cand, max_groups, streams)
     if best is None:
         raise NnamError("no recurrent kernel configuration fits this layer size / precision")
-    return best[1], best[2]
+    _, cand, max_groups, streams = best
+    res = (Schedule(steps, cand, plan.n_dirs, max_groups, device, streams), cand)
+    if len(cache) >= 8:
+        cache.pop(next(iter(cache)))
+    cache[key] = res
+    return res
 
 
 def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=None, aux=None):
     H, nd = plan.hidden, plan.n_dirs
     d = RnnDesc()
     d.cell, d.hidden, d.n_dirs, d.batch, d.nsplit = plan.cell, H, nd, nb, 3 if plan.split else 1
+    d.streams = sched.streams
     d.flags = plan.gru_flags
     for k in range(nd):
         d.gx[k] = gx.data_ptr() + 4 * k * 4 * H
@@ -280,22 +315,33 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         split = plan.split
         if any(p.split != split for p in plans):
             raise NnamError("forward_utterances: all ensemble members must use the same precision mode")
-        sched, nb = pick_schedule(plan, lens + timedelay, device, nb)
+        if plan.cell == CELL_PEEPHOLE:  # time-step launches over ONE batch holding every utterance of the shard
+            nb = len(lens)
+            sched = Schedule(lens + timedelay, nb, 1, 1, device, 1)
+        else:
+            sched, nb = pick_schedule(plan, lens + timedelay, device, nb)
         scheds = {(plan.cell, plan.hidden, plan.n_dirs): sched}
         rows = sched.n_rows
-        # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1)
-        utt = sched.order[sched.row_sorted_utt]  # original utterance (shard-relative)
-        step = sched.row_step
-        l_row = lens[utt]
-        start = offsets[u0:u1][utt] - f_lo
-        src = start + np.minimum(step, l_row - 1)
-        dst = start + step - timedelay
-        keep = step >= timedelay
-        if not fix_timedelay_tail:
-            keep &= step < l_row  # predict_folds.py:50,60-61: rows are written only while utt_len > t (quirk Q4)
-        dst = np.where(keep, dst, -1)
-        d_src = torch.from_numpy(src.astype(np.int32)).to(device)
-        d_dst = torch.from_numpy(dst.astype(np.int32)).to(device)
+        # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1); like the schedule
+        # these maps depend only on the utterance lengths and are cached with it
+        maps = plan.__dict__.setdefault("_map_cache", {})
+        mkey = (lens.tobytes(), timedelay, bool(fix_timedelay_tail), nb)
+        if mkey not in maps:
+            utt = sched.order[sched.row_sorted_utt]  # original utterance (shard-relative)
+            step = sched.row_step
+            l_row = lens[utt]
+            start = offsets[u0:u1][utt] - f_lo
+            src = start + np.minimum(step, l_row - 1)
+            dst = start + step - timedelay
+            keep = step >= timedelay
+            if not fix_timedelay_tail:
+                keep &= step < l_row  # predict_folds.py:50,60-61: rows are written only while utt_len > t (quirk Q4)
+            dst = np.where(keep, dst, -1)
+            if len(maps) >= 8:
+                maps.pop(next(iter(maps)))
+            maps[mkey] = (torch.from_numpy(src.astype(np.int32)).to(device),
+                          torch.from_numpy(dst.astype(np.int32)).to(device))
+        d_src, d_dst = maps[mkey]
 
         if isinstance(x, torch.Tensor) and x.is_cuda:
             x_dev = x[f_lo:f_hi]
@@ -328,9 +374,15 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
             if m.in_size != d_in or m.n_out != n_out:
                 raise NnamError("forward_utterances: ensemble members must share input and output sizes")
             key = (pl.cell, pl.hidden, pl.n_dirs)
-            if key not in scheds:  # same utterances and batch width => same packed row order, other grouping
-                scheds[key], _ = pick_schedule(pl, lens + timedelay, device, nb)
-            h_hi, h_lo, _ = run_layers(m, pl, scheds[key], a_hi, a_lo, rows, nb, ws=ws)
+            if (pl.cell == CELL_PEEPHOLE) != (plan.cell == CELL_PEEPHOLE):
+                raise NnamError("forward_utterances: peephole and non-peephole nets cannot share one ensemble pass")
+            if pl.cell == CELL_PEEPHOLE:
+                from . import peephole_engine
+                h_hi, h_lo = peephole_engine.run_layers(m, pl, sched, a_hi, a_lo, rows, ws=ws)
+            else:
+                if key not in scheds:  # same utterances and batch width => same packed row order, other grouping
+                    scheds[key], _ = pick_schedule(pl, lens + timedelay, device, nb)
+                h_hi, h_lo, _ = run_layers(m, pl, scheds[key], a_hi, a_lo, rows, nb, ws=ws)
             lg = ws.get(f"rnn.logits{k}", rows, round_up(n_out, 16), torch.float32)
             pl.out(h_hi, h_lo, rows, "identity", OUT_F32, out=(lg, None))
             logits.append(lg)
@@ -350,16 +402,19 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
 def step(model, plan, xd):
     """Stateful ``model(x)`` for recurrent specs: one time step for a batch of B rows
     (chainer_networks.py:58-62); ``reset_state()`` clears the carried (h, c)."""
+    if plan.cell == CELL_PEEPHOLE:
+        from . import peephole_engine
+        return peephole_engine.step(model, plan, xd)
     B = xd.shape[0]
     nb = 32
     split = plan.split
     if model.bidirectional:
         raise NnamError("bidirectional models have no per-step form; use predict()/forward_utterances()")
-    g_ctas, max_groups = ops.rnn_plan(plan.cell, plan.hidden, nb, 3 if split else 1)
+    _, max_groups, _, streams = ops.rnn_plan(plan.cell, plan.hidden, nb, 3 if split else 1)
     st = model._state
     if st is not None and st["B"] != B:
         raise NnamError("model(x): batch size changed between steps; call reset_state() first")
-    sched = st["sched"] if st is not None else Schedule(np.ones(B, np.int64), nb, 1, max_groups, plan.device)
+    sched = st["sched"] if st is not None else Schedule(np.ones(B, np.int64), nb, 1, max_groups, plan.device, streams)
     a_hi, a_lo = ops.convert_f32(xd.contiguous(), plan.act_kind)
     h_hi, h_lo, new = run_layers(model, plan, sched, a_hi, a_lo, B, nb, state_in=None if st is None else st["s"],
                                  want_state=True, tag="step")

@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Per-phase SM-cycle breakdown of the K3 recurrence kernel (cfg3 geometry)."""
+"""Per-phase SM-cycle breakdown of the K3 recurrence kernel (cfg3 geometry): clock64 counters of thread 0 of stream 0
+in every CTA (NnamRnnDesc.debug_cycles).  usage: gpu_profile_rnn.py [slots per stream: 16|32|64] [bf16|fp32] [lstm|gru]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,9 +10,10 @@ from oracle import nnam_oracle as O
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
+net = sys.argv[3] if len(sys.argv) > 3 else "lstm"
 x, off, _ = O.synth_set(1234, 1344)
-p = O.init_recurrent(np.random.default_rng(1), "lstm", 40, 512, 4, 1909)
-m = nn.get_nn("lstm", 4, [512], 1909, nn.F.relu, [5]); m.load_params(p); m.precision = prec
+p = O.init_recurrent(np.random.default_rng(1), net, 40, 512, 4, 1909)
+m = nn.get_nn(net, 4, [512], 1909, nn.F.relu, [5]); m.load_params(p); m.precision = prec
 dev = torch.device("cuda:0")
 xd = torch.from_numpy(x).to(dev); out = torch.empty((len(x), 1909), device=dev)
 for _ in range(2):
@@ -20,12 +22,13 @@ R.PROFILE_CYCLES = []
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record(); R.forward_utterances(m, xd, off, out, 0, len(off) - 1, timedelay=5, device=0, nb=nb); e.record()
 torch.cuda.synchronize()
-print(f"nb={nb} {prec}: total {s.elapsed_time(e):.1f} ms")
+print(f"{net} nb={nb} {prec}: total {s.elapsed_time(e):.1f} ms")
 names = ["gx_issue", "wait_group", "h_load", "mma", "tmem_ld", "gates+store", "fence+publish", "steps"]
 for l, buf in enumerate(R.PROFILE_CYCLES):
     a = buf.cpu().numpy().reshape(-1, 8)
     a = a[a[:, 7] > 0]
     steps = a[:, 7]
-    print(f"layer {l}: CTAs {len(a)}, steps/CTA min {steps.min()} max {steps.max()}")
     per = a[:, :7].sum(axis=0) / steps.sum()
-    print("   cycles/step: " + ", ".join(f"{n}={v:.0f}" for n, v in zip(names, per)) + f"  sum={per.sum():.0f}")
+    if l in (0, len(R.PROFILE_CYCLES) - 1):
+        print(f"layer {l}: CTAs {len(a)}, stream-0 steps/CTA min {steps.min()} max {steps.max()}")
+        print("   cycles/step: " + ", ".join(f"{n}={v:.0f}" for n, v in zip(names, per)) + f"  sum={per.sum():.0f}")

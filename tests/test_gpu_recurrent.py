@@ -172,3 +172,34 @@ def test_gru_stateful_call(nn):
     m.reset_state()
     for t in range(5):
         assert np.abs(m(xs[t]) - ref(xs[t])).max() < 1e-3
+
+
+@pytest.mark.parametrize("units,layers,lens,td", [(64, 2, [7, 3, 12, 1, 9], 0), (128, 2, [30, 41, 17, 25, 33, 8] * 3, 2),
+                                                  (512, 2, [40, 55, 31], 5)])
+def test_predict_peephole_lstm(nn, golden_dir, units, layers, lens, td):
+    """L.StatefulPeepholeLSTM (chainer_networks.py:103-121): full-matrix peepholes, time-step launches on the device."""
+    off = _offsets(lens)
+    x = np.random.default_rng(sum(lens) + 2).standard_normal((off[-1], 40)).astype(np.float32)
+    n_out = 1909 if units == 512 else 39
+    p = O.init_recurrent(np.random.default_rng(units), "peepholelstm", 40, units, layers, n_out)
+    rng = np.random.default_rng(units + 1)
+    for k in p:
+        if k.endswith("upward/b"):
+            p[k] = p[k] + (0.1 * rng.standard_normal(p[k].shape)).astype(np.float32)
+    m = nn.get_nn("peepholelstm", layers, [units], n_out, nn.F.relu, [5])
+    m.load_params(p)
+    ft = nn.adapt_transform(nn.loadKaldiFeatureTransform(os.path.join(golden_dir, "final.feature_transform")),
+                            "peepholelstm", 0, True)
+    want = O.predict(O.RecurrentNet(p, "peepholelstm", layers), x, off, "peepholelstm", 1, td, ft)
+    got = nn.predict(m, x, off, n_out, "peepholelstm", 0, 1, td, ft, progress=False)
+    assert np.abs(got - want).max() < 1e-3
+    m.precision = "bf16"
+    got16 = nn.predict(m, x, off, n_out, "peepholelstm", 0, 1, td, ft, progress=False)
+    assert np.abs(got16 - want).max() < 5e-2
+    # stateful per-step surface
+    m.precision = "fp32"
+    ref = O.RecurrentNet(p, "peepholelstm", layers)
+    xs = np.random.default_rng(3).standard_normal((4, 6, 40)).astype(np.float32)
+    m.reset_state()
+    for t in range(4):
+        assert np.abs(m(xs[t]) - ref(xs[t])).max() < 1e-3

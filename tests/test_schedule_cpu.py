@@ -29,6 +29,32 @@ def test_schedule_covers_every_utterance_step_once():
     assert gs[0] == 0 and gs[-1] == 6 and len(gs) == s.n_groups + 1
 
 
+def test_schedule_lanes_with_streams():
+    """Several streams per CTA group: lanes = groups x streams, every lane's items are direction-sorted (a group
+    works on one direction at a time), and the critical path accounts for the per-group direction switch."""
+    rng = np.random.default_rng(1)
+    steps = rng.integers(5, 60, size=300)
+    s = Schedule(steps, 16, 2, 3, torch.device("cpu"), streams=4)
+    assert s.n_batches == 19 and s.n_groups == 3 and s.n_lanes == 12
+    gs = s.d_group_start.tolist()
+    assert len(gs) == s.n_lanes + 1 and gs[-1] == s.n_items == 38
+    dirs, batches = s.d_item_dir.tolist(), s.d_item_batch.tolist()
+    for ln in range(s.n_lanes):
+        d = dirs[gs[ln]:gs[ln + 1]]
+        assert d == sorted(d)
+    assert sorted(zip(batches, dirs)) == [(b, d) for b in range(19) for d in range(2)]
+    bsteps = s.d_steps.numpy()
+    load = np.zeros((12, 2), np.int64)
+    for ln in range(12):
+        for i in range(gs[ln], gs[ln + 1]):
+            load[ln, dirs[i]] += bsteps[batches[i]]
+    assert s.max_group_steps == load.reshape(3, 4, 2).max(axis=1).sum(axis=1).max()
+    assert s.d_counters.numel() == 12
+    # fewer batches than lanes: no empty groups are launched
+    s = Schedule([9] * 20, 16, 1, 9, torch.device("cpu"), streams=4)
+    assert s.n_batches == 2 and s.n_groups == 1 and s.n_lanes == 4
+
+
 def test_schedule_single_and_equal_lengths():
     s = Schedule([5], 32, 1, 9, torch.device("cpu"))
     assert s.n_rows == 5 and s.n_groups == 1 and s.d_base.tolist() == [0, 1, 2, 3, 4, 5]
