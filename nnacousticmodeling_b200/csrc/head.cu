@@ -134,6 +134,132 @@ __global__ void __launch_bounds__(HEAD_THREADS, (MULTI || NV < 64) ? 1 : 2) head
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Fast path for the common case: ONE input, optional prior, optional scatter map (predict() and the evaluate path of a
+// single net).  The first ncu pass of the generic kernel (profiles/r01_cfg2_gemm_before.md) showed ~2100 warp
+// instructions per row -- per-element predicates, 4-byte loads and stores -- i.e. issue-bound at 40 % of the DRAM
+// roofline.  Here a lane owns whole 16-byte chunks: chunk k = lane + 32 i holds columns 4k .. 4k+3.
+//   * loads are 128-bit and unpredicated for every chunk that lies inside the row (only the last i is checked);
+//   * exp is ex2.approx of a pre-scaled argument (one FFMA + one MUFU per element);
+//   * the output matrix is (rows, C) with C = 1909: a row starts at an address that is only 4-byte aligned, so the
+//     lanes RE-ALIGN the row with shuffles (each takes the last `a` elements of its left neighbour's chunk, where
+//     a = (row start / 4) mod 4) and store 16-byte aligned chunks; only the row's ragged ends are scalar stores.
+constexpr int HEAD_FAST_THREADS = 128;
+
+template <int NV4>
+__global__ void __launch_bounds__(HEAD_FAST_THREADS, 4) head_fast_kernel(const HeadParams p) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * HEAD_FAST_THREADS + threadIdx.x) >> 5;
+  const long long n_warps = (static_cast<long long>(gridDim.x) * HEAD_FAST_THREADS) >> 5;
+  const int C = p.n_classes;
+  const int n_full = C >> 7;  // iterations whose 32 chunks all lie inside the row
+  const float w0 = p.w[0];
+  constexpr float LOG2E = 1.4426950408889634f;
+  for (long long row = warp_global; row < p.rows; row += n_warps) {
+    const float4* src = reinterpret_cast<const float4*>(p.in[0] + row * p.ld_in);
+    float4 v[NV4];
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int k = lane + 32 * i;
+      if (i < n_full) {
+        v[i] = __ldcs(src + k);
+      } else {
+        // ragged end of the row: the buffer is only guaranteed to hold ld_in >= C floats per row
+        const float* s1 = reinterpret_cast<const float*>(src) + 4 * k;
+        v[i].x = 4 * k < C ? __ldcs(s1) : 0.0f;
+        v[i].y = 4 * k + 1 < C ? __ldcs(s1 + 1) : 0.0f;
+        v[i].z = 4 * k + 2 < C ? __ldcs(s1 + 2) : 0.0f;
+        v[i].w = 4 * k + 3 < C ? __ldcs(s1 + 3) : 0.0f;
+      }
+    }
+    if (w0 != 1.0f) {
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        v[i].x *= w0; v[i].y *= w0; v[i].z *= w0; v[i].w *= w0;
+      }
+    }
+    if (p.prior != nullptr) {
+      const float ps = p.prior_scale;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const int k = lane + 32 * i;
+        if (i < n_full) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(p.prior) + k);
+          v[i].x -= ps * a.x; v[i].y -= ps * a.y; v[i].z -= ps * a.z; v[i].w -= ps * a.w;
+        } else {
+          if (4 * k < C) v[i].x -= ps * __ldg(p.prior + 4 * k);
+          if (4 * k + 1 < C) v[i].y -= ps * __ldg(p.prior + 4 * k + 1);
+          if (4 * k + 2 < C) v[i].z -= ps * __ldg(p.prior + 4 * k + 2);
+          if (4 * k + 3 < C) v[i].w -= ps * __ldg(p.prior + 4 * k + 3);
+        }
+      }
+    }
+    float lse = 0.0f;
+    if (p.final_normalize) {
+      // columns past the end of the row become -inf: neutral for the max, and exp2 maps them to 0
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        if (i < n_full) continue;
+        const int k = lane + 32 * i;
+        if (4 * k >= C) v[i].x = -CUDART_INF_F;
+        if (4 * k + 1 >= C) v[i].y = -CUDART_INF_F;
+        if (4 * k + 2 >= C) v[i].z = -CUDART_INF_F;
+        if (4 * k + 3 >= C) v[i].w = -CUDART_INF_F;
+      }
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
+      mx = warp_max(mx);
+      const float mxs = mx * LOG2E;
+      float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        s0 += exp2f(fmaf(v[i].x, LOG2E, -mxs)) + exp2f(fmaf(v[i].y, LOG2E, -mxs));
+        s1 += exp2f(fmaf(v[i].z, LOG2E, -mxs)) + exp2f(fmaf(v[i].w, LOG2E, -mxs));
+      }
+      lse = mx + logf(warp_sum(s0 + s1));
+    }
+    long long out_row = row;
+    if (p.out_row_map != nullptr) {
+      out_row = __ldg(p.out_row_map + row);
+      if (out_row < 0) continue;  // warp-uniform: one row per warp
+    }
+    float* dst = p.out + out_row * p.ld_out;
+    const int a = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);  // row start modulo 16 bytes, in floats
+    float4* dst4 = reinterpret_cast<float4*>(dst - a);                              // aligned chunk 0 of the row
+    float c1 = 0.0f, c2 = 0.0f, c3 = 0.0f;  // last elements of lane 31's previous chunk (for lane 0)
+#pragma unroll
+    for (int i = 0; i < NV4; ++i) {
+      const int k = lane + 32 * i;
+      float4 x = v[i];
+      x.x -= lse; x.y -= lse; x.z -= lse; x.w -= lse;
+      // y = aligned chunk k of the output row = columns 4k-a .. 4k-a+3
+      float p1 = __shfl_up_sync(0xffffffffu, x.y, 1), p2 = __shfl_up_sync(0xffffffffu, x.z, 1),
+            p3 = __shfl_up_sync(0xffffffffu, x.w, 1);
+      if (lane == 0) { p1 = c1; p2 = c2; p3 = c3; }
+      c1 = __shfl_sync(0xffffffffu, x.y, 31);
+      c2 = __shfl_sync(0xffffffffu, x.z, 31);
+      c3 = __shfl_sync(0xffffffffu, x.w, 31);
+      float4 y;
+      if (a == 0) y = x;
+      else if (a == 1) y = make_float4(p3, x.x, x.y, x.z);
+      else if (a == 2) y = make_float4(p2, p3, x.x, x.y);
+      else y = make_float4(p1, p2, p3, x.x);
+      const int col0 = 4 * k - a;
+      if (col0 >= 0 && col0 + 3 < C) {
+        __stcs(dst4 + k, y);
+      } else {  // ragged ends of the row
+        if (col0 >= 0 && col0 < C) __stcs(dst + col0, y.x);
+        if (col0 + 1 >= 0 && col0 + 1 < C) __stcs(dst + col0 + 1, y.y);
+        if (col0 + 2 >= 0 && col0 + 2 < C) __stcs(dst + col0 + 2, y.z);
+        if (col0 + 3 >= 0 && col0 + 3 < C) __stcs(dst + col0 + 3, y.w);
+      }
+    }
+    // the last `a` elements of chunk 32*NV4-1 would belong to aligned chunk 32*NV4: they exist only when C > 128*NV4 - a,
+    // which the host excludes by choosing NV4 with 128*NV4 >= C + 3
+  }
+}
+
 int head(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in, int pre_normalize,
          const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior, float prior_scale,
          int final_normalize, float* out, long long ld_out, long long rows, int n_classes, const int* out_row_map,
@@ -166,6 +292,25 @@ int head(const float* const* logits_host, const float* weights_host, int n_input
   p.rows = rows;
   p.n_classes = n_classes;
   p.out_row_map = out_row_map;
+  // fast path: one input, no RPL4 / per-input normalisation, 16-byte aligned input rows
+  const bool fast_ok = n_inputs == 1 && !pre_normalize && rpl_w == nullptr && ld_in % 4 == 0 &&
+                       (reinterpret_cast<uintptr_t>(logits_host[0]) & 15) == 0 &&
+                       (prior == nullptr || (reinterpret_cast<uintptr_t>(prior) & 15) == 0) &&
+                       (reinterpret_cast<uintptr_t>(out) & 3) == 0 && n_classes + 3 <= 2048;
+  if (fast_ok) {
+    const int wpb = HEAD_FAST_THREADS / 32;
+    long long fb = (rows + wpb - 1) / wpb;
+    const long long fcap = static_cast<long long>(sm_count()) * 16;
+    if (fb > fcap) fb = fcap;
+    const unsigned fg = static_cast<unsigned>(fb);
+    const int need = n_classes + 3;  // see the kernel's closing comment
+    if (need <= 128) head_fast_kernel<1><<<fg, HEAD_FAST_THREADS, 0, stream>>>(p);
+    else if (need <= 512) head_fast_kernel<4><<<fg, HEAD_FAST_THREADS, 0, stream>>>(p);
+    else if (need <= 1024) head_fast_kernel<8><<<fg, HEAD_FAST_THREADS, 0, stream>>>(p);
+    else if (need <= 1920) head_fast_kernel<15><<<fg, HEAD_FAST_THREADS, 0, stream>>>(p);
+    else head_fast_kernel<16><<<fg, HEAD_FAST_THREADS, 0, stream>>>(p);
+    return check_launch("head_fast_kernel");
+  }
   const int warps_per_block = HEAD_THREADS / 32;
   long long blocks = (rows + warps_per_block - 1) / warps_per_block;
   const long long cap = static_cast<long long>(sm_count()) * 8;  // grid-stride beyond 8 resident blocks per SM
