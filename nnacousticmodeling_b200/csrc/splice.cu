@@ -127,34 +127,64 @@ __global__ void __launch_bounds__(SPLICE_THREADS) splice_transform_kernel(const 
     __nv_bfloat16* out_hi = static_cast<__nv_bfloat16*>(p.out_hi) + (tile_f0 - p.f0) * p.ldo;
     __nv_bfloat16* out_lo =
         OUT_KIND == NNAM_OUT_BF16_SPLIT ? static_cast<__nv_bfloat16*>(p.out_lo) + (tile_f0 - p.f0) * p.ldo : nullptr;
-    const int vpr = static_cast<int>(p.ldo >> 3);
-    for (int i = threadIdx.x; i < tile_n * vpr; i += SPLICE_THREADS) {
-      const int r = i / vpr, c = (i - r * vpr) << 3;
-      float v[8];
-      if (VEC && c + 8 <= p.spl_cols) {
-        const float4 v0 = *reinterpret_cast<const float4*>(s_x + r * p.dim + c);
-        const float4 v1 = *reinterpret_cast<const float4*>(s_x + r * p.dim + c + 4);
-        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
-        v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-        if (has_ft) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __fmul_rn(__fadd_rn(v[j], s_add[c + j]), s_mul[c + j]);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = splice_elem(p, s_x, t_add, s_mul, r, tile_f0 + r, c + j);
+    // A thread owns ONE 16-byte output chunk column (8 elements) and walks the tile's rows: the transform of its
+    // columns stays in registers, so a chunk costs two 128-bit shared loads and one 128-bit store (the first version
+    // re-read the transform from shared memory for every chunk and ran at 94 % L1/shared-pipe utilisation).
+    const int vpr = static_cast<int>(p.ldo >> 3);            // chunks per output row
+    const bool narrow = vpr <= SPLICE_THREADS;               // the usual case: one chunk column per thread
+    const int lanes_r = narrow ? SPLICE_THREADS / vpr : 1;   // rows processed per sweep of the block
+    const int tid = static_cast<int>(threadIdx.x);
+    const int r_first = narrow ? tid / vpr : 0;
+    const bool active = !narrow || tid < vpr * lanes_r;
+    for (int cc = narrow ? tid % vpr : tid; active && cc < vpr; cc += narrow ? vpr : SPLICE_THREADS) {
+      const int c = cc << 3;
+      const int kind = (VEC && c + 8 <= p.spl_cols) ? 0
+                       : (VEC && c >= p.spl_cols && c + 8 <= p.spl_cols + p.ivec_dim && (p.spl_cols & 7) == 0) ? 1 : 2;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, m0 = make_float4(1.f, 1.f, 1.f, 1.f), m1 = m0;
+      if (kind == 0 && has_ft) {
+        a0 = *reinterpret_cast<const float4*>(s_add + c);
+        a1 = *reinterpret_cast<const float4*>(s_add + c + 4);
+        m0 = *reinterpret_cast<const float4*>(s_mul + c);
+        m1 = *reinterpret_cast<const float4*>(s_mul + c + 4);
       }
-      uint32_t h[4];
+      for (int r = r_first; r < tile_n; r += lanes_r) {
+        float v[8];
+        if (kind == 0) {
+          const float4 v0 = *reinterpret_cast<const float4*>(s_x + r * p.dim + c);
+          const float4 v1 = *reinterpret_cast<const float4*>(s_x + r * p.dim + c + 4);
+          v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
+          v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+          if (has_ft) {
+            v[0] = __fmul_rn(__fadd_rn(v[0], a0.x), m0.x);
+            v[1] = __fmul_rn(__fadd_rn(v[1], a0.y), m0.y);
+            v[2] = __fmul_rn(__fadd_rn(v[2], a0.z), m0.z);
+            v[3] = __fmul_rn(__fadd_rn(v[3], a0.w), m0.w);
+            v[4] = __fmul_rn(__fadd_rn(v[4], a1.x), m1.x);
+            v[5] = __fmul_rn(__fadd_rn(v[5], a1.y), m1.y);
+            v[6] = __fmul_rn(__fadd_rn(v[6], a1.z), m1.z);
+            v[7] = __fmul_rn(__fadd_rn(v[7], a1.w), m1.w);
+          }
+        } else if (kind == 1) {  // i-vector columns: straight from global memory, 128-bit
+          const float4* iv = reinterpret_cast<const float4*>(p.ivec + (tile_f0 + r - p.f0) * p.ivec_dim + (c - p.spl_cols));
+          const float4 v0 = __ldg(iv), v1 = __ldg(iv + 1);
+          v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
+          v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+        } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-      reinterpret_cast<uint4*>(out_hi + static_cast<long long>(r) * p.ldo)[c >> 3] = make_uint4(h[0], h[1], h[2], h[3]);
-      if (OUT_KIND == NNAM_OUT_BF16_SPLIT) {
-        uint32_t l[4];
+          for (int j = 0; j < 8; ++j) v[j] = splice_elem(p, s_x, t_add, s_mul, r, tile_f0 + r, c + j);
+        }
+        uint32_t h[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          l[j] = pack_bf16x2(v[2 * j] - bf16_round(v[2 * j]), v[2 * j + 1] - bf16_round(v[2 * j + 1]));
-        reinterpret_cast<uint4*>(out_lo + static_cast<long long>(r) * p.ldo)[c >> 3] =
-            make_uint4(l[0], l[1], l[2], l[3]);
+        for (int j = 0; j < 4; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+        reinterpret_cast<uint4*>(out_hi + static_cast<long long>(r) * p.ldo)[c >> 3] = make_uint4(h[0], h[1], h[2], h[3]);
+        if (OUT_KIND == NNAM_OUT_BF16_SPLIT) {
+          uint32_t l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            l[j] = pack_bf16x2(v[2 * j] - bf16_round(v[2 * j]), v[2 * j + 1] - bf16_round(v[2 * j + 1]));
+          reinterpret_cast<uint4*>(out_lo + static_cast<long long>(r) * p.ldo)[c >> 3] =
+              make_uint4(l[0], l[1], l[2], l[3]);
+        }
       }
     }
   }
