@@ -42,6 +42,12 @@ WORKLOADS = {
                  desc="cfg3: 4x512 LSTM, 40 fMLLR -> 1909, timedelay 5, test-shaped 1344 utts"),
     "cfg4": dict(network="blstm", ivec=100, units=512, layers=4, utts=TEST_UTTS, frames=None, flop=46999552,
                  desc="cfg4: 4x(2x512) bidirectional LSTM, 40 fMLLR + 100 i-vector -> 1909, test-shaped 1344 utts"),
+    # cfg5: ensembles of 10 fold models, logit mean fused into the head (evaluate.py:35-51)
+    "cfg5": dict(network="ff", ivec=0, units=1024, layers=6, utts=TEST_UTTS, frames=None, flop=10 * 15296512, folds=10,
+                 desc="cfg5: ensemble of 10 fold 6x1024 MLPs (logit mean), 440 spliced fMLLR -> 1909, test-shaped 1344 utts"),
+    "cfg5b": dict(network="blstm", ivec=100, units=512, layers=4, utts=TEST_UTTS, frames=None, flop=10 * 46999552,
+                  folds=10,
+                  desc="cfg5b: ensemble of 10 fold 4x(2x512) BLSTMs (logit mean), 40 fMLLR + 100 i-vector -> 1909, test-shaped 1344 utts"),
 }
 
 
@@ -134,8 +140,12 @@ def cpu_reference_rate(wname, sample_frames, steps=1, warmup=0):
     """Frames/s of the reference-equivalent NumPy CPU forward (oracle port) on a bounded sample."""
     from oracle import nnam_oracle as O
     w, x, offsets, iv = make_workload(wname, 0)
-    p = make_params(w)
+    folds = w.get("folds", 1)
+    ps = [make_params(w, 4321 + k) for k in range(folds)]
+    p = ps[0]
     ft = transform()
+    if folds > 1:
+        sample_frames = max(sample_frames // folds, 2048)
     if w["network"] == "ff":
         n = min(sample_frames, len(x))
         xs, ivs = x[:n], (iv[:n] if iv is not None else None)
@@ -148,14 +158,18 @@ def cpu_reference_rate(wname, sample_frames, steps=1, warmup=0):
                 f = O.apply_kaldi_feature_transform(O.prepare_batch(xs, np.arange(o, e), 11), ft)
                 if ivs is not None:
                     f = np.concatenate((f, ivs[o:e]), axis=1)
-                ys.append(O.log_softmax(O.mlp_forward(p, f, w["layers"])))
+                if folds > 1:  # evaluate.py:35-51: mean of the fold logits, then log-softmax
+                    ys.append(O.log_softmax(O.nn_with_rpl(None, [(lambda v, q=q: O.mlp_forward(q, v, w["layers"]))
+                                                                 for q in ps], None, f)))
+                else:
+                    ys.append(O.log_softmax(O.mlp_forward(p, f, w["layers"])))
             return np.concatenate(ys)
         sample = f"first {n} frames, predict() FF loop batch 1024"
     else:
         n_utt = int(min(max(sample_frames // 1024, 16), 256, len(offsets) - 1))  # the loop batches all of them per step
         bid = w["network"] == "blstm"
         if bid:  # no batched reference loop exists for the bidirectional nets: per-utterance, so a smaller sample
-            n_utt = max(n_utt // 4, 16)
+            n_utt = max(n_utt // 4, 16) if folds == 1 else max(n_utt // (4 * folds), 2)
         off = offsets[:n_utt + 1]
         n = int(off[-1])
         ftm = O.select_transform_for_network(ft, "lstm")
@@ -163,8 +177,8 @@ def cpu_reference_rate(wname, sample_frames, steps=1, warmup=0):
 
         def run():
             if bid:
-                return [O.log_softmax(O.birnn_forward_utterance(p, "lstm", w["layers"], xs[off[i]:off[i + 1]]))
-                        for i in range(n_utt)]
+                return [O.log_softmax(sum(O.birnn_forward_utterance(q, "lstm", w["layers"], xs[off[i]:off[i + 1]])
+                                          for q in ps) / np.float32(folds)) for i in range(n_utt)]
             net = O.RecurrentNet(p, "lstm", w["layers"])
             return O.predict(net, xs, off, "lstm", 1, 5, ftm if iv is None else None)
         sample = f"first {n_utt} utterances ({n} frames), time-major loop"
@@ -217,10 +231,16 @@ def run_ours(args):
     ft_full = transform()
     net = w["network"]
     recurrent = nn.is_nn_recurrent(net)
-    model = nn.get_nn(net, w["layers"], [w["units"]], N_CLASSES, nn.F.relu, [5])
-    model.load_params(make_params(w))
-    model.precision = args.precision
-    model.to_gpu(local)
+    folds = w.get("folds", 1)
+    members = []
+    for k in range(folds):
+        m = nn.get_nn(net, w["layers"], [w["units"]], N_CLASSES, nn.F.relu, [5])
+        m.load_params(make_params(w, 4321 + k))
+        m.precision = args.precision
+        m.to_gpu(local)
+        members.append(m)
+    model = members[0] if folds == 1 else members
+    head = None if folds == 1 else nn.HeadSpec(weights=[1.0 / folds] * folds)
     ft = nn.adapt_transform(ft_full, net, 5, recurrent)
     timedelay = 5 if net == "lstm" else 0
 
@@ -241,14 +261,14 @@ def run_ours(args):
 
         def step_device():
             recurrent_engine.forward_utterances(model, x_dev, offsets, out_dev, 0, len(offsets) - 1, ft=ft,
-                                                ivectors=iv_dev, timedelay=timedelay, device=local)
+                                                ivectors=iv_dev, timedelay=timedelay, device=local, head=head)
     else:
         def step_device():
-            engine.ff_forward_frames(model, x_dev, ft, 5, out_dev, ivectors=iv_dev, device=local)
+            engine.ff_forward_frames(model, x_dev, ft, 5, out_dev, ivectors=iv_dev, device=local, head=head)
 
     def step_e2e():
         nn.predict(model, xp, offsets if recurrent else None, N_CLASSES, net, local, 11, timedelay, ft,
-                   progress=False, ivectors=ivp, out=out_host)
+                   progress=False, ivectors=ivp, out=out_host, head=head)
 
     def barrier():
         torch.cuda.synchronize()
