@@ -20,6 +20,8 @@
 //   warp 2 : TMEM allocator
 //   warps 4-7 : epilogue -- tcgen05.ld 32x32b, + bias, activation, (hi/lo split), vector stores
 // Tile order is n-fastest so that CTAs running concurrently share the A tile in L2 while W stays L2-resident.
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "nnam_internal.h"
 
@@ -291,24 +293,287 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
   }
 }
 
+// =====================================================================================================
+// CTA-pair variant (cta_group::2): the two CTAs of a cluster (one TPC) compute ONE 256 x bn tile.
+//
+// Why: with a 128 x 256 tile per SM the main loop pulls A 16 KiB + W 32 KiB per 512 tensor-core clocks = 96 B/clk from
+// L2 into each SM and reads the same 96 B/clk back out of shared memory for the MMA; 4 stages of 48 KiB cover only
+// ~2 k clocks of L2 latency, and the second ncu pass (profiles/r01_cfg2_gemm_v2.md) shows the tensor pipe capped at
+// ~85 % with ~3 k clocks lost per tile.  In a pair, each CTA loads its own 128 rows of A and only HALF of the W tile
+// (32 KiB per stage, so SIX stages fit), the leader issues tcgen05.mma.cta_group::2 with M = 256, and each CTA's
+// tensor core accumulates its 128 rows in its own TMEM: 64 B/clk per SM from L2 and from shared memory.
+//
+// Protocol (same barriers at the same offsets in both CTAs; rank 0 = leader):
+//   full[s]    leader only: arrive.expect_tx by the leader's producer for BOTH CTAs' bytes; both producers' TMA loads
+//              complete_tx on it (cp.async.bulk.tensor ... cta_group::2 may signal the peer's mbarrier)
+//   empty[s]   each CTA: tcgen05.commit.cta_group::2 ... multicast (mask 0b11) from the leader's MMA thread
+//   tfull[a]   each CTA: same multicast commit after the last k-block of a tile
+//   tempty[a]  leader only, count 8: the four epilogue warps of BOTH CTAs arrive (the follower's remotely)
+constexpr int STAGES2 = 6;
+constexpr int B2_STAGE_BYTES = (MAX_BN / 2) * BK * 2;  // 16 KiB: this CTA's half of the W tile
+constexpr int GEMM2_SMEM_BYTES = STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) + EPI_BYTES + 256 + 1024;
+
+template <int OUT_KIND>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+    gemm_bias_act_2sm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                             const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
+                             const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
+                             const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES2 * A_STAGE_BYTES;
+  uint8_t* smem_epi = smem_b + STAGES2 * B2_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tfull_bar = empty_bar + STAGES2;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int n_pairs = gridDim.x >> 1;
+  const int total_tiles = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row blocks here
+  const int k_iters = p.k_blocks * p.nsplit;
+  const int half_bn = p.bn >> 1;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a_hi);
+    prefetch_tmap(&tm_w_hi);
+    prefetch_tmap(&tm_o_hi);
+    if (p.nsplit > 1) {
+      prefetch_tmap(&tm_a_lo);
+      prefetch_tmap(&tm_w_lo);
+    }
+    if (OUT_KIND == NNAM_OUT_BF16_SPLIT) prefetch_tmap(&tm_o_lo);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 8);  // four epilogue warps of each CTA of the pair
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2sm(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  // both CTAs' barriers are initialised (and both TMEM allocations done) before any cross-CTA signal
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = static_cast<uint32_t>(2 * (BM + half_bn) * BK * 2);  // both CTAs' boxes
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        const int m_blk = tile / p.tiles_n;
+        const int n_blk = tile % p.tiles_n;
+        const int row_a = m_blk * (2 * BM) + static_cast<int>(rank) * BM;
+        const int row_w = n_blk * p.bn + static_cast<int>(rank) * half_bn;
+        for (int pass = 0; pass < p.nsplit; ++pass) {
+          const CUtensorMap* ma = (pass == 2) ? &tm_a_lo : &tm_a_hi;
+          const CUtensorMap* mw = (pass == 1) ? &tm_w_lo : &tm_w_hi;
+          for (int kb = 0; kb < p.k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
+            if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
+            tma_load_2d_2sm(smem_a + stage * A_STAGE_BYTES, ma, full_leader, kb * BK, row_a);
+            tma_load_2d_2sm(smem_b + stage * B2_STAGE_BYTES, mw, full_leader, kb * BK, row_w);
+            if (++stage == STAGES2) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA only)
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint32_t idesc = make_idesc_bf16_f32(2 * BM, static_cast<uint32_t>(p.bn));
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        mbar_wait_cluster_acquire(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * MAX_BN);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * B2_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t adesc = make_sw128_kmajor_desc(a_addr + k * UK * 2);
+            const uint64_t bdesc = make_sw128_kmajor_desc(b_addr + k * UK * 2);
+            umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 0b11);  // frees the slot in both CTAs
+          if (it == k_iters - 1) umma_commit_2sm(&tfull_bar[acc], 0b11);
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // -------------------------------------------------------------- epilogue (both CTAs, own 128 rows)
+    constexpr int BOX_COLS = OUT_KIND == NNAM_OUT_F32 ? 32 : 64;
+    const int q = warp & 3;
+    uint8_t* boxes = smem_epi + q * 2 * EPI_BOX_BYTES;
+    int box_sel = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      const int m_blk = tile / p.tiles_n;
+      const int n_blk = tile % p.tiles_n;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * MAX_BN);
+      const int row0 = m_blk * (2 * BM) + static_cast<int>(rank) * BM + q * 32;
+      for (int c0 = 0; c0 < p.bn; c0 += BOX_COLS) {
+        const int col = n_blk * p.bn + c0;
+        if (col >= p.N || row0 >= p.M) break;
+        float v[BOX_COLS];
+#pragma unroll
+        for (int j0 = 0; j0 < BOX_COLS; j0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + c0 + j0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j0 + j] = __uint_as_float(r[j]);
+        }
+        if (p.bias != nullptr) {
+          if (col + BOX_COLS <= p.N) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+#pragma unroll
+            for (int j = 0; j < BOX_COLS / 4; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j] += b.x;
+              v[4 * j + 1] += b.y;
+              v[4 * j + 2] += b.z;
+              v[4 * j + 3] += b.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < BOX_COLS; ++j)
+              if (col + j < p.N) v[j] += __ldg(p.bias + col + j);
+          }
+        }
+        apply_act<BOX_COLS>(v, p.act);
+        constexpr int N_OUT = OUT_KIND == NNAM_OUT_BF16_SPLIT ? 2 : 1;
+#pragma unroll
+        for (int o = 0; o < N_OUT; ++o) {
+          uint4 chunks[8];
+          if (OUT_KIND == NNAM_OUT_F32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              chunks[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                     __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else {
+            if (o == 1) {
+#pragma unroll
+              for (int j = 0; j < BOX_COLS; ++j) v[j] -= bf16_round(v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              chunks[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+          }
+          uint8_t* box = boxes + box_sel * EPI_BOX_BYTES;
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          stage_row_128B(box, lane, chunks);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(o == 0 ? &tm_o_hi : &tm_o_lo, box, col, row0);
+            tma_store_commit();
+          }
+          box_sel ^= 1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_release(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  // neither CTA may retire (or free TMEM) while its peer can still signal it or its tensor core is still in use
+  tc_fence_before();
+  __syncthreads();
+  cluster_arrive_release();
+  cluster_wait_acquire();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------------------------ host side
-// Tile width: the narrowest multiple of the store box width that covers N in ceil(N / 256) tiles, or -- when that
-// would pad N by more than ~3 % (N = 1909 -> 8 x 256) -- the best of the box multiples >= 128 (N = 1909 -> 10 x 192).
+// Tile width: the narrowest multiple of the store box width that covers N in ceil(N / 256) tiles.  Wide tiles win even
+// when they pad N (N = 1909 -> 8 x 256, 7 % padding): measured 400 us vs 433 us for 10 x 192 on the cfg2 output layer
+// (scripts/gpu_gemm_bench.py), because the A traffic per FLOP falls with the tile width.
 static int pick_bn(int n, int box_cols) {
+  if (const char* v = getenv("NNAM_GEMM_BN")) {  // tuning aid
+    const int bn = atoi(v);
+    if (bn >= box_cols && bn <= MAX_BN && bn % box_cols == 0) return bn;
+  }
   const int tiles = (n + MAX_BN - 1) / MAX_BN;
   int bn = (n + tiles - 1) / tiles;
   bn = (bn + box_cols - 1) / box_cols * box_cols;
-  long long best_pad = static_cast<long long>((n + bn - 1) / bn) * bn;
-  if (best_pad * 100 > static_cast<long long>(n) * 103) {
-    for (int cand = MAX_BN - box_cols; cand >= 128; cand -= box_cols) {
-      const long long pad = static_cast<long long>((n + cand - 1) / cand) * cand;
-      if (pad < best_pad) {
-        best_pad = pad;
-        bn = cand;
-      }
-    }
-  }
   return bn;
+}
+
+template <int OUT_KIND>
+static int launch_gemm_2sm(const CUtensorMap (&tm)[6], const GemmParams& p, int grid, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_2sm_kernel<OUT_KIND>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute(2sm)");
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  gemm_bias_act_2sm_kernel<OUT_KIND><<<grid, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3],
+                                                                                        tm[4], tm[5], p);
+  return check_launch("gemm_bias_act_2sm_kernel");
+}
+
+// CTA pairs pay off (+1..7 % on the K >= 1024 shapes of the BASELINE configs) once there are enough 256-row tiles to
+// keep every pair busy; NNAM_GEMM_2SM=0 forces the single-CTA kernel (A/B measurements).
+static bool use_2sm(int M, int N, int K) {
+  static int env = -1;
+  if (env < 0) {
+    const char* v = getenv("NNAM_GEMM_2SM");
+    env = (v != nullptr && v[0] == '0') ? 0 : 1;
+  }
+  // short-K shapes are bound by the output stream, where the pair kernel measured slower (cfg3 upward 512 -> 2048)
+  return env == 1 && M >= 4096 && N >= 128 && K >= 1024;
 }
 
 template <int OUT_KIND>
@@ -352,8 +617,9 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
   p.M = M;
   p.N = N;
   p.K = K;
+  const bool pair = use_2sm(M, N, K);
   p.bn = pick_bn(N, box_cols);
-  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_m = pair ? (M + 2 * BM - 1) / (2 * BM) : (M + BM - 1) / BM;
   p.tiles_n = (N + p.bn - 1) / p.bn;
   p.k_blocks = (K + BK - 1) / BK;
   p.nsplit = nsplit;
@@ -364,10 +630,11 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
   CUtensorMap tm[6];
   int rc;
   if ((rc = encode_tmap_bf16_2d(&tm[0], a_hi, K, M, lda, BK, BM))) return rc;
-  if ((rc = encode_tmap_bf16_2d(&tm[2], w_hi, K, N, ldw, BK, p.bn))) return rc;
+  const int w_box_rows = pair ? p.bn / 2 : p.bn;  // a CTA of a pair loads half of the W tile
+  if ((rc = encode_tmap_bf16_2d(&tm[2], w_hi, K, N, ldw, BK, w_box_rows))) return rc;
   if (nsplit == 3) {
     if ((rc = encode_tmap_bf16_2d(&tm[1], a_lo, K, M, lda, BK, BM))) return rc;
-    if ((rc = encode_tmap_bf16_2d(&tm[3], w_lo, K, N, ldw, BK, p.bn))) return rc;
+    if ((rc = encode_tmap_bf16_2d(&tm[3], w_lo, K, N, ldw, BK, w_box_rows))) return rc;
   } else {
     tm[1] = tm[0];
     tm[3] = tm[2];
@@ -380,6 +647,15 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
   }
 
   const int total = p.tiles_m * p.tiles_n;
+  if (pair) {
+    const int pairs = sm_count() / 2;
+    const int grid2 = 2 * (total < pairs ? total : pairs);
+    switch (out_kind) {
+      case NNAM_OUT_F32: return launch_gemm_2sm<NNAM_OUT_F32>(tm, p, grid2, stream);
+      case NNAM_OUT_BF16: return launch_gemm_2sm<NNAM_OUT_BF16>(tm, p, grid2, stream);
+      default: return launch_gemm_2sm<NNAM_OUT_BF16_SPLIT>(tm, p, grid2, stream);
+    }
+  }
   const int grid = total < sm_count() ? total : sm_count();
   switch (out_kind) {
     case NNAM_OUT_F32: return launch_gemm<NNAM_OUT_F32>(tm, p, grid, stream);
