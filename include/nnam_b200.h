@@ -154,8 +154,11 @@ typedef struct NnamRnnDesc {
   void* h_hi;          /* layer output (rows, h_ld) bf16; direction d writes columns [d*H, (d+1)*H) */
   void* h_lo;          /* low halves (bf16x3) or NULL */
   long long h_ld;
-  void* aux_hi;        /* GRU with reset gate: scratch (rows, h_ld) bf16 for the r*h exchange (+ aux_lo in bf16x3) */
+  void* aux_hi;        /* unused (kept for ABI stability): the r*h product travels through the exchange buffer */
   void* aux_lo;
+  void* xchg_hi;       /* exchange buffer, (n_groups * streams * 4 * batch, H) bf16, zero-initialised scratch: every
+                          CTA of a group publishes its h slice here each step and TMA-loads the whole tile back */
+  void* xchg_lo;       /* low halves (bf16x3) or NULL */
   int n_items;                 /* work items = (batch, direction) pairs, grouped by lane = (CTA group, stream);
                                   inside a lane the items are sorted by direction */
   const int* item_batch;       /* device arrays */

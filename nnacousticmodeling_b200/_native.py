@@ -114,6 +114,7 @@ class RnnDesc(ctypes.Structure):
         ("w_hi", c_void_p * 2), ("w_lo", c_void_p * 2), ("w_ld", c_longlong),
         ("u_bias", c_void_p * 2),
         ("h_hi", c_void_p), ("h_lo", c_void_p), ("h_ld", c_longlong), ("aux_hi", c_void_p), ("aux_lo", c_void_p),
+        ("xchg_hi", c_void_p), ("xchg_lo", c_void_p),
         ("n_items", c_int), ("item_batch", c_void_p), ("item_dir", c_void_p),
         ("n_groups", c_int), ("group_item_start", c_void_p),
         ("batch_row0", c_void_p), ("batch_steps", c_void_p), ("batch_nutt", c_void_p), ("batch_base_off", c_void_p),

@@ -12,8 +12,12 @@
 //   * a GROUP of G = 4H / M_ROWS co-resident CTAs owns one (batch, direction) work item at a time; CTA r keeps the
 //     M_ROWS lateral-weight rows [r*M_ROWS, (r+1)*M_ROWS) (= M_ROWS/4 whole units, thanks to Chainer's interleaved
 //     layout) resident in shared memory as the A operand of tcgen05.mma (K-major, SWIZZLE_128B, loaded by TMA);
-//   * per step: h_{t-1} (n_t x H, bf16 [hi, lo]) is read from the layer's own output buffer in L2 into a swizzled
-//     smem tile (the B operand), D[M_ROWS x NB] = W_slice . h^T accumulates in TMEM (3 MMAs passes in bf16x3 mode),
+//   * per step: every CTA of the group writes its new h slice twice -- into the layer output rows (the next layer's
+//     GEMM input) and into a small slot-indexed EXCHANGE buffer (NB x H per lane, double-buffered by step parity).
+//     After the group's release/acquire counter, ONE thread pulls the whole h tile back with KB TMA box loads
+//     (hardware swizzle, one mbarrier) -- the first versions issued 4096 16-byte cp.async per step from all threads,
+//     which cost ~2 k cycles of load/store-unit issue time (profiles/r01_k3_phase_cycles.md).
+//     D[M_ROWS x NB] = W_slice . h^T accumulates in TMEM (3 MMAs passes in bf16x3 mode),
 //     each thread owns one gate row (TMEM lane), adds gx, applies the nonlinearity, the 4 gates of a unit are
 //     exchanged inside a lane quad with a 4x4 shuffle transpose, the cell state lives in registers for the whole
 //     utterance, and the new h slice is written (bf16 hi/lo) straight into the layer output rows -- which is what
@@ -82,7 +86,8 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
   uint8_t* tail = tiles + S * (PLANES * KB * H_BLOCK) + S * (PLANES * STAGE_BYTES);
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(tail);
   uint64_t* bar_mma = bar_w + 1 + stream;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 1 + S);
+  uint64_t* bar_h = bar_w + 1 + S + stream;  // this stream's h tile has landed (TMA complete_tx)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 1 + 2 * S);
   int* s_len = reinterpret_cast<int*>(tmem_slot + 2) + stream * NB;
   int* s_base = reinterpret_cast<int*>(tmem_slot + 2) + S * NB + stream * (BASE_SMEM + 1);
   constexpr int TMEM_COLS = S * NB < 32 ? 32 : S * NB;
@@ -90,7 +95,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    for (int i = 0; i < S; ++i) mbar_init(bar_w + 1 + i, 1);
+    for (int i = 0; i < 2 * S; ++i) mbar_init(bar_w + 1 + i, 1);
     fence_mbar_init();
   }
   if (tid < 32) {
@@ -129,19 +134,28 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
 #define PROF_MARK(i) do { if (prof_on) { const long long now = clock64(); prof_acc[i] += now - prof_t; prof_t = now; } } while (0)
 
   unsigned int steps_done = 0;  // arrivals of this CTA on the lane counter so far
-  uint32_t w_phase = 0, mma_phase = 0;
+  uint32_t w_phase = 0, mma_phase = 0, h_phase = 0;
   const int lane_id = group * S + stream;  // (group, stream) = one "lane" of the schedule
   unsigned int* counter = p.counters + lane_id;
   int it = p.group_item_start[lane_id];
   const int it_end = p.group_item_start[lane_id + 1];
 
-  auto group_wait = [&]() {  // every CTA of the group has published its slice of the previous exchange
+  // Wait until every CTA of the group has published its slice of the previous exchange, then pull the whole tile
+  // (exchange slot `slot` of this lane) into the swizzled B-operand tile: KB (x planes) TMA box loads, one thread.
+  // Only the issuing thread waits; the others go on to prefetch gx and meet it again at the MMA barrier.
+  auto group_fetch = [&](int slot) {
     if (tid_s == 0) {
       const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
-      while (ld_acquire_gpu(counter) < target) {
+      while (ld_acquire_gpu(counter) < target) {  // (relaxed polls + one fence.acq_rel measured ~900 cycles slower)
+      }
+      fence_proxy_async_all();  // the peers' generic-proxy stores -> visible to this async-proxy (TMA) read
+      mbar_expect_tx(bar_h, static_cast<uint32_t>(KB * H_BLOCK * PLANES));
+      const int row = (lane_id * 4 + slot) * NB;
+      for (int kb = 0; kb < KB; ++kb) {
+        tma_load_2d(h_hi_s + kb * H_BLOCK, &tmaps.x_hi, bar_h, kb * 64, row);
+        if (NSPLIT == 3) tma_load_2d(h_lo_s + kb * H_BLOCK, &tmaps.x_lo, bar_h, kb * 64, row);
       }
     }
-    stream_sync();
   };
   // The CTA barrier orders every thread's slice stores before thread 0's release (cumulativity), so one
   // red.release.gpu publishes the whole slice: no per-thread __threadfence (the pattern of a grid barrier).
@@ -151,11 +165,16 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
     ++steps_done;
   };
   // D[M_ROWS x NB] = W_slice . tile^T (3 passes in bf16x3 mode): issue (one thread) ...
-  auto mma_issue = [&]() {
-    cp_async_wait_all();
-    fence_proxy_async_smem();
-    stream_sync();
+  auto mma_issue = [&](bool via_tma) {
+    if (!via_tma) {  // tile staged by the threads with cp.async (initial-state rows of the stateful API)
+      cp_async_wait_all();
+      fence_proxy_async_smem();
+      stream_sync();
+    }
     if (tid_s == 0) {
+      if (via_tma) {
+        mbar_wait(bar_h, h_phase);
+      }
       tc_fence_after();
       const uint64_t wd_hi = make_sw128_kmajor_desc(smem_u32(w_hi_s));
       const uint64_t wd_lo = make_sw128_kmajor_desc(smem_u32(w_lo_s));
@@ -185,6 +204,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
       }
       umma_commit(bar_mma);
     }
+    if (via_tma) h_phase ^= 1;
   };
   // ... and collect: on return acc[] = my (row, slots) of D
   auto mma_collect = [&](float (&acc)[NBT]) {
@@ -305,16 +325,24 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
               __float2bfloat16_rn(v - __bfloat162float(hb));
       };
       // staging tile -> rows of `dst` (the layer output / the r*h exchange buffer): 16-byte coalesced stores
-      auto stage_flush = [&](__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, int n_act, int s) {
+      // (dst may be NULL: the r*h product of the GRU reset gate only travels through the exchange buffer)
+      auto stage_flush = [&](__nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo, int n_act, int s, int slot) {
         constexpr int CPR = UNITS / 8;  // 16-byte chunks per row
         stream_sync();
         for (int q = tid_s; q < n_act * CPR; q += TPS) {
           const int u = q / CPR, j = q - u * CPR;
-          const int t_idx = bwd ? (s_len[u] - 1 - s) : s;
-          const long long off = (row0 + bp[t_idx] + u) * p.h_ld + h_col0 + rank * UNITS + j * 8;
-          *reinterpret_cast<uint4*>(dst_hi + off) = *reinterpret_cast<const uint4*>(stage_hi + (u * UNITS + j * 8) * 2);
-          if (NSPLIT == 3)
-            *reinterpret_cast<uint4*>(dst_lo + off) = *reinterpret_cast<const uint4*>(stage_lo + (u * UNITS + j * 8) * 2);
+          const uint4 v_hi = *reinterpret_cast<const uint4*>(stage_hi + (u * UNITS + j * 8) * 2);
+          uint4 v_lo = v_hi;
+          if (NSPLIT == 3) v_lo = *reinterpret_cast<const uint4*>(stage_lo + (u * UNITS + j * 8) * 2);
+          const long long xoff = (static_cast<long long>(lane_id * 4 + slot) * NB + u) * H + rank * UNITS + j * 8;
+          *reinterpret_cast<uint4*>(p.xchg_hi + xoff) = v_hi;
+          if (NSPLIT == 3) *reinterpret_cast<uint4*>(p.xchg_lo + xoff) = v_lo;
+          if (dst_hi != nullptr) {
+            const int t_idx = bwd ? (s_len[u] - 1 - s) : s;
+            const long long off = (row0 + bp[t_idx] + u) * p.h_ld + h_col0 + rank * UNITS + j * 8;
+            *reinterpret_cast<uint4*>(dst_hi + off) = v_hi;
+            if (NSPLIT == 3) *reinterpret_cast<uint4*>(dst_lo + off) = v_lo;
+          }
         }
       };
 
@@ -326,17 +354,16 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
         const bool have_h = (s > 0) || has_h0;
         float acc[NBT], gxn[NBT];
         if (have_h) {
-          if (s > 0) group_wait();
-          PROF_MARK(1);
-          if (s == 0)
-            load_tile(p.h0_hi, p.h0_lo, n_s, s, 0);
+          if (s > 0)
+            group_fetch((s - 1) & 1);  // h of step s-1 sits in exchange slot (s-1) & 1
           else
-            load_tile(p.h_hi, p.h_lo, n_s, s, 1);
-          // the next step's input projection is requested while the h rows are still in flight and lands while the
+            load_tile(p.h0_hi, p.h0_lo, n_s, s, 0);
+          PROF_MARK(1);
+          // the next step's input projection is requested while the h tile is still in flight and lands while the
           // tensor core works (tcgen05.mma issue back-pressures the issuing thread, so it must come last)
           if (s + 1 < T) load_gx(s + 1, gxn);
           PROF_MARK(2);
-          mma_issue();
+          mma_issue(s > 0);
           PROF_MARK(0);
           mma_collect(acc);
         } else {
@@ -368,7 +395,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
                 p.c_out[(static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0 + unit] = c_new;
             }
           }
-          stage_flush(p.h_hi, p.h_lo, n_s, s);
+          stage_flush(p.h_hi, p.h_lo, n_s, s, s & 1);
           PROF_MARK(5);
         } else {
           // ---- GRU family (MGRU.py:67-85): U terms and their biases exist only when h does (:70-83)
@@ -393,11 +420,10 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
             }
           }
           if (two_phase) {
-            stage_flush(p.aux_hi, p.aux_lo, n_s, s);
+            stage_flush(nullptr, nullptr, n_s, s, 2 + (s & 1));
             group_publish();  // r*h slices are out
-            group_wait();
-            load_tile(p.aux_hi, p.aux_lo, n_s, s, 2);
-            mma_issue();
+            group_fetch(2 + (s & 1));
+            mma_issue(true);
             mma_collect(acc);  // row 4j+2 now holds U (r*h)
           }
 #pragma unroll
@@ -424,7 +450,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
               stage_put(u, h_new);
             }
           }
-          stage_flush(p.h_hi, p.h_lo, n_s, s);
+          stage_flush(p.h_hi, p.h_lo, n_s, s, s & 1);
         }
         group_publish();
         PROF_MARK(6);
@@ -456,7 +482,7 @@ struct RnnCfg {
 };
 #define NNAM_RNN_INSTANCES(X)                                                                      \
   /* H = 512, bf16: the BASELINE geometry */                                                       \
-  X(128, 16, 1, 8, 4, 4) X(128, 32, 1, 8, 2, 8) X(128, 64, 1, 8, 1, 8)                             \
+  X(128, 16, 1, 8, 4, 4) X(128, 32, 1, 8, 1, 16) X(128, 64, 1, 8, 1, 16)                           \
   /* H = 512, bf16x3 (fp32-accurate mode): 64-row slices */                                        \
   X(64, 16, 3, 8, 2, 8) X(64, 32, 3, 8, 1, 8)                                                      \
   /* any H, bf16 */                                                                                \
@@ -477,7 +503,7 @@ static size_t rnn_smem_bytes(const RnnCfg& c, int hidden) {
   const size_t planes = c.ns == 3 ? 2 : 1;
   const size_t base_smem = c.s >= 4 ? 1024 : 2048;
   const size_t stage = planes * static_cast<size_t>(c.s) * c.nb * (c.m / 4) * 2;
-  return kb * planes * (static_cast<size_t>(c.m) * 128 + static_cast<size_t>(c.s) * c.nb * 128) + stage + 8 * (1 + c.s) +
+  return kb * planes * (static_cast<size_t>(c.m) * 128 + static_cast<size_t>(c.s) * c.nb * 128) + stage + 8 * (1 + 2 * c.s) +
          16 + static_cast<size_t>(c.s) * (c.nb + base_smem + 1) * 4 + 1024;
 }
 
@@ -566,6 +592,15 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
     tm.w_hi[1] = tm.w_hi[0];
     tm.w_lo[1] = tm.w_lo[0];
   }
+  if (!d->xchg_hi || (d->nsplit == 3 && !d->xchg_lo))
+    return set_error(NNAM_ERR_ARG, "rnn: the exchange buffer (n_groups * streams * 4 * batch rows of H bf16) is missing");
+  const unsigned long long x_rows = static_cast<unsigned long long>(d->n_groups) * cfg->s * 4 * d->batch;
+  if ((rc = encode_tmap_bf16_2d(&tm.x_hi, d->xchg_hi, H, x_rows, H, 64, d->batch))) return rc;
+  if (d->nsplit == 3) {
+    if ((rc = encode_tmap_bf16_2d(&tm.x_lo, d->xchg_lo, H, x_rows, H, 64, d->batch))) return rc;
+  } else {
+    tm.x_lo = tm.x_hi;
+  }
   RnnParams p;
   p.hidden = H;
   p.n_dirs = d->n_dirs;
@@ -581,11 +616,11 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   p.h_lo = static_cast<__nv_bfloat16*>(d->h_lo);
   p.aux_hi = static_cast<__nv_bfloat16*>(d->aux_hi);
   p.aux_lo = static_cast<__nv_bfloat16*>(d->aux_lo);
+  p.xchg_hi = static_cast<__nv_bfloat16*>(d->xchg_hi);
+  p.xchg_lo = static_cast<__nv_bfloat16*>(d->xchg_lo);
   if (d->cell == NNAM_CELL_GRU) {
     for (int k = 0; k < d->n_dirs; ++k)
       if (!d->u_bias[k]) return set_error(NNAM_ERR_ARG, "rnn: GRU cells need u_bias");
-    if ((d->flags & 1) && (!d->aux_hi || (d->nsplit == 3 && !d->aux_lo)))
-      return set_error(NNAM_ERR_ARG, "rnn: reset-gate GRU needs the aux (r*h) exchange buffer");
   }
   p.item_batch = d->item_batch;
   p.item_dir = d->item_dir;
@@ -625,7 +660,7 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
   *max_groups = sm_count() / *group_ctas;
   // measured SM cycles per recurrence step of ONE stream while all S streams of the CTA are busy
   // (profiles/r01_k3_phase_cycles.md); the host uses it to choose the batch width
-  int cycles = cfg->s == 4 ? 12800 : (cfg->s == 2 ? 11200 : (batch == 64 ? 11300 : 8000));
+  int cycles = cfg->s == 4 ? 12800 : (cfg->s == 2 ? 9500 : (batch == 64 ? 8300 : 7800));
   if (nsplit == 3) cycles = cycles * 3 / 2;
   if (cell == NNAM_CELL_GRU) cycles = cycles * 3 / 2;
   const int cl = (cfg->m == 128 && cfg->s == 1) ? rnn_cluster_groups(cell, hidden, batch, nsplit) : 0;

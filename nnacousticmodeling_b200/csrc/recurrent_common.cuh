@@ -13,6 +13,8 @@ constexpr int RNN_THREADS = 256;  // cluster variant; the default kernels use S 
 struct RnnTmaps {
   CUtensorMap w_hi[2];
   CUtensorMap w_lo[2];
+  CUtensorMap x_hi;  // exchange buffer (lanes * 4 * NB rows, H columns): box {64, NB}
+  CUtensorMap x_lo;
 };
 
 struct RnnParams {
@@ -27,6 +29,8 @@ struct RnnParams {
   __nv_bfloat16* h_lo;
   __nv_bfloat16* aux_hi;  // GRU reset-gate variants: r*h exchange buffer, same shape as h
   __nv_bfloat16* aux_lo;
+  __nv_bfloat16* xchg_hi;  // (lanes * 4 * NB, H): per lane 4 slots of NB rows -- h parity 0/1, r*h parity 0/1
+  __nv_bfloat16* xchg_lo;
   const int* item_batch;
   const int* item_dir;
   const int* group_item_start;  // n_groups + 1
@@ -60,6 +64,12 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

@@ -234,9 +234,9 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
         d.w_hi[k] = layer.lat[k][0].data_ptr()
         d.w_lo[k] = layer.lat[k][1].data_ptr() if plan.split else None
         d.u_bias[k] = layer.u_bias[k].data_ptr() if layer.u_bias[k] is not None else None
-    if aux is not None:
-        d.aux_hi = aux[0].data_ptr()
-        d.aux_lo = aux[1].data_ptr() if aux[1] is not None else None
+    xh, xl = aux
+    d.xchg_hi = xh.data_ptr()
+    d.xchg_lo = xl.data_ptr() if xl is not None else None
     d.gx_ld = gx.stride(0)
     d.w_ld = layer.lat[0][0].stride(0)
     d.h_hi, d.h_lo, d.h_ld = h_hi.data_ptr(), (h_lo.data_ptr() if h_lo is not None else None), h_hi.stride(0)
@@ -275,10 +275,15 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
             h0, c0 = state_in[l]
         if want_state and plan.cell == CELL_LSTM:
             c_out = torch.zeros((sched.n_batches * nb, nd * H), dtype=torch.float32, device=plan.device)
-        aux = None
-        if plan.cell == CELL_GRU and (plan.gru_flags & 1):  # r*h exchange scratch, same shape as h
-            aux = (ws.get(f"{tag}.aux.hi", rows, nd * H, torch.bfloat16),
-                   ws.get(f"{tag}.aux.lo", rows, nd * H, torch.bfloat16) if plan.split else None)
+        # exchange buffer: per lane 4 slots (h parity 0/1, r*h parity 0/1) of nb rows x H; zeroed once when it is created
+        x_rows = sched.n_lanes * 4 * nb
+        fresh = ws.buf.get(f"{tag}.xchg.hi") is None or ws.buf[f"{tag}.xchg.hi"].numel() < x_rows * H
+        aux = (ws.get(f"{tag}.xchg.hi", x_rows, H, torch.bfloat16),
+               ws.get(f"{tag}.xchg.lo", x_rows, H, torch.bfloat16) if plan.split else None)
+        if fresh:
+            aux[0].zero_()
+            if aux[1] is not None:
+                aux[1].zero_()
         desc = _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0, c0, c_out, aux)
         # algorithmic lateral flops: LSTM 4 gates, GRU 3 (2 without reset gate) H x H products per frame
         n_mats = 4 if plan.cell == CELL_LSTM else (3 if plan.gru_flags & 1 else 2)
