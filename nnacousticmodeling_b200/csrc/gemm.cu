@@ -82,8 +82,13 @@ __device__ __forceinline__ void stage_row_128B(uint8_t* box, int lane, const uin
   for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(row + ((j ^ (lane & 7)) << 4)) = chunks[j];
 }
 
+// Registers are capped (not via __launch_bounds__, which would let ptxas take 240) so that a 256-thread GEMM CTA leaves
+// room on the SM for one 128-thread CTA of the HBM-bound head / splice kernels, which the engine runs on a second
+// stream in the shadow of the GEMMs.
+constexpr int GEMM_MAX_REGS = 184;
+
 template <int OUT_KIND>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __maxnreg__(GEMM_MAX_REGS)
     gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                          const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
@@ -314,7 +319,7 @@ constexpr int B2_STAGE_BYTES = (MAX_BN / 2) * BK * 2;  // 16 KiB: this CTA's hal
 constexpr int GEMM2_SMEM_BYTES = STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) + EPI_BYTES + 256 + 1024;
 
 template <int OUT_KIND>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
     gemm_bias_act_2sm_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                              const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                              const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,

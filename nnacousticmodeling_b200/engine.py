@@ -273,37 +273,56 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         if have != d_in:
             raise NnamError(f"model expects {d_in} inputs per frame, the data provides {have}")
         ld_in = round_up(d_in, 8)
-        a_hi = ws.get("ff.a.hi", chunk, ld_in, torch.bfloat16)
-        a_lo = ws.get("ff.a.lo", chunk, ld_in, torch.bfloat16) if plan0.split else None
+        a_bufs = [(ws.get("ff.a.hi", chunk, ld_in, torch.bfloat16),
+                   ws.get("ff.a.lo", chunk, ld_in, torch.bfloat16) if plan0.split else None)]
         out_dev = None if out_on_device else [ws.get(f"ff.out{i}", chunk, n_out, torch.float32) for i in range(2)]
-        copied = [None, None]
+        # Three streams: `main` runs splice + the GEMM stack of chunk i; `aux` runs the HBM-bound head of chunk i-1 in
+        # their shadow (the GEMM kernels cap their registers so that one head CTA fits next to a GEMM CTA on every SM);
+        # `side` carries the D2H copies.  Logits and head outputs are double-buffered by chunk parity.  (Moving the
+        # splice kernel to `aux` as well was measured and dropped: it needs shared memory, cannot co-reside with a
+        # GEMM CTA and only delayed the head.)
+        aux = plan0.__dict__.setdefault("_aux_stream", torch.cuda.Stream(device=device))
+        aux.wait_stream(main)
+        a_hi, a_lo = a_bufs[0]
+        copied = [None, None]      # D2H of the chunk that last used out_dev[buf]
+        head_done = [None, None]   # head of the chunk that last used the logits buffers of this parity
         for ci, c0 in enumerate(range(f0, f1, chunk)):
             c1 = min(c0 + chunk, f1)
             rows = c1 - c0
+            buf = ci % 2
             if presliced:
                 ops.convert_f32(x_dev[c0 - lo:c1 - lo], plan0.act_kind, ldd=ld_in, out=(a_hi, a_lo))
             else:
                 ops.splice_transform(x_dev, n_total, splice, add, mul,
                                      None if iv_dev is None else iv_dev[c0 - iv0:c1 - iv0], f0=c0, f1=c1, x_row0=lo,
                                      out_kind=plan0.act_kind, ldo=ld_in, out=(a_hi, a_lo))
-            logits = [ff_logits(m, p, a_hi, a_lo, rows, f"ff{k}", ws) for k, (m, p) in enumerate(zip(models, plans))]
+            if head_done[buf] is not None:
+                main.wait_event(head_done[buf])  # the head of chunk i-2 still reads these logits
+            logits = [ff_logits(m, p, a_hi, a_lo, rows, f"ff{k}.{buf}", ws) for k, (m, p) in enumerate(zip(models, plans))]
+            gemm_done = torch.cuda.Event()
+            gemm_done.record(main)
             hkw = dict(rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
                        prior_scale=head.prior_scale, final_normalize=head.final_normalize)
+            aux.wait_event(gemm_done)
+            with torch.cuda.stream(aux):
+                if out_on_device:
+                    ops.head(logits, n_out, out=out[c0:c1], **hkw)
+                else:
+                    if copied[buf] is not None:
+                        aux.wait_event(copied[buf])  # the side stream still reads this buffer
+                    ops.head(logits, n_out, out=out_dev[buf], **hkw)
+                hd = torch.cuda.Event()
+                hd.record(aux)
+            head_done[buf] = hd
             if out_on_device:
-                ops.head(logits, n_out, out=out[c0:c1], **hkw)
                 continue
-            buf = ci % 2
-            if copied[buf] is not None:
-                main.wait_event(copied[buf])  # the side stream still reads this buffer
-            ops.head(logits, n_out, out=out_dev[buf], **hkw)
-            done = torch.cuda.Event()
-            done.record(main)
-            side.wait_event(done)
+            side.wait_event(hd)
             with torch.cuda.stream(side):
                 out_h[c0:c1].copy_(out_dev[buf][:rows], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(side)
             copied[buf] = ev
+        main.wait_stream(aux)  # callers that time or consume on the current stream see the whole pass
         side.synchronize()
         main.synchronize()
     return out
