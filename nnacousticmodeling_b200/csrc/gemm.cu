@@ -37,7 +37,8 @@ constexpr int B_STAGE_BYTES = MAX_BN * BK * 2;  // 32 KiB
 constexpr int GEMM_THREADS = 256;
 constexpr int EPI_BOX_BYTES = 32 * 128;         // one epilogue warp's store box: 32 rows x 128 B, SWIZZLE_128B
 constexpr int EPI_BYTES = 4 * 2 * EPI_BOX_BYTES;  // 4 epilogue warps x 2 alternating boxes
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_BYTES + 256 + 1024;
+constexpr int BIAS_BYTES = 2 * MAX_BN * 4;        // the tile's bias slice, double-buffered by tile parity
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_BYTES + BIAS_BYTES + 256;
 constexpr int TMEM_COLS = 512;
 
 struct GemmParams {
@@ -49,6 +50,9 @@ struct GemmParams {
   int act;        // NNAM_ACT_*
   const float* bias;
 };
+
+// barrier among the four epilogue warps only (named barrier 1, 128 threads)
+__device__ __forceinline__ void named_bar_sync_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 template <int ACT>
 __device__ __forceinline__ float act_fn(float v) {
@@ -93,13 +97,12 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
                          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                          const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                          const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024 B alignment
+  extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024 B alignment (checked below)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* smem_epi = smem_b + STAGES * B_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
+  float* smem_bias = reinterpret_cast<float*>(smem_epi + EPI_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES + BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -109,6 +112,7 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
   const int k_iters = p.k_blocks * p.nsplit;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // the dynamic shared window is 1024-byte aligned on sm_100
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
@@ -140,64 +144,72 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // The producer and MMA warps run their loops with ALL lanes (warp-uniform control flow keeps addresses and
+  // descriptors in uniform registers) and elect one lane only around the TMA / tcgen05 instructions.  The first version
+  // ran the loops under `if (lane == 0)`: ptxas then wraps every uniform-datapath instruction in an ELECT waterfall
+  // loop, and the MMA warp needed ~680 clocks to issue the 4 MMAs of a k-block that the tensor pipe retires in 512 --
+  // the issue loop, not memory, capped the tensor pipe at 85 % (profiles/r01_cfg2_gemm_v2.md).
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>((BM + p.bn) * BK * 2);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / p.tiles_n;
-        const int n_blk = tile % p.tiles_n;
-        for (int pass = 0; pass < p.nsplit; ++pass) {
-          const CUtensorMap* ma = (pass == 2) ? &tm_a_lo : &tm_a_hi;
-          const CUtensorMap* mw = (pass == 1) ? &tm_w_lo : &tm_w_hi;
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ------------------------------------------------------------ TMA producer
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>((BM + p.bn) * BK * 2);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_blk = tile / p.tiles_n;
+      const int n_blk = tile % p.tiles_n;
+      for (int pass = 0; pass < p.nsplit; ++pass) {
+        const CUtensorMap* ma = (pass == 2) ? &tm_a_lo : &tm_a_hi;
+        const CUtensorMap* mw = (pass == 1) ? &tm_w_lo : &tm_w_hi;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
             mbar_expect_tx(&full_bar[stage], tx_bytes);
             tma_load_2d(smem_a + stage * A_STAGE_BYTES, ma, &full_bar[stage], kb * BK, m_blk * BM);
             tma_load_2d(smem_b + stage * B_STAGE_BYTES, mw, &full_bar[stage], kb * BK, n_blk * p.bn);
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
           }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ MMA issuer
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc_bf16_f32(BM, static_cast<uint32_t>(p.bn));
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * MAX_BN);
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * B_STAGE_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t adesc = make_sw128_kmajor_desc(a_addr + k * UK * 2);
-            const uint64_t bdesc = make_sw128_kmajor_desc(b_addr + k * UK * 2);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
       }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t idesc = make_idesc_bf16_f32(BM, static_cast<uint32_t>(p.bn));
+    const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(smem_a));
+    const uint64_t bdesc0 = make_sw128_kmajor_desc(smem_u32(smem_b));
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * MAX_BN);
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          // the start-address field of the descriptor counts 16-byte units: stage and k offsets are plain adds
+          const uint64_t ad = adesc0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
+          const uint64_t bd = bdesc0 + static_cast<uint64_t>((stage * B_STAGE_BYTES) >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k)
+            umma_bf16(tmem_d, ad + static_cast<uint64_t>((k * UK * 2) >> 4), bd + static_cast<uint64_t>((k * UK * 2) >> 4),
+                      idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     // -------------------------------------------------------------- epilogue
@@ -211,6 +223,17 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.tiles_n;
       const int n_blk = tile % p.tiles_n;
+      // the tile's bias slice goes to shared memory once (each thread of the four epilogue warps loads two values);
+      // every thread needs every column's bias, and as broadcast shared loads that costs a fraction of the 256
+      // 128-bit global loads per tile the first version issued (they alone held short-K layers ~25 us back)
+      float* bias_s = smem_bias + acc * MAX_BN;
+      if (p.bias != nullptr) {
+        for (int c = q * 32 + lane; c < p.bn; c += 128) {
+          const int gc = n_blk * p.bn + c;
+          bias_s[c] = gc < p.N ? __ldg(p.bias + gc) : 0.0f;
+        }
+      }
+      named_bar_sync_epi();
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * MAX_BN);
@@ -228,20 +251,14 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
           for (int j = 0; j < 32; ++j) v[j0 + j] = __uint_as_float(r[j]);
         }
         if (p.bias != nullptr) {
-          if (col + BOX_COLS <= p.N) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);  // broadcast reads of the staged slice
 #pragma unroll
-            for (int j = 0; j < BOX_COLS / 4; ++j) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j] += b.x;
-              v[4 * j + 1] += b.y;
-              v[4 * j + 2] += b.z;
-              v[4 * j + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < BOX_COLS; ++j)
-              if (col + j < p.N) v[j] += __ldg(p.bias + col + j);
+          for (int j = 0; j < BOX_COLS / 4; ++j) {
+            const float4 b = b4[j];
+            v[4 * j] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
           }
         }
         apply_act<BOX_COLS>(v, p.act);
@@ -316,7 +333,7 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
 //   tempty[a]  leader only, count 8: the four epilogue warps of BOTH CTAs arrive (the follower's remotely)
 constexpr int STAGES2 = 6;
 constexpr int B2_STAGE_BYTES = (MAX_BN / 2) * BK * 2;  // 16 KiB: this CTA's half of the W tile
-constexpr int GEMM2_SMEM_BYTES = STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) + EPI_BYTES + 256 + 1024;
+constexpr int GEMM2_SMEM_BYTES = STAGES2 * (A_STAGE_BYTES + B2_STAGE_BYTES) + EPI_BYTES + BIAS_BYTES + 256;
 
 template <int OUT_KIND>
 __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
@@ -324,13 +341,12 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
                              const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                              const __grid_constant__ CUtensorMap tm_o_hi, const __grid_constant__ CUtensorMap tm_o_lo,
                              const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES2 * A_STAGE_BYTES;
   uint8_t* smem_epi = smem_b + STAGES2 * B2_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES);
+  float* smem_bias = reinterpret_cast<float*>(smem_epi + EPI_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES + BIAS_BYTES);
   uint64_t* empty_bar = full_bar + STAGES2;
   uint64_t* tfull_bar = empty_bar + STAGES2;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -338,6 +354,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
@@ -380,41 +397,44 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      // ------------------------------------------------------------ TMA producer (both CTAs)
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = static_cast<uint32_t>(2 * (BM + half_bn) * BK * 2);  // both CTAs' boxes
-      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        const int m_blk = tile / p.tiles_n;
-        const int n_blk = tile % p.tiles_n;
-        const int row_a = m_blk * (2 * BM) + static_cast<int>(rank) * BM;
-        const int row_w = n_blk * p.bn + static_cast<int>(rank) * half_bn;
-        for (int pass = 0; pass < p.nsplit; ++pass) {
-          const CUtensorMap* ma = (pass == 2) ? &tm_a_lo : &tm_a_hi;
-          const CUtensorMap* mw = (pass == 1) ? &tm_w_lo : &tm_w_hi;
-          for (int kb = 0; kb < p.k_blocks; ++kb) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ------------------------------------------------------------ TMA producer (both CTAs; all lanes, one elected)
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t tx_bytes = static_cast<uint32_t>(2 * (BM + half_bn) * BK * 2);  // both CTAs' boxes
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      const int m_blk = tile / p.tiles_n;
+      const int n_blk = tile % p.tiles_n;
+      const int row_a = m_blk * (2 * BM) + static_cast<int>(rank) * BM;
+      const int row_w = n_blk * p.bn + static_cast<int>(rank) * half_bn;
+      for (int pass = 0; pass < p.nsplit; ++pass) {
+        const CUtensorMap* ma = (pass == 2) ? &tm_a_lo : &tm_a_hi;
+        const CUtensorMap* mw = (pass == 1) ? &tm_w_lo : &tm_w_hi;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
             const uint32_t full_leader = mapa_shared(smem_u32(&full_bar[stage]), 0);
             if (leader) mbar_expect_tx(&full_bar[stage], tx_bytes);
             tma_load_2d_2sm(smem_a + stage * A_STAGE_BYTES, ma, full_leader, kb * BK, row_a);
             tma_load_2d_2sm(smem_b + stage * B2_STAGE_BYTES, mw, full_leader, kb * BK, row_w);
-            if (++stage == STAGES2) {
-              stage = 0;
-              phase ^= 1;
-            }
+          }
+          __syncwarp();
+          if (++stage == STAGES2) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && leader) {
-      // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {
+      // ------------------------------------------------------------ MMA issuer (leader CTA only; all lanes, one elected)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t idesc = make_idesc_bf16_f32(2 * BM, static_cast<uint32_t>(p.bn));
+      const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(smem_a));
+      const uint64_t bdesc0 = make_sw128_kmajor_desc(smem_u32(smem_b));
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
         mbar_wait_cluster_acquire(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -422,16 +442,17 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * B2_STAGE_BYTES);
+          if (elect_one()) {
+            const uint64_t ad = adesc0 + static_cast<uint64_t>((stage * A_STAGE_BYTES) >> 4);
+            const uint64_t bd = bdesc0 + static_cast<uint64_t>((stage * B2_STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t adesc = make_sw128_kmajor_desc(a_addr + k * UK * 2);
-            const uint64_t bdesc = make_sw128_kmajor_desc(b_addr + k * UK * 2);
-            umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UK; ++k)
+              umma_bf16_2sm(tmem_d, ad + static_cast<uint64_t>((k * UK * 2) >> 4),
+                            bd + static_cast<uint64_t>((k * UK * 2) >> 4), idesc, (it | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage], 0b11);  // frees the slot in both CTAs
+            if (it == k_iters - 1) umma_commit_2sm(&tfull_bar[acc], 0b11);
           }
-          umma_commit_2sm(&empty_bar[stage], 0b11);  // frees the slot in both CTAs
-          if (it == k_iters - 1) umma_commit_2sm(&tfull_bar[acc], 0b11);
+          __syncwarp();
           if (++stage == STAGES2) {
             stage = 0;
             phase ^= 1;
@@ -452,6 +473,14 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
       const int m_blk = tile / p.tiles_n;
       const int n_blk = tile % p.tiles_n;
+      float* bias_s = smem_bias + acc * MAX_BN;  // staged bias slice of this tile (see the single-CTA kernel)
+      if (p.bias != nullptr) {
+        for (int c = q * 32 + lane; c < p.bn; c += 128) {
+          const int gc = n_blk * p.bn + c;
+          bias_s[c] = gc < p.N ? __ldg(p.bias + gc) : 0.0f;
+        }
+      }
+      named_bar_sync_epi();
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * MAX_BN);
@@ -469,20 +498,14 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
           for (int j = 0; j < 32; ++j) v[j0 + j] = __uint_as_float(r[j]);
         }
         if (p.bias != nullptr) {
-          if (col + BOX_COLS <= p.N) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);  // broadcast reads of the staged slice
 #pragma unroll
-            for (int j = 0; j < BOX_COLS / 4; ++j) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j] += b.x;
-              v[4 * j + 1] += b.y;
-              v[4 * j + 2] += b.z;
-              v[4 * j + 3] += b.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < BOX_COLS; ++j)
-              if (col + j < p.N) v[j] += __ldg(p.bias + col + j);
+          for (int j = 0; j < BOX_COLS / 4; ++j) {
+            const float4 b = b4[j];
+            v[4 * j] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
           }
         }
         apply_act<BOX_COLS>(v, p.act);
@@ -578,7 +601,12 @@ static bool use_2sm(int M, int N, int K) {
     env = (v != nullptr && v[0] == '0') ? 0 : 1;
   }
   // short-K shapes are bound by the output stream, where the pair kernel measured slower (cfg3 upward 512 -> 2048)
-  return env == 1 && M >= 4096 && N >= 128 && K >= 1024;
+  static int min_k = -1;
+  if (min_k < 0) {
+    const char* v = getenv("NNAM_GEMM_2SM_MINK");  // tuning aid
+    min_k = v != nullptr ? atoi(v) : 1024;
+  }
+  return env == 1 && M >= 4096 && N >= 128 && K >= min_k;
 }
 
 template <int OUT_KIND>
