@@ -144,17 +144,20 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
   // (exchange slot `slot` of this lane) into the swizzled B-operand tile: KB (x planes) TMA box loads, one thread.
   // Only the issuing thread waits; the others go on to prefetch gx and meet it again at the MMA barrier.
   auto group_fetch = [&](int slot) {
-    if (tid_s == 0) {
+    if (warp_s == 0) {  // warp-uniform loop, one elected lane issues (keeps the TMA operands in uniform registers)
       const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
-      while (ld_acquire_gpu(counter) < target) {  // (relaxed polls + one fence.acq_rel measured ~900 cycles slower)
+      while (ld_acquire_gpu(counter) < target) {
       }
-      fence_proxy_async_all();  // the peers' generic-proxy stores -> visible to this async-proxy (TMA) read
-      mbar_expect_tx(bar_h, static_cast<uint32_t>(KB * H_BLOCK * PLANES));
-      const int row = (lane_id * 4 + slot) * NB;
-      for (int kb = 0; kb < KB; ++kb) {
-        tma_load_2d(h_hi_s + kb * H_BLOCK, &tmaps.x_hi, bar_h, kb * 64, row);
-        if (NSPLIT == 3) tma_load_2d(h_lo_s + kb * H_BLOCK, &tmaps.x_lo, bar_h, kb * 64, row);
+      if (elect_one()) {
+        fence_proxy_async_all();  // the peers' generic-proxy stores -> visible to this async-proxy (TMA) read
+        mbar_expect_tx(bar_h, static_cast<uint32_t>(KB * H_BLOCK * PLANES));
+        const int row = (lane_id * 4 + slot) * NB;
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_2d(h_hi_s + kb * H_BLOCK, &tmaps.x_hi, bar_h, kb * 64, row);
+          if (NSPLIT == 3) tma_load_2d(h_lo_s + kb * H_BLOCK, &tmaps.x_lo, bar_h, kb * 64, row);
+        }
       }
+      __syncwarp();
     }
   };
   // The CTA barrier orders every thread's slice stores before thread 0's release (cumulativity), so one
@@ -171,38 +174,41 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
       fence_proxy_async_smem();
       stream_sync();
     }
-    if (tid_s == 0) {
-      if (via_tma) {
-        mbar_wait(bar_h, h_phase);
-      }
+    if (warp_s == 0) {
+      // All lanes of the issuing warp run this block and one elected lane issues: under `if (tid == 0)` ptxas wraps
+      // every tcgen05.mma in an ELECT waterfall loop, which made the 32 MMAs of a step cost ~55 clocks each to issue.
+      if (via_tma) mbar_wait(bar_h, h_phase);
       tc_fence_after();
-      const uint64_t wd_hi = make_sw128_kmajor_desc(smem_u32(w_hi_s));
-      const uint64_t wd_lo = make_sw128_kmajor_desc(smem_u32(w_lo_s));
-      const uint64_t hd_hi = make_sw128_kmajor_desc(h_hi_sa);
-      const uint64_t hd_lo = make_sw128_kmajor_desc(h_lo_sa);
-      uint32_t accum = 0;
+      if (elect_one()) {
+        const uint64_t wd_hi = make_sw128_kmajor_desc(smem_u32(w_hi_s));
+        const uint64_t wd_lo = make_sw128_kmajor_desc(smem_u32(w_lo_s));
+        const uint64_t hd_hi = make_sw128_kmajor_desc(h_hi_sa);
+        const uint64_t hd_lo = make_sw128_kmajor_desc(h_lo_sa);
+        uint32_t accum = 0;
 #pragma unroll
-      for (int pass = 0; pass < NSPLIT; ++pass) {
-        const uint64_t wa = pass == 2 ? wd_lo : wd_hi;
-        const uint64_t ha = pass == 1 ? hd_lo : hd_hi;
-        if (KBT > 0) {
+        for (int pass = 0; pass < NSPLIT; ++pass) {
+          const uint64_t wa = pass == 2 ? wd_lo : wd_hi;
+          const uint64_t ha = pass == 1 ? hd_lo : hd_hi;
+          if (KBT > 0) {
 #pragma unroll
-          for (int kb = 0; kb < KBT; ++kb)
+            for (int kb = 0; kb < KBT; ++kb)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
-              accum = 1;
-            }
-        } else {
-          for (int kb = 0; kb < KB; ++kb)
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
+                accum = 1;
+              }
+          } else {
+            for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
-              accum = 1;
-            }
+              for (int k = 0; k < 4; ++k) {
+                umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
+                accum = 1;
+              }
+          }
         }
+        umma_commit(bar_mma);
       }
-      umma_commit(bar_mma);
+      __syncwarp();
     }
     if (via_tma) h_phase ^= 1;
   };
@@ -660,8 +666,8 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
   *max_groups = sm_count() / *group_ctas;
   // measured SM cycles per recurrence step of ONE stream while all S streams of the CTA are busy
   // (profiles/r01_k3_phase_cycles.md); the host uses it to choose the batch width
-  int cycles = cfg->s == 4 ? 12800 : (cfg->s == 2 ? 9500 : (batch == 64 ? 8300 : 7800));
-  if (nsplit == 3) cycles = cycles * 3 / 2;
+  int cycles = cfg->s == 4 ? 12800 : (cfg->s == 2 ? 9500 : (batch == 64 ? 7900 : 6500));
+  if (nsplit == 3) cycles = cycles * 7 / 5;
   if (cell == NNAM_CELL_GRU) cycles = cycles * 3 / 2;
   const int cl = (cfg->m == 128 && cfg->s == 1) ? rnn_cluster_groups(cell, hidden, batch, nsplit) : 0;
   if (cl > 0) {
