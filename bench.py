@@ -224,6 +224,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist_util.init("nccl", dev)
+    numa_cpus = dist_util.bind_to_gpu_numa(local) if world > 1 else None  # before the pinned buffers are allocated
     peaks = load_peaks()
 
     w, x, offsets, iv = make_workload(args.workload, rank)
@@ -351,7 +352,8 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3(fp32-accurate)",
         "data": "synthetic",
         "config": {"workload": w["desc"], "frames_per_gpu": n, "precision": args.precision,
-                   "l2": "inputs+activations larger than L2 (no flush needed)", "parallelism": f"dp{world} utterance shards, no collective"},
+                   "l2": "inputs+activations larger than L2 (no flush needed)", "parallelism": f"dp{world} utterance shards, no collective",
+                   "cpu_binding": None if numa_cpus is None else f"{len(numa_cpus)} CPUs local to the GPU"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "matches_device_leg": same},

@@ -25,6 +25,32 @@ def init(backend, device=None):
     return world
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs NVML reports as local to GPU ``device_index`` (same NUMA node / PCIe root), so that
+    the pinned host buffers it allocates next are placed next to the GPU that will DMA into them.  Returns the CPU
+    list used, or None when NVML or the container's cpuset does not allow it (then nothing changes)."""
+    try:
+        import pynvml as nv
+        import torch
+        nv.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+            h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:  # noqa: BLE001
+            h = nv.nvmlDeviceGetHandleByIndex(device_index)
+        n_cpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (max(n_cpu, 1024) + 63) // 64)
+        local = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = sorted(local & allowed)
+        if not cpus or len(cpus) == len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def barrier():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
