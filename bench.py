@@ -220,6 +220,8 @@ def run_ours(args):
     from nnacousticmodeling_b200 import engine, ops
 
     from nnacousticmodeling_b200 import dist_util
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
     world, rank, local = dist_util.env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
