@@ -103,9 +103,10 @@ int nnam_head(const float* const* logits_host, const float* weights_host, int n_
               float prior_scale, int final_normalize, float* out, long long ld_out, long long rows,
               int n_classes, void* stream);
 
-/* nnam_head with a scatter map: logits row r is written to out row out_row_map[r] (a negative entry drops the
- * row).  Used by the recurrent path, whose rows are time-major "packed"; dropping rows reproduces the reference's
- * unwritten last `timedelay` frames (predict_folds.py:50,60-61, quirk Q4).  */
+/* nnam_head with a scatter map: logits row r is written to out row out_row_map[r]; an entry of -1 drops the row and an
+ * entry -2 - q fills out row q with zeros.  Used by the recurrent path, whose rows are time-major "packed"; the zero
+ * rows reproduce the reference's unwritten last `timedelay` frames (predict_folds.py:50,60-61, quirk Q4) without a
+ * separate pass over the output.  */
 int nnam_head_scatter(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in,
                       int pre_normalize, const float* rpl_w, const float* rpl_b, const float* rpl_lb,
                       const float* prior, float prior_scale, int final_normalize, float* out, long long ld_out,
@@ -143,8 +144,9 @@ typedef struct NnamRnnDesc {
   int streams; /* independent batches a CTA group runs concurrently (from nnam_rnn_plan) */
   int nsplit;  /* 1 = bf16 operands, 3 = bf16x3 (needs the _lo buffers) */
   int flags;   /* GRU family: bit 0 = reset gate, bits 1-2 = candidate activation (NNAM_ACT_*) */
-  const float* gx[2];  /* per direction: input projection + bias for every packed row, (rows, gx_ld) fp32,
-                          columns gate-interleaved exactly like Chainer's upward/W rows */
+  const void* gx[2];   /* per direction: input projection + bias for every packed row, (rows, gx_ld), columns
+                          gate-interleaved exactly like Chainer's upward/W rows; fp32 when nsplit == 3, bf16 when
+                          nsplit == 1 (in bf16 mode it is the largest HBM stream of a layer) */
   long long gx_ld;
   const void* w_hi[2]; /* per direction: lateral weights (4H, H) bf16 K-major.  LSTM: Chainer lateral/W as is.
                           GRU family: rows interleaved per unit [U_z, U_r (or 0), U, 0]; gx and u_bias likewise */

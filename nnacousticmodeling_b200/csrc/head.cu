@@ -121,15 +121,20 @@ __global__ void __launch_bounds__(HEAD_THREADS, (MULTI || NV < 64) ? 1 : 2) head
     }
     const float lse = p.final_normalize ? row_logsumexp<NV>(h, lane, C) : 0.0f;
     long long out_row = row;
+    bool zero = false;
     if (p.out_row_map != nullptr) {
       out_row = __ldg(p.out_row_map + row);
-      if (out_row < 0) continue;  // warp-uniform: one row per warp
+      if (out_row == -1) continue;  // warp-uniform: one row per warp
+      if (out_row < 0) {            // -2 - r: fill output row r with zeros (quirk Q4 rows the reference never writes)
+        out_row = -2 - out_row;
+        zero = true;
+      }
     }
     float* dst = p.out + out_row * p.ld_out;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
-      if (c < C) dst[c] = h[i] - lse;
+      if (c < C) dst[c] = zero ? 0.0f : h[i] - lse;
     }
   }
 }
@@ -222,7 +227,13 @@ __global__ void __launch_bounds__(HEAD_FAST_THREADS, 4) head_fast_kernel(const H
     long long out_row = row;
     if (p.out_row_map != nullptr) {
       out_row = __ldg(p.out_row_map + row);
-      if (out_row < 0) continue;  // warp-uniform: one row per warp
+      if (out_row == -1) continue;  // warp-uniform: one row per warp
+      if (out_row < 0) {            // -2 - r: fill output row r with zeros (quirk Q4 rows the reference never writes)
+        out_row = -2 - out_row;
+        lse = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV4; ++i) v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
     }
     float* dst = p.out + out_row * p.ld_out;
     const int a = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);  // row start modulo 16 bytes, in floats

@@ -30,6 +30,7 @@
 //     barrier and group counter.  While one stream waits on its chain the others issue, which is what hides the
 //     latency (profiles/r01_k3_phase_cycles.md).
 #include <cooperative_groups.h>
+#include <type_traits>
 
 #include "recurrent_common.cuh"
 
@@ -260,7 +261,9 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
       const int nutt = p.batch_nutt[b];
       const int* base = p.base + p.batch_base_off[b];
       const int* len = p.utt_len + b * NB;
-      const float* gx = p.gx[d] + gate_col;
+      // input projection: fp32 in the fp32-accurate mode, bf16 in bf16 mode (halves the largest HBM stream of a layer)
+      using GxT = typename std::conditional<NSPLIT == 3, float, __nv_bfloat16>::type;
+      const GxT* gx = reinterpret_cast<const GxT*>(p.gx[d]) + gate_col;
       stream_sync();  // previous item's readers of s_len / s_base are done
       if (tid_s < NB) s_len[tid_s] = tid_s < nutt ? len[tid_s] : 0;
       const bool base_in_smem = T <= BASE_SMEM;
@@ -319,7 +322,10 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
           const int u = u_lo + j;
           const int uu = u < n_act ? u : n_act - 1;
           const long long row = row0 + (bwd ? bp[s_len[uu] - 1 - s] : base_s) + uu;
-          dst[j] = __ldg(gx + row * p.gx_ld);
+          if (NSPLIT == 3)
+            dst[j] = __ldg(reinterpret_cast<const float*>(gx) + row * p.gx_ld);
+          else
+            dst[j] = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(gx) + row * p.gx_ld));
         }
       };
       // my value for (utterance u, my unit) -> staging tile (utterance-major, UNITS bf16 per row, hi [+ lo] planes)

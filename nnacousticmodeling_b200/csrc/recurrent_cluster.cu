@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
       const int nutt = p.batch_nutt[b];
       const int* base = p.base + p.batch_base_off[b];
       const int* len = p.utt_len + b * NB;
-      const float* gx = p.gx[d] + gate_col;
+      const __nv_bfloat16* gx = reinterpret_cast<const __nv_bfloat16*>(p.gx[d]) + gate_col;  // bf16 mode only
       const int h_col0 = d * H;
       __syncthreads();
       if (tid < NB) s_len[tid] = tid < nutt ? len[tid] : 0;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(RNN_THREADS, 1)
           const int u = u_lo + j;
           const int uu = u < n_s ? u : n_s - 1;
           const long long row = row0 + (bwd ? bp[s_len[uu] - 1 - s] : base_s) + uu;
-          gxr[j] = __ldg(gx + row * p.gx_ld);
+          gxr[j] = __bfloat162float(__ldg(gx + row * p.gx_ld));
         }
         PROF_MARK(0);
         // all h slices of global step g-1 have landed in tile g&1 (also orders tile / staging reuse, see header)

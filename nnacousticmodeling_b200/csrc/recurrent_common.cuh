@@ -23,7 +23,7 @@ struct RnnParams {
   int n_groups;   // groups that have work
   int group_ctas; // G
   long long gx_ld, h_ld;
-  const float* gx[2];     // per direction: (rows, gx_ld) fp32, gate-interleaved columns
+  const void* gx[2];      // per direction: (rows, gx_ld) gate-interleaved columns; fp32 (nsplit 3) or bf16 (nsplit 1)
   const float* u_bias[2]; // GRU family only
   __nv_bfloat16* h_hi;    // (rows, h_ld); direction d owns columns [d*H, (d+1)*H)
   __nv_bfloat16* h_lo;

@@ -230,7 +230,7 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
     d.streams = sched.streams
     d.flags = plan.gru_flags
     for k in range(nd):
-        d.gx[k] = gx.data_ptr() + 4 * k * 4 * H
+        d.gx[k] = gx.data_ptr() + gx.element_size() * k * 4 * H
         d.w_hi[k] = layer.lat[k][0].data_ptr()
         d.w_lo[k] = layer.lat[k][1].data_ptr() if plan.split else None
         d.u_bias[k] = layer.u_bias[k].data_ptr() if layer.u_bias[k] is not None else None
@@ -265,8 +265,13 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
     H, nd = plan.hidden, plan.n_dirs
     state_out = []
     for l, layer in enumerate(plan.rec_layers):
-        gx = ws.get(f"{tag}.gx", rows, nd * 4 * H, torch.float32)
-        layer.upward(a_hi, a_lo, rows, "identity", OUT_F32, out=(gx, None))
+        # input projection of every frame: fp32 in the fp32-accurate mode, bf16 in bf16 mode
+        if plan.split:
+            gx = ws.get(f"{tag}.gx", rows, nd * 4 * H, torch.float32)
+            layer.upward(a_hi, a_lo, rows, "identity", OUT_F32, out=(gx, None))
+        else:
+            gx = ws.get(f"{tag}.gx16", rows, nd * 4 * H, torch.bfloat16)
+            layer.upward(a_hi, a_lo, rows, "identity", OUT_BF16, out=(gx, None))
         slot = l if want_state else l % 2  # a carried state needs every layer's h kept
         h_hi = ws.get(f"{tag}.h{slot}.hi", rows, nd * H, torch.bfloat16)
         h_lo = ws.get(f"{tag}.h{slot}.lo", rows, nd * H, torch.bfloat16) if plan.split else None
@@ -339,9 +344,12 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
             src = start + np.minimum(step, l_row - 1)
             dst = start + step - timedelay
             keep = step >= timedelay
-            if not fix_timedelay_tail:
-                keep &= step < l_row  # predict_folds.py:50,60-61: rows are written only while utt_len > t (quirk Q4)
             dst = np.where(keep, dst, -1)
+            if not fix_timedelay_tail:
+                # predict_folds.py:50,60-61: rows are written only while utt_len > t (quirk Q4), so the last `timedelay`
+                # frames of every utterance stay 0; the head zero-fills exactly those rows (entry -2 - row) and every
+                # output row is written once -- no separate memset of the (N, C) matrix
+                dst = np.where(keep & (step >= l_row), -2 - dst, dst)
             if len(maps) >= 8:
                 maps.pop(next(iter(maps)))
             maps[mkey] = (torch.from_numpy(src.astype(np.int32)).to(device),
@@ -393,7 +401,8 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
             logits.append(lg)
         on_dev = isinstance(out, torch.Tensor) and out.is_cuda
         out_dev = out[f_lo:f_hi] if on_dev else ws.get("rnn.out", f_hi - f_lo, n_out, torch.float32)
-        out_dev.zero_()
+        if np.any(lens < timedelay):  # utterances shorter than the delay have rows no packed row maps to
+            out_dev.zero_()
         prior = _dev_vec(head.prior, device)
         rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
         ops.head(logits, n_out, rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
