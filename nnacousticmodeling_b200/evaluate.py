@@ -149,3 +149,118 @@ def evaluateModelTestTri(model, data, offsets, PIP, LMW, ap=None, GPUID=0, testO
     p39 = Path(lab_dir, "vysledek_" + testOrDev + "_p39.txt")
     convert_results(str(Path(recogdir, "phones.60-48-39.map")), str(res), str(p39))
     return computeWER(loadMlf(str(p39)), loadMlf(str(Path(recogdir, testOrDev + "_ref.mlf"))), True)
+
+
+def main(arg_list=None):
+    """scripts/common/evaluate.py:53-214 -- same flags and data flow (splice -> transform -> i-vector concat on the
+    device, evaluate.py:163-171), model / NNWithRPL construction (:101-138), then evaluateModelTestTri.  Extensions:
+    ``--precision bf16|fp32`` and ``--tmp-dir`` for the .lab directory (the reference hard-codes 'lab')."""
+    import argparse
+    import sys
+
+    from . import functions as F
+    from .features import adapt_transform, loadKaldiFeatureTransform, splice_and_transform
+    from .networks import Classifier, get_nn, is_nn_recurrent, load_npz
+
+    parser = argparse.ArgumentParser(description="B200 evaluation step (evaluate.py drop-in)")
+    parser.add_argument("--network", "-n", default="ff")
+    parser.add_argument("--model", "-m", default="")
+    parser.add_argument("--units", "-u", type=int, nargs="+", default=[1024])
+    parser.add_argument("--layers", "-l", type=int, default=2)
+    parser.add_argument("--activation", "-a", default="relu")
+    parser.add_argument("--tdnn-ksize", type=int, nargs="+", default=[5])
+    parser.add_argument("--timedelay", type=int, default=0)  # parsed and never used, as in the reference (quirk Q4)
+    parser.add_argument("--splice", type=int, default=0)
+    parser.add_argument("--dropout", "-d", type=float, nargs="+", default=[0])
+    parser.add_argument("--tri", action="store_true")
+    parser.add_argument("--ft", default="final.feature_transform")
+    parser.add_argument("--data-dir", default="data/fmllr")
+    parser.add_argument("--offset-dir", default="data")
+    parser.add_argument("--ivector-dir")
+    parser.add_argument("--recog-dir", required=True)
+    parser.add_argument("--utt-list-dir", default="data")
+    parser.add_argument("--data", default="data_{}.npy")
+    parser.add_argument("--offsets", default="offsets_{}.npy")
+    parser.add_argument("--ivectors", default="ivectors_{}.npy")
+    parser.add_argument("--PIP", type=float, default=20)
+    parser.add_argument("--LMW", type=float, default=1)
+    parser.add_argument("--ap-coef", type=float, default=1)
+    parser.add_argument("--ap-file", default="log_ap_Kaldi1909.npy")
+    parser.add_argument("--gpu", "-g", type=int, default=0)
+    parser.add_argument("--test-or-dev", default="test")
+    parser.add_argument("--rpl", action="store_true")
+    parser.add_argument("--no-rpl-layer", action="store_true")
+    parser.add_argument("--rpl-model", default="result_rpl/model")
+    parser.add_argument("--fold-model-dir", default="fold_models")
+    parser.add_argument("--fold-network-pattern", default="fold_{0}.npz")
+    parser.add_argument("--master-network", default="-")
+    parser.add_argument("--no-progress", action="store_true")
+    parser.add_argument("--precision", default=None, choices=["fp32", "bf16"])
+    parser.add_argument("--tmp-dir", default="lab")
+    args = parser.parse_args(list(map(str, arg_list)) if arg_list is not None else None)
+
+    num_classes = 1909 if args.tri else 39
+    if args.activation not in ("sigmoid", "tanh", "relu"):
+        print("Wrong activation function specified")
+        return None
+    activation = F.resolve(args.activation)
+
+    def new_net(path):
+        m = get_nn(args.network, args.layers, args.units, num_classes, activation, args.tdnn_ksize, args.dropout)
+        if args.precision:
+            m.precision = args.precision
+        load_npz(str(path), Classifier(m))
+        return m
+
+    if args.rpl:
+        master = None
+        if args.master_network != "-":
+            print("Loading master network")
+            master = new_net(args.master_network)
+        folds = []
+        if args.fold_network_pattern != "-":
+            while True:
+                f = Path(args.fold_model_dir, args.fold_network_pattern.format(len(folds)))
+                if not f.is_file():
+                    break
+                print("Loading fold {} network".format(len(folds)))
+                folds.append(new_net(f))
+        rpl = None
+        if args.rpl_model != "-" and not args.no_rpl_layer:
+            rpl = RPL4(num_classes)
+            with np.load(str(args.rpl_model)) as z:
+                rpl.load_params({k: z[k] for k in z.files})
+        model = NNWithRPL(master, folds, rpl)
+    else:
+        model = new_net(args.model)
+
+    recurrent = is_nn_recurrent(args.network)
+    splice = (sum(args.tdnn_ksize) - len(args.tdnn_ksize)) // 2 if args.network == "tdnn" else args.splice
+    ft = None
+    if args.ft is not None and args.ft != "-":
+        ft = adapt_transform(loadKaldiFeatureTransform(str(Path(args.data_dir, args.ft))), args.network, splice,
+                             recurrent)
+    data = np.load(str(Path(args.data_dir, args.data.format(args.test_or_dev))))
+    ivectors = None
+    if args.ivector_dir is not None:
+        ivectors = np.load(str(Path(args.ivector_dir, args.ivectors.format(args.test_or_dev))))
+    # evaluate.py:163-171: splicing -> applyKaldiFeatureTransform -> concatenate i-vectors, here one K1 pass
+    if splice > 0 or ft is not None or ivectors is not None:
+        data = splice_and_transform(data, splice, ft, ivectors, device=args.gpu)
+    offsets = np.load(str(Path(args.offset_dir, args.offsets.format(args.test_or_dev))))
+    if not args.tri:
+        print("Monophones not implemented")
+        return None
+    ap = np.float32(args.ap_coef) * np.load(str(Path(args.recog_dir, args.ap_file))).astype(np.float32)
+    per = evaluateModelTestTri(model, data, offsets, args.PIP, args.LMW, ap=ap, GPUID=args.gpu,
+                               testOrDev=args.test_or_dev, tmpDir=args.tmp_dir, uttlistdir=args.utt_list_dir,
+                               recogdir=args.recog_dir, progress=not args.no_progress, rnn=recurrent)
+    if per is None:
+        print("Network outputs written to {}; PhoneRecog is not part of this package".format(args.tmp_dir))
+    elif per != -1:
+        print("PER: {0:.2f} %".format(per))
+    return per
+
+
+if __name__ == "__main__":
+    main()

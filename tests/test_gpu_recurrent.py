@@ -203,3 +203,25 @@ def test_predict_peephole_lstm(nn, golden_dir, units, layers, lens, td):
     m.reset_state()
     for t in range(4):
         assert np.abs(m(xs[t]) - ref(xs[t])).max() < 1e-3
+
+
+@pytest.mark.parametrize("network", ["lstm", "gru", "peepholelstm"])
+def test_timedelay_longer_than_some_utterances_and_empty_input(nn, network):
+    """Edge cases of predict_folds.py:34-64: utterances shorter than the delay produce only zero rows (quirk Q4), and
+    an empty feature matrix gives an empty output."""
+    lens = [2, 9, 1, 4, 30]
+    td = 3
+    off = _offsets(lens)
+    x = np.random.default_rng(5).standard_normal((off[-1], 40)).astype(np.float32)
+    p = O.init_recurrent(np.random.default_rng(6), network, 40, 64, 2, 39, bias_scale=0.2)
+    m = nn.get_nn(network, 2, [64], 39, nn.F.relu, [5])
+    m.load_params(p)
+    want = O.predict(O.RecurrentNet(p, network, 2), x, off, network, 1, td, None)
+    got = nn.predict(m, x, off, 39, network, 0, 1, td, None, progress=False)
+    assert np.abs(got - want).max() < 1e-3
+    assert np.all(got[off[0]:off[1]] == 0) and np.all(got[off[2]:off[3]] == 0)  # shorter than the delay
+    pinned = nn.empty_pinned((off[-1], 39))
+    pinned[:] = 7.0  # a caller-owned buffer with stale contents: every row must still be written
+    assert np.array_equal(nn.predict(m, x, off, 39, network, 0, 1, td, None, progress=False, out=pinned), got)
+    empty = nn.predict(m, x[:0], np.zeros(1, np.int32), 39, network, 0, 1, td, None, progress=False)
+    assert empty.shape == (0, 39)

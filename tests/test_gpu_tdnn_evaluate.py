@@ -197,3 +197,40 @@ def test_predict_folds_cli_dev_mode_and_fold_mode(nn, golden_dir, tmp_path):
     acc = acc / n_folds
     want = acc - O.logsum(acc, axis=1)
     assert np.abs(got - want).max() < 1e-3
+
+
+def test_evaluate_cli_matches_reference_data_flow(nn, golden_dir, tmp_path):
+    """evaluate.py:53-214: splice -> transform -> i-vector concat -> net -> minus ap_coef * log_ap -> log-softmax -> .lab."""
+    import shutil
+    n_out = 1909
+    lens = [64, 80, 37]
+    off = _offsets(lens)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    iv = (0.5 * rng.standard_normal((off[-1], 20))).astype(np.float32)
+    data_dir, recog, lists, ivd = (tmp_path / d for d in ("data", "recog", "lists", "iv"))
+    for d in (data_dir, recog, lists, ivd):
+        d.mkdir()
+    shutil.copy(os.path.join(golden_dir, "final.feature_transform"), str(data_dir / "final.feature_transform"))
+    shutil.copy(os.path.join(golden_dir, "log_ap_Kaldi1909.npy"), str(recog / "log_ap_Kaldi1909.npy"))
+    np.save(str(data_dir / "data_test.npy"), x)
+    np.save(str(lists / "offsets_test.npy"), off)
+    np.save(str(ivd / "ivectors_test.npy"), iv)
+    names = ["a/u0", "a/u1", "b/u2"]
+    (lists / "test.list").write_text("\n".join(names) + "\n")
+    m, p = _mlp(nn, 33, 460, 128, 2, n_out)
+    nn.save_npz(str(tmp_path / "model.npz"), nn.Classifier(m))
+    lab = tmp_path / "lab"
+    per = nn.evaluate.main(["--network", "ff", "--model", str(tmp_path / "model.npz"), "--units", 128, "--layers", 2,
+                            "--splice", 5, "--tri", "--data-dir", str(data_dir), "--offset-dir", str(lists),
+                            "--ivector-dir", str(ivd), "--recog-dir", str(recog), "--utt-list-dir", str(lists),
+                            "--ap-coef", 0.7, "--no-progress", "--tmp-dir", str(lab)])
+    assert per is None  # decoder not present
+    oft = O.load_kaldi_feature_transform(os.path.join(golden_dir, "final.feature_transform"))
+    feats = np.concatenate((O.apply_kaldi_feature_transform(O.splicing(x, range(-5, 6)), oft), iv), axis=1)
+    ap = (np.float32(0.7) * np.load(os.path.join(golden_dir, "log_ap_Kaldi1909.npy")).astype(np.float32)).reshape(1, -1)
+    want = O.evaluate_forward(lambda v: O.mlp_forward(p, v, 2), feats, off, ap=ap, rnn=False)
+    for i, name in enumerate(names):
+        got = O.load_bin(str(lab / (name + ".lab")))
+        assert got.shape == (lens[i], n_out)
+        assert np.abs(got - want[i]).max() < 1e-3
