@@ -149,7 +149,9 @@ typedef struct NnamRnnDesc {
                           nsplit == 1 (in bf16 mode it is the largest HBM stream of a layer) */
   long long gx_ld;
   const void* w_hi[2]; /* per direction: lateral weights (4H, H) bf16 K-major.  LSTM: Chainer lateral/W as is.
-                          GRU family: rows interleaved per unit [U_z, U_r (or 0), U, 0]; gx and u_bias likewise */
+                          GRU family: rows interleaved per unit [U_z, U_r (or 0), U, 0]; gx and u_bias likewise.
+                          PEEPHOLE (unidirectional): [0] = lateral/W, [1] = peephole block, rows per unit
+                          [0, peep_i, peep_f, peep_o] (L.StatefulPeepholeLSTM, chainer_networks.py:103-121) */
   const void* w_lo[2];
   long long w_ld;
   const float* u_bias[2]; /* GRU family: hidden-side biases, applied from the second step on (MGRU.py:70-83) */

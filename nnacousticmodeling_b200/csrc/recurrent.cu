@@ -41,7 +41,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 }
 
 // One kernel for both cell families.
-//   CELL   : NNAM_CELL_LSTM | NNAM_CELL_GRU
+//   CELL   : NNAM_CELL_LSTM | NNAM_CELL_GRU | NNAM_CELL_PEEPHOLE (a second resident block [0, P_i, P_f, P_o] per unit
+//            next to the lateral slice, a second operand tile for the cell state, two exchanges per step)
 //   M_ROWS : gate rows per CTA (128, or 64 when the slice would not fit in shared memory)
 //   NB     : utterance slots per stream (= N of the MMA)
 //   NSPLIT : 1 bf16 | 3 bf16x3
@@ -75,23 +76,29 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
 
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  constexpr bool PEEP = CELL == NNAM_CELL_PEEPHOLE;
+  constexpr int SETS = PEEP ? 2 : 1;  // resident weight blocks (lateral [+ peephole]) and operand tiles (h [+ c])
   uint8_t* w_hi_s = smem;
   uint8_t* w_lo_s = w_hi_s + (NSPLIT == 3 ? KB * W_BLOCK : 0);
-  uint8_t* tiles = w_lo_s + KB * W_BLOCK;
-  uint8_t* h_hi_s = tiles + stream * (PLANES * KB * H_BLOCK);
+  uint8_t* pw_hi_s = w_lo_s + KB * W_BLOCK;                      // peephole block (PEEP only)
+  uint8_t* pw_lo_s = pw_hi_s + (NSPLIT == 3 ? KB * W_BLOCK : 0);
+  uint8_t* tiles = w_hi_s + SETS * PLANES * KB * W_BLOCK;
+  uint8_t* h_hi_s = tiles + stream * (SETS * PLANES * KB * H_BLOCK);
   uint8_t* h_lo_s = h_hi_s + (NSPLIT == 3 ? KB * H_BLOCK : 0);
+  uint8_t* c_hi_s = h_hi_s + PLANES * KB * H_BLOCK;               // cell-state tile (PEEP only)
+  uint8_t* c_lo_s = c_hi_s + (NSPLIT == 3 ? KB * H_BLOCK : 0);
   constexpr int UNITS = M_ROWS / 4;              // hidden units per CTA
   constexpr int STAGE_BYTES = NB * UNITS * 2;     // one plane of this stream's freshly computed slice (NB x UNITS bf16)
-  uint8_t* stage_hi = tiles + S * (PLANES * KB * H_BLOCK) + stream * (PLANES * STAGE_BYTES);
+  uint8_t* stage_hi = tiles + S * (SETS * PLANES * KB * H_BLOCK) + stream * (PLANES * STAGE_BYTES);
   uint8_t* stage_lo = stage_hi + STAGE_BYTES;
-  uint8_t* tail = tiles + S * (PLANES * KB * H_BLOCK) + S * (PLANES * STAGE_BYTES);
+  uint8_t* tail = tiles + S * (SETS * PLANES * KB * H_BLOCK) + S * (PLANES * STAGE_BYTES);
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(tail);
   uint64_t* bar_mma = bar_w + 1 + stream;
   uint64_t* bar_h = bar_w + 1 + S + stream;  // this stream's h tile has landed (TMA complete_tx)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 1 + 2 * S);
   int* s_len = reinterpret_cast<int*>(tmem_slot + 2) + stream * NB;
   int* s_base = reinterpret_cast<int*>(tmem_slot + 2) + S * NB + stream * (BASE_SMEM + 1);
-  constexpr int TMEM_COLS = S * NB < 32 ? 32 : S * NB;
+  constexpr int TMEM_COLS = SETS * S * NB < 32 ? 32 : SETS * S * NB;  // D1 (lateral . h) [+ D2 (peephole . c)]
   static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM allocations are powers of two");
 
   if (tid == 0) {
@@ -125,6 +132,8 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
   const uint32_t tmem_lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + u_lo;
   const uint32_t idesc = make_idesc_bf16_f32(M_ROWS, NB);
   const uint32_t h_hi_sa = smem_u32(h_hi_s), h_lo_sa = smem_u32(h_lo_s);
+  const uint32_t c_hi_sa = smem_u32(c_hi_s), c_lo_sa = smem_u32(c_lo_s);
+  const uint32_t tmem_d2 = tmem_base + static_cast<uint32_t>(S * NB);  // second accumulator of this stream (PEEP)
   const bool gru_reset = (p.gru_flags & 1) != 0;
   const int gru_act = (p.gru_flags >> 1) & 3;
 
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
   // Wait until every CTA of the group has published its slice of the previous exchange, then pull the whole tile
   // (exchange slot `slot` of this lane) into the swizzled B-operand tile: KB (x planes) TMA box loads, one thread.
   // Only the issuing thread waits; the others go on to prefetch gx and meet it again at the MMA barrier.
-  auto group_fetch = [&](int slot) {
+  auto group_fetch = [&](int slot, bool into_c = false) {
     if (warp_s == 0) {  // warp-uniform loop, one elected lane issues (keeps the TMA operands in uniform registers)
       const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
       while (ld_acquire_gpu(counter) < target) {
@@ -153,9 +162,11 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
         fence_proxy_async_all();  // the peers' generic-proxy stores -> visible to this async-proxy (TMA) read
         mbar_expect_tx(bar_h, static_cast<uint32_t>(KB * H_BLOCK * PLANES));
         const int row = (lane_id * 4 + slot) * NB;
+        uint8_t* t_hi = into_c ? c_hi_s : h_hi_s;
+        uint8_t* t_lo = into_c ? c_lo_s : h_lo_s;
         for (int kb = 0; kb < KB; ++kb) {
-          tma_load_2d(h_hi_s + kb * H_BLOCK, &tmaps.x_hi, bar_h, kb * 64, row);
-          if (NSPLIT == 3) tma_load_2d(h_lo_s + kb * H_BLOCK, &tmaps.x_lo, bar_h, kb * 64, row);
+          tma_load_2d(t_hi + kb * H_BLOCK, &tmaps.x_hi, bar_h, kb * 64, row);
+          if (NSPLIT == 3) tma_load_2d(t_lo + kb * H_BLOCK, &tmaps.x_lo, bar_h, kb * 64, row);
         }
       }
       __syncwarp();
@@ -169,7 +180,8 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
     ++steps_done;
   };
   // D[M_ROWS x NB] = W_slice . tile^T (3 passes in bf16x3 mode): issue (one thread) ...
-  auto mma_issue = [&](bool via_tma) {
+  // mode 0: D1 = lateral . h      mode 1 (PEEP): D1 = lateral . h and D2 = peephole . c      mode 2 (PEEP): D2 = peephole . c
+  auto mma_issue = [&](bool via_tma, int mode = 0) {
     if (!via_tma) {  // tile staged by the threads with cp.async (initial-state rows of the stateful API)
       cp_async_wait_all();
       fence_proxy_async_smem();
@@ -181,30 +193,36 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
       if (via_tma) mbar_wait(bar_h, h_phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t wd_hi = make_sw128_kmajor_desc(smem_u32(w_hi_s));
-        const uint64_t wd_lo = make_sw128_kmajor_desc(smem_u32(w_lo_s));
-        const uint64_t hd_hi = make_sw128_kmajor_desc(h_hi_sa);
-        const uint64_t hd_lo = make_sw128_kmajor_desc(h_lo_sa);
-        uint32_t accum = 0;
 #pragma unroll
-        for (int pass = 0; pass < NSPLIT; ++pass) {
-          const uint64_t wa = pass == 2 ? wd_lo : wd_hi;
-          const uint64_t ha = pass == 1 ? hd_lo : hd_hi;
-          if (KBT > 0) {
+        for (int set = 0; set < SETS; ++set) {
+          if (set == 0 && mode == 2) continue;
+          if (set == 1 && mode == 0) continue;
+          const uint64_t wd_hi = make_sw128_kmajor_desc(smem_u32(set == 0 ? w_hi_s : pw_hi_s));
+          const uint64_t wd_lo = make_sw128_kmajor_desc(smem_u32(set == 0 ? w_lo_s : pw_lo_s));
+          const uint64_t hd_hi = make_sw128_kmajor_desc(set == 0 ? h_hi_sa : c_hi_sa);
+          const uint64_t hd_lo = make_sw128_kmajor_desc(set == 0 ? h_lo_sa : c_lo_sa);
+          const uint32_t d = set == 0 ? tmem_base : tmem_d2;
+          uint32_t accum = 0;
 #pragma unroll
-            for (int kb = 0; kb < KBT; ++kb)
+          for (int pass = 0; pass < NSPLIT; ++pass) {
+            const uint64_t wa = pass == 2 ? wd_lo : wd_hi;
+            const uint64_t ha = pass == 1 ? hd_lo : hd_hi;
+            if (KBT > 0) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
-                accum = 1;
-              }
-          } else {
-            for (int kb = 0; kb < KB; ++kb)
+              for (int kb = 0; kb < KBT; ++kb)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                umma_bf16(tmem_base, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
-                accum = 1;
-              }
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(d, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
+                  accum = 1;
+                }
+            } else {
+              for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  umma_bf16(d, wa + ((kb * W_BLOCK + k * 32) >> 4), ha + ((kb * H_BLOCK + k * 32) >> 4), idesc, accum);
+                  accum = 1;
+                }
+            }
           }
         }
         umma_commit(bar_mma);
@@ -214,6 +232,30 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
     if (via_tma) h_phase ^= 1;
   };
   // ... and collect: on return acc[] = my (row, slots) of D
+  auto tmem_read = [&](uint32_t addr, float (&acc)[NBT]) {
+#pragma unroll
+    for (int c0 = 0; c0 < NBT; c0 += (NBT >= 16 ? 16 : NBT)) {
+      if (NBT >= 16) {
+        uint32_t r[16];
+        tmem_ld16(addr + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[c0 + j] = __uint_as_float(r[j]);
+      } else {
+        uint32_t r[8];
+        tmem_ld8(addr + c0, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < (NBT < 8 ? NBT : 8); ++j) acc[c0 + j] = __uint_as_float(r[j]);
+      }
+    }
+  };
+  // wait for the MMAs, then read D2 (PEEP) into acc2 -- the caller reads D1 through mma_collect
+  auto mma_wait = [&]() {
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+  };
   auto mma_collect = [&](float (&acc)[NBT]) {
     mbar_wait(bar_mma, mma_phase);
     mma_phase ^= 1;
@@ -243,10 +285,14 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
     // ---- (re)load this CTA's slice of the direction's lateral weights; all streams work on one direction at a time
     __syncthreads();
     if (tid == 0) {
-      mbar_expect_tx(bar_w, static_cast<uint32_t>(KB * W_BLOCK * PLANES));
+      mbar_expect_tx(bar_w, static_cast<uint32_t>(SETS * KB * W_BLOCK * PLANES));
       for (int kb = 0; kb < KB; ++kb) {
         tma_load_2d(w_hi_s + kb * W_BLOCK, &tmaps.w_hi[d], bar_w, kb * 64, rank * M_ROWS);
         if (NSPLIT == 3) tma_load_2d(w_lo_s + kb * W_BLOCK, &tmaps.w_lo[d], bar_w, kb * 64, rank * M_ROWS);
+        if (PEEP) {  // the peephole block travels in the (unused) direction-1 slot of the descriptor
+          tma_load_2d(pw_hi_s + kb * W_BLOCK, &tmaps.w_hi[1], bar_w, kb * 64, rank * M_ROWS);
+          if (NSPLIT == 3) tma_load_2d(pw_lo_s + kb * W_BLOCK, &tmaps.w_lo[1], bar_w, kb * 64, rank * M_ROWS);
+        }
       }
     }
     mbar_wait(bar_w, w_phase);
@@ -305,7 +351,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
           const long long o = (static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0 + unit;
           if (CELL == NNAM_CELL_LSTM) {
             if (p.c0 != nullptr) st_reg[m] = p.c0[o];
-          } else if (has_h0) {
+          } else if (CELL == NNAM_CELL_GRU && has_h0) {
             st_reg[m] = __bfloat162float(p.h0_hi[o]) + (NSPLIT == 3 ? __bfloat162float(p.h0_lo[o]) : 0.0f);
           }
         }
@@ -375,7 +421,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
           // tensor core works (tcgen05.mma issue back-pressures the issuing thread, so it must come last)
           if (s + 1 < T) load_gx(s + 1, gxn);
           PROF_MARK(2);
-          mma_issue(s > 0);
+          mma_issue(s > 0, PEEP ? 1 : 0);
           PROF_MARK(0);
           mma_collect(acc);
         } else {
@@ -384,7 +430,63 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
           if (s + 1 < T) load_gx(s + 1, gxn);
         }
 
-        if (CELL == NNAM_CELL_LSTM) {
+        if (PEEP) {
+          // ---- L.StatefulPeepholeLSTM (chainer_networks.py:103-121): i, f see P_i c, P_f c; o sees P_o c' -- the new
+          // cell state has to go round the group before the output gate can be formed: two exchanges per step.
+          // The c tile still holds c_{s-1} from phase 2 of the previous step, so phase 1 only fetched h.
+          const uint32_t lane_addr2 = tmem_d2 + (static_cast<uint32_t>(quarter * 32) << 16) + u_lo;
+          float acc2[NBT];
+          if (have_h) {
+            tc_fence_after();
+            tmem_read(lane_addr2, acc2);
+            tc_fence_before();
+          } else {
+#pragma unroll
+            for (int j = 0; j < NBT; ++j) acc2[j] = 0.0f;
+          }
+          float o_pre[NBT / 4];
+#pragma unroll
+          for (int m = 0; m < NBT / 4; ++m) {
+            o_pre[m] = 0.0f;
+            if (u_lo + 4 * m >= n_s) break;  // warp-uniform
+            float x[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float v = acc[4 * m + i] + gxr[4 * m + i] + ((gate == 1 || gate == 2) ? acc2[4 * m + i] : 0.0f);
+              const float t = tanh_sel<FAST_TANH>(gate == 0 ? v : 0.5f * v);
+              x[i] = gate == 0 ? t : (gate == 3 ? v : fmaf(t, 0.5f, 0.5f));  // the output gate stays a pre-activation
+            }
+            quad_transpose(x, gate);  // x = {a, i, f, o_pre} of utterance u = u_lo + 4m + gate
+            const int u = u_lo + 4 * m + gate;
+            const float c_new = fmaf(x[0], x[1], x[2] * st_reg[m]);
+            o_pre[m] = x[3];
+            if (row_valid && u < n_s) {
+              st_reg[m] = c_new;
+              stage_put(u, c_new);
+            }
+          }
+          stage_flush(nullptr, nullptr, n_s, s, 2 + (s & 1));
+          group_publish();  // c' slices are out
+          group_fetch(2 + (s & 1), true);
+          mma_issue(true, 2);  // D2 = peephole block . c'
+          mma_wait();
+          tmem_read(lane_addr2, acc2);
+          tc_fence_before();
+#pragma unroll
+          for (int m = 0; m < NBT / 4; ++m) {
+            if (u_lo + 4 * m >= n_s) break;
+            float y[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[i] = gate == 3 ? acc2[4 * m + i] : 0.0f;
+            quad_transpose(y, gate);  // y[3] = (P_o c')[unit] of utterance u
+            const int u = u_lo + 4 * m + gate;
+            const float o = fmaf(tanh_sel<FAST_TANH>(0.5f * (o_pre[m] + y[3])), 0.5f, 0.5f);
+            const float h_new = o * tanh_sel<FAST_TANH>(st_reg[m]);
+            if (row_valid && u < n_s) stage_put(u, h_new);
+          }
+          stage_flush(p.h_hi, p.h_lo, n_s, s, s & 1);
+          PROF_MARK(5);
+        } else if (CELL == NNAM_CELL_LSTM) {
           // ---- gates, quad transpose, cell update  (chainer F.lstm: c = tanh(a) s(i) + s(f) c; h = s(o) tanh(c))
 #pragma unroll
           for (int m = 0; m < NBT / 4; ++m) {
@@ -504,19 +606,29 @@ struct RnnCfg {
   X(128, 16, 3, 0, 2, 8) X(128, 32, 3, 0, 1, 8) X(64, 16, 3, 0, 2, 8) X(64, 32, 3, 0, 1, 8)        \
   X(64, 16, 3, 0, 1, 8)
 
+// PeepholeLSTM: lateral slice + peephole block + two operand tiles must fit, so 64-row slices only
+#define NNAM_PEEP_INSTANCES(X) X(64, 32, 1, 8, 1, 8) X(64, 32, 1, 0, 1, 8) X(64, 16, 1, 0, 1, 8) X(64, 32, 3, 0, 1, 8) X(64, 16, 3, 0, 1, 8)
+
+static const RnnCfg kPeepCfgs[] = {
+#define X(M, NBV, NS, KBTV, SV, WPSV) {M, NBV, NS, KBTV, SV, WPSV},
+    NNAM_PEEP_INSTANCES(X)
+#undef X
+};
+
 static const RnnCfg kRnnCfgs[] = {
 #define X(M, NBV, NS, KBTV, SV, WPSV) {M, NBV, NS, KBTV, SV, WPSV},
     NNAM_RNN_INSTANCES(X)
 #undef X
 };
 
-static size_t rnn_smem_bytes(const RnnCfg& c, int hidden) {
+static size_t rnn_smem_bytes(const RnnCfg& c, int hidden, int cell) {
   const size_t kb = hidden / 64;
   const size_t planes = c.ns == 3 ? 2 : 1;
+  const size_t sets = cell == NNAM_CELL_PEEPHOLE ? 2 : 1;  // lateral [+ peephole] blocks, h [+ c] tiles
   const size_t base_smem = c.s >= 4 ? 1024 : 2048;
   const size_t stage = planes * static_cast<size_t>(c.s) * c.nb * (c.m / 4) * 2;
-  return kb * planes * (static_cast<size_t>(c.m) * 128 + static_cast<size_t>(c.s) * c.nb * 128) + stage + 8 * (1 + 2 * c.s) +
-         16 + static_cast<size_t>(c.s) * (c.nb + base_smem + 1) * 4 + 1024;
+  return sets * kb * planes * (static_cast<size_t>(c.m) * 128 + static_cast<size_t>(c.s) * c.nb * 128) + stage +
+         8 * (1 + 2 * c.s) + 16 + static_cast<size_t>(c.s) * (c.nb + base_smem + 1) * 4 + 1024;
 }
 
 // The instance used for (hidden, slots per stream, precision), or nullptr.
@@ -524,11 +636,14 @@ static const RnnCfg* rnn_pick_cfg(int cell, int hidden, int nb, int nsplit) {
   const int kbt = hidden / 64;
   // the opt-in cluster experiment replaces the single-stream instance
   const bool single = (4 * hidden) % 128 == 0 && rnn_cluster_groups(cell, hidden, nb, nsplit) > 0;
-  for (const RnnCfg& c : kRnnCfgs) {
+  const RnnCfg* list = cell == NNAM_CELL_PEEPHOLE ? kPeepCfgs : kRnnCfgs;
+  const size_t n_list = cell == NNAM_CELL_PEEPHOLE ? sizeof(kPeepCfgs) / sizeof(RnnCfg) : sizeof(kRnnCfgs) / sizeof(RnnCfg);
+  for (size_t i = 0; i < n_list; ++i) {
+    const RnnCfg& c = list[i];
     if (c.nb != nb || c.ns != nsplit || (c.kbt != 0 && c.kbt != kbt)) continue;
     if (single && c.s != 1) continue;
     if ((4 * hidden) % c.m) continue;
-    if (rnn_smem_bytes(c, hidden) > 227 * 1024) continue;
+    if (rnn_smem_bytes(c, hidden, cell) > 227 * 1024) continue;
     if (sm_count() < 4 * hidden / c.m) continue;
     return &c;
   }
@@ -550,6 +665,14 @@ static int launch_rnn_instance(const RnnTmaps& tm, const RnnParams& p, int grid,
 
 static int launch_rnn(int cell, const RnnCfg& c, const RnnTmaps& tm, const RnnParams& p, int grid, size_t smem,
                       cudaStream_t stream) {
+  if (cell == NNAM_CELL_PEEPHOLE) {
+#define X(M, NBV, NS, KBTV, SV, WPSV)                                                        \
+  if (c.m == M && c.nb == NBV && c.ns == NS && c.kbt == KBTV && c.s == SV && c.wps == WPSV) \
+    return launch_rnn_instance<NNAM_CELL_PEEPHOLE, M, NBV, NS, KBTV, SV, WPSV>(tm, p, grid, smem, stream);
+    NNAM_PEEP_INSTANCES(X)
+#undef X
+    return set_error(NNAM_ERR_UNSUPPORTED, "rnn: no peephole kernel instance for this configuration");
+  }
 #define X(M, NBV, NS, KBTV, SV, WPSV)                                                                         \
   if (c.m == M && c.nb == NBV && c.ns == NS && c.kbt == KBTV && c.s == SV && c.wps == WPSV)                  \
     return cell == NNAM_CELL_GRU ? launch_rnn_instance<NNAM_CELL_GRU, M, NBV, NS, KBTV, SV, WPSV>(tm, p, grid, smem, stream) \
@@ -561,8 +684,11 @@ static int launch_rnn(int cell, const RnnCfg& c, const RnnTmaps& tm, const RnnPa
 
 int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   if (d == nullptr) return set_error(NNAM_ERR_ARG, "rnn: NULL descriptor");
-  if (d->cell != NNAM_CELL_LSTM && d->cell != NNAM_CELL_GRU)
+  if (d->cell != NNAM_CELL_LSTM && d->cell != NNAM_CELL_GRU && d->cell != NNAM_CELL_PEEPHOLE)
     return set_error(NNAM_ERR_UNSUPPORTED, "rnn: cell kind %d not implemented", d->cell);
+  if (d->cell == NNAM_CELL_PEEPHOLE && (d->n_dirs != 1 || d->h0_hi || d->c0 || d->c_out || !d->w_hi[1]))
+    return set_error(NNAM_ERR_ARG, "rnn: the peephole cell is unidirectional, takes no carried state here, and needs "
+                     "its peephole block in w_hi[1]");
   const int H = d->hidden;
   if (H <= 0 || H % 64) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: hidden size must be a multiple of 64 (got %d)", H);
   if (d->n_dirs != 1 && d->n_dirs != 2) return set_error(NNAM_ERR_ARG, "rnn: n_dirs must be 1 or 2");
@@ -591,7 +717,8 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
 
   RnnTmaps tm;
   int rc;
-  for (int k = 0; k < d->n_dirs; ++k) {
+  const int n_blocks = d->cell == NNAM_CELL_PEEPHOLE ? 2 : d->n_dirs;  // peephole: [1] is the peephole block
+  for (int k = 0; k < n_blocks; ++k) {
     if ((rc = encode_tmap_bf16_2d(&tm.w_hi[k], d->w_hi[k], H, gate_rows, d->w_ld, 64, m_rows))) return rc;
     if (d->nsplit == 3) {
       if (!d->w_lo[k]) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs w_lo");
@@ -600,7 +727,7 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
       tm.w_lo[k] = tm.w_hi[k];
     }
   }
-  if (d->n_dirs == 1) {
+  if (n_blocks == 1) {
     tm.w_hi[1] = tm.w_hi[0];
     tm.w_lo[1] = tm.w_lo[0];
   }
@@ -655,12 +782,12 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   if (use_cluster) return rnn_cluster_launch(tm, p, G, H, stream);
   cudaError_t e = cudaMemsetAsync(d->counters, 0, sizeof(unsigned int) * d->n_groups * cfg->s, stream);
   if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaMemsetAsync");
-  return launch_rnn(d->cell, *cfg, tm, p, d->n_groups * G, rnn_smem_bytes(*cfg, H), stream);
+  return launch_rnn(d->cell, *cfg, tm, p, d->n_groups * G, rnn_smem_bytes(*cfg, H, d->cell), stream);
 }
 
 int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles,
              int* streams) {
-  if (cell != NNAM_CELL_LSTM && cell != NNAM_CELL_GRU)
+  if (cell != NNAM_CELL_LSTM && cell != NNAM_CELL_GRU && cell != NNAM_CELL_PEEPHOLE)
     return set_error(NNAM_ERR_UNSUPPORTED, "rnn: cell kind %d not implemented", cell);
   if (hidden <= 0 || hidden % 64) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: hidden size must be a multiple of 64");
   const RnnCfg* cfg = rnn_pick_cfg(cell, hidden, batch, nsplit);
@@ -674,7 +801,7 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
   // (profiles/r01_k3_phase_cycles.md); the host uses it to choose the batch width
   int cycles = cfg->s == 4 ? 12800 : (cfg->s == 2 ? 9500 : (batch == 64 ? 7900 : 6500));
   if (nsplit == 3) cycles = cycles * 7 / 5;
-  if (cell == NNAM_CELL_GRU) cycles = cycles * 3 / 2;
+  if (cell == NNAM_CELL_GRU || cell == NNAM_CELL_PEEPHOLE) cycles = cycles * 3 / 2;
   const int cl = (cfg->m == 128 && cfg->s == 1) ? rnn_cluster_groups(cell, hidden, batch, nsplit) : 0;
   if (cl > 0) {
     if (cl < *max_groups) *max_groups = cl;

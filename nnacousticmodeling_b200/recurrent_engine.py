@@ -94,9 +94,33 @@ def build_plan(plan, model):
             L.upward = LinearDev(np.concatenate(ups, axis=0), np.concatenate(upb, axis=0), dev, split)
             plan.rec_layers.append(L)
     elif net == "peepholelstm":
+        # chainer_networks.py:103-121.  The time-step engine (peephole_engine) always exists: it serves the stateful
+        # model(x) surface and shapes the persistent kernel cannot hold.  Where the lateral slice, the peephole block
+        # [0, P_i, P_f, P_o] per unit and two operand tiles fit in shared memory, whole sets run in K3.
         from . import peephole_engine
         plan.cell = CELL_PEEPHOLE
         peephole_engine.build_plan(plan, model)
+        plan.peep_persistent = False
+        try:
+            for cand in (32, 16):
+                try:
+                    ops.rnn_plan(CELL_PEEPHOLE, h, cand, 3 if split else 1)
+                    plan.peep_persistent = True
+                    break
+                except NnamError:
+                    continue
+        except Exception:  # noqa: BLE001
+            plan.peep_persistent = False
+        if plan.peep_persistent:
+            for l in range(model.layers):
+                pre = f"layer_{l}/"
+                L = RecLayer()
+                L.upward = LinearDev(p[pre + "upward/W"], p[pre + "upward/b"], dev, split)
+                pblock = _interleave4([None, p[pre + "peep_i/W"], p[pre + "peep_f/W"]], h, h)
+                pblock[3::4] = p[pre + "peep_o/W"]
+                L.lat = [to_dev_bf16(p[pre + "lateral/W"]), to_dev_bf16(pblock)]
+                L.u_bias = [None]
+                plan.rec_layers.append(L)
         return
     else:
         raise NnamError(f"network '{net}' is not implemented on the B200 path")
@@ -234,6 +258,9 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
         d.w_hi[k] = layer.lat[k][0].data_ptr()
         d.w_lo[k] = layer.lat[k][1].data_ptr() if plan.split else None
         d.u_bias[k] = layer.u_bias[k].data_ptr() if layer.u_bias[k] is not None else None
+    if plan.cell == CELL_PEEPHOLE:  # the peephole block travels in the direction-1 weight slot
+        d.w_hi[1] = layer.lat[1][0].data_ptr()
+        d.w_lo[1] = layer.lat[1][1].data_ptr() if plan.split else None
     xh, xl = aux
     d.xchg_hi = xh.data_ptr()
     d.xchg_lo = xl.data_ptr() if xl is not None else None
@@ -291,7 +318,7 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
                 aux[1].zero_()
         desc = _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0, c0, c_out, aux)
         # algorithmic lateral flops: LSTM 4 gates, GRU 3 (2 without reset gate) H x H products per frame
-        n_mats = 4 if plan.cell == CELL_LSTM else (3 if plan.gru_flags & 1 else 2)
+        n_mats = {CELL_LSTM: 4, CELL_PEEPHOLE: 7}.get(plan.cell, 3 if plan.gru_flags & 1 else 2)
         ops.rnn_seq(desc, 2.0 * rows * nd * n_mats * H * H)
         if want_state:
             state_out.append(((h_hi, h_lo), c_out))
@@ -325,7 +352,8 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         split = plan.split
         if any(p.split != split for p in plans):
             raise NnamError("forward_utterances: all ensemble members must use the same precision mode")
-        if plan.cell == CELL_PEEPHOLE:  # time-step launches over ONE batch holding every utterance of the shard
+        stepwise = plan.cell == CELL_PEEPHOLE and not plan.peep_persistent
+        if stepwise:  # time-step launches over ONE batch holding every utterance of the shard
             nb = len(lens)
             sched = Schedule(lens + timedelay, nb, 1, 1, device, 1)
         else:
@@ -387,9 +415,10 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
             if m.in_size != d_in or m.n_out != n_out:
                 raise NnamError("forward_utterances: ensemble members must share input and output sizes")
             key = (pl.cell, pl.hidden, pl.n_dirs)
-            if (pl.cell == CELL_PEEPHOLE) != (plan.cell == CELL_PEEPHOLE):
-                raise NnamError("forward_utterances: peephole and non-peephole nets cannot share one ensemble pass")
-            if pl.cell == CELL_PEEPHOLE:
+            pl_stepwise = pl.cell == CELL_PEEPHOLE and not pl.peep_persistent
+            if pl_stepwise != stepwise:
+                raise NnamError("forward_utterances: time-step and persistent nets cannot share one ensemble pass")
+            if pl_stepwise:
                 from . import peephole_engine
                 h_hi, h_lo = peephole_engine.run_layers(m, pl, sched, a_hi, a_lo, rows, ws=ws)
             else:
