@@ -42,6 +42,9 @@ WORKLOADS = {
                  desc="cfg3: 4x512 LSTM, 40 fMLLR -> 1909, timedelay 5, test-shaped 1344 utts"),
     "cfg4": dict(network="blstm", ivec=100, units=512, layers=4, utts=TEST_UTTS, frames=None, flop=46999552,
                  desc="cfg4: 4x(2x512) bidirectional LSTM, 40 fMLLR + 100 i-vector -> 1909, test-shaped 1344 utts"),
+    "cfg4g": dict(network="bgru", ivec=100, units=512, layers=4, utts=TEST_UTTS, frames=None,
+                  flop=2 * (2 * (140 * 1536 + 512 * 1536) + 3 * 2 * (1024 * 1536 + 512 * 1536) + 1024 * 1909),
+                  desc="cfg4g: 4x(2x512) bidirectional GRU, 40 fMLLR + 100 i-vector -> 1909, test-shaped 1344 utts"),
     # cfg5: ensembles of 10 fold models, logit mean fused into the head (evaluate.py:35-51)
     "cfg5": dict(network="ff", ivec=0, units=1024, layers=6, utts=TEST_UTTS, frames=None, flop=10 * 15296512, folds=10,
                  desc="cfg5: ensemble of 10 fold 6x1024 MLPs (logit mean), 440 spliced fMLLR -> 1909, test-shaped 1344 utts"),
@@ -76,8 +79,9 @@ def make_params(w, seed=4321):
     rng = np.random.default_rng(seed)
     if w["network"] == "ff":
         return O.init_mlp(rng, 440 + w["ivec"], w["units"], w["layers"], N_CLASSES)
-    bid = w["network"] == "blstm"
-    return O.init_recurrent(rng, "lstm", 40 + w["ivec"], w["units"], w["layers"], N_CLASSES, bidirectional=bid)
+    bid = w["network"] in ("blstm", "bgru")
+    cell = "gru" if w["network"] == "bgru" else "lstm"
+    return O.init_recurrent(rng, cell, 40 + w["ivec"], w["units"], w["layers"], N_CLASSES, bidirectional=bid)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -167,7 +171,8 @@ def cpu_reference_rate(wname, sample_frames, steps=1, warmup=0):
         sample = f"first {n} frames, predict() FF loop batch 1024"
     else:
         n_utt = int(min(max(sample_frames // 1024, 16), 256, len(offsets) - 1))  # the loop batches all of them per step
-        bid = w["network"] == "blstm"
+        bid = w["network"] in ("blstm", "bgru")
+        cell = "gru" if w["network"] == "bgru" else "lstm"
         if bid:  # no batched reference loop exists for the bidirectional nets: per-utterance, so a smaller sample
             n_utt = max(n_utt // 4, 16) if folds == 1 else max(n_utt // (4 * folds), 2)
         off = offsets[:n_utt + 1]
@@ -177,7 +182,7 @@ def cpu_reference_rate(wname, sample_frames, steps=1, warmup=0):
 
         def run():
             if bid:
-                return [O.log_softmax(sum(O.birnn_forward_utterance(q, "lstm", w["layers"], xs[off[i]:off[i + 1]])
+                return [O.log_softmax(sum(O.birnn_forward_utterance(q, cell, w["layers"], xs[off[i]:off[i + 1]])
                                           for q in ps) / np.float32(folds)) for i in range(n_utt)]
             net = O.RecurrentNet(p, "lstm", w["layers"])
             return O.predict(net, xs, off, "lstm", 1, 5, ftm if iv is None else None)
