@@ -246,18 +246,40 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         ws = plan0.ws
         main = torch.cuda.current_stream()
         side = plan0.__dict__.setdefault("_side_stream", torch.cuda.Stream(device=device))
+        # Host inputs are uploaded chunk by chunk on their own stream (`up`): the GEMMs of chunk 0 start after ~1/18 of
+        # the upload instead of all of it, and later uploads overlap the D2H copies (the two directions are full duplex).
+        up = plan0.__dict__.setdefault("_up_stream", torch.cuda.Stream(device=device))
+        x_host = iv_host = None
         if isinstance(x, torch.Tensor) and x.is_cuda:
             x_dev, lo = x, 0
         else:
             x_dev = ws.get("ff.x", hi - lo, x.shape[1], torch.float32)
-            x_dev.copy_(_as_host_tensor(x)[lo:hi], non_blocking=True)
+            x_host = _as_host_tensor(x)
         iv_dev, iv0 = None, f0
         if ivectors is not None:
             if isinstance(ivectors, torch.Tensor) and ivectors.is_cuda:
                 iv_dev, iv0 = ivectors, 0
             else:
                 iv_dev = ws.get("ff.iv", f1 - f0, ivectors.shape[1], torch.float32)
-                iv_dev.copy_(_as_host_tensor(ivectors)[f0:f1], non_blocking=True)
+                iv_host = _as_host_tensor(ivectors)
+        up.wait_stream(main)  # the buffers may still be read by a previous pass
+        uploaded = []         # per chunk: event after which its raw rows (+ halo) and i-vector rows are resident
+        if x_host is not None or iv_host is not None:
+            x_done = lo  # global raw rows [lo, x_done) have been queued
+            step = min(chunk, f1 - f0)
+            with torch.cuda.stream(up):
+                for c0 in range(f0, f1, step):
+                    c1 = min(c0 + step, f1)
+                    if x_host is not None:
+                        need = min(c1 + halo_of(presliced, splice), hi)
+                        if need > x_done:
+                            x_dev[x_done - lo:need - lo].copy_(x_host[x_done:need], non_blocking=True)
+                            x_done = need
+                    if iv_host is not None:
+                        iv_dev[c0 - f0:c1 - f0].copy_(iv_host[c0:c1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(up)
+                    uploaded.append(ev)
         add = mul = None
         if ft is not None and not presliced:
             add, mul = _dev_vec(ft["addShift"], device), _dev_vec(ft["rescale"], device)
@@ -290,6 +312,8 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
             c1 = min(c0 + chunk, f1)
             rows = c1 - c0
             buf = ci % 2
+            if uploaded:
+                main.wait_event(uploaded[ci])
             if presliced:
                 ops.convert_f32(x_dev[c0 - lo:c1 - lo], plan0.act_kind, ldd=ld_in, out=(a_hi, a_lo))
             else:
@@ -326,6 +350,11 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         side.synchronize()
         main.synchronize()
     return out
+
+
+def halo_of(presliced, splice):
+    """Raw frames a chunk needs beyond its own range on each side."""
+    return 0 if presliced else splice
 
 
 def run_sharded(fn, shards, devices):
