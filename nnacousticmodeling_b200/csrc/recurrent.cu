@@ -310,7 +310,15 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
       // input projection: fp32 in the fp32-accurate mode, bf16 in bf16 mode (halves the largest HBM stream of a layer)
       using GxT = typename std::conditional<NSPLIT == 3, float, __nv_bfloat16>::type;
       const GxT* gx = reinterpret_cast<const GxT*>(p.gx[d]) + gate_col;
-      stream_sync();  // previous item's readers of s_len / s_base are done
+      // Exchange slots are reused by the next item: nobody may write one before every CTA of the group has finished
+      // the previous item's last step (its TMA read of a slot may still be in flight).  Inside an item the step's
+      // own group_fetch gives that guarantee; across items this extra wait does.
+      if (steps_done > 0 && warp_s == 0) {
+        const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
+        while (ld_acquire_gpu(counter) < target) {
+        }
+      }
+      stream_sync();  // (also: previous item's readers of s_len / s_base are done)
       if (tid_s < NB) s_len[tid_s] = tid_s < nutt ? len[tid_s] : 0;
       const bool base_in_smem = T <= BASE_SMEM;
       if (base_in_smem)
