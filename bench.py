@@ -40,6 +40,8 @@ WORKLOADS = {
                  desc="cfg2: 6x2048 ReLU MLP, 440 spliced fMLLR + 100 i-vector -> 1909, train-shaped 3696 utts / 1,124,823 frames"),
     "cfg3": dict(network="lstm", ivec=0, units=512, layers=4, utts=TEST_UTTS, frames=None, flop=16798720,
                  desc="cfg3: 4x512 LSTM, 40 fMLLR -> 1909, timedelay 5, test-shaped 1344 utts"),
+    "cfg3t": dict(network="lstm", ivec=0, units=512, layers=4, utts=TRAIN_UTTS, frames=TRAIN_FRAMES, flop=16798720,
+                  desc="cfg3t: 4x512 LSTM, 40 fMLLR -> 1909, timedelay 5, train-shaped 3696 utts / 1,124,823 frames"),
     "cfg4": dict(network="blstm", ivec=100, units=512, layers=4, utts=TEST_UTTS, frames=None, flop=46999552,
                  desc="cfg4: 4x(2x512) bidirectional LSTM, 40 fMLLR + 100 i-vector -> 1909, test-shaped 1344 utts"),
     "cfg4g": dict(network="bgru", ivec=100, units=512, layers=4, utts=TEST_UTTS, frames=None,

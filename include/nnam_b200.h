@@ -140,7 +140,7 @@ typedef struct NnamRnnDesc {
   int cell;    /* NNAM_CELL_* */
   int hidden;  /* H (multiple of 64) */
   int n_dirs;  /* 1, or 2 = bidirectional: direction 1 walks every utterance backwards */
-  int batch;   /* utterance slots per batch (= per stream): 16, 32 or 64 */
+  int batch;   /* utterance slots per batch (= per stream): 16, 32, 64, or 128 (LSTM in bf16 mode: the "wide" kernel) */
   int streams; /* independent batches a CTA group runs concurrently (from nnam_rnn_plan) */
   int nsplit;  /* 1 = bf16 operands, 3 = bf16x3 (needs the _lo buffers) */
   int flags;   /* GRU family: bit 0 = reset gate, bits 1-2 = candidate activation (NNAM_ACT_*) */

@@ -700,13 +700,20 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   const int H = d->hidden;
   if (H <= 0 || H % 64) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: hidden size must be a multiple of 64 (got %d)", H);
   if (d->n_dirs != 1 && d->n_dirs != 2) return set_error(NNAM_ERR_ARG, "rnn: n_dirs must be 1 or 2");
-  if (d->batch != 16 && d->batch != 32 && d->batch != 64) return set_error(NNAM_ERR_ARG, "rnn: batch must be 16, 32 or 64");
+  if (d->batch != 16 && d->batch != 32 && d->batch != 64 && d->batch != 128)
+    return set_error(NNAM_ERR_ARG, "rnn: batch must be 16, 32, 64 or 128");
   if (d->nsplit != 1 && d->nsplit != 3) return set_error(NNAM_ERR_ARG, "rnn: nsplit must be 1 or 3");
   if (d->n_items <= 0) return NNAM_OK;
   if (d->nsplit == 3 && (d->h_lo == nullptr)) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs h_lo");
   if (d->h_ld % 8 || d->w_ld % 8) return set_error(NNAM_ERR_ARG, "rnn: h_ld and w_ld must be multiples of 8");
   const int gate_rows = 4 * H;
-  const RnnCfg* cfg = rnn_pick_cfg(d->cell, H, d->batch, d->nsplit);
+  // 128 slots per batch: the "wide" LSTM kernel (utterances on the MMA's M axis, h streamed through a TMA ring)
+  static const RnnCfg kWideCfg = {128, 128, 1, 0, 1, 16};
+  const bool wide = d->batch == 128;
+  if (wide && (!rnn_wide_applies(d->cell, H, d->batch, d->nsplit) || d->h0_hi || d->c0 || d->c_out))
+    return set_error(NNAM_ERR_UNSUPPORTED, "rnn: 128 slots per batch are available for LSTM in bf16 mode without "
+                     "carried state only");
+  const RnnCfg* cfg = wide ? &kWideCfg : rnn_pick_cfg(d->cell, H, d->batch, d->nsplit);
   if (!cfg)
     return set_error(NNAM_ERR_UNSUPPORTED,
                      "rnn: no kernel instance holds the lateral weights of H=%d in shared memory with %d slots per "
@@ -788,6 +795,11 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   if (p.h0_hi && d->nsplit == 3 && !p.h0_lo) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs h0_lo with h0_hi");
 
   if (use_cluster) return rnn_cluster_launch(tm, p, G, H, stream);
+  if (wide) {
+    cudaError_t ew = cudaMemsetAsync(d->counters, 0, sizeof(unsigned int) * d->n_groups, stream);
+    if (ew != cudaSuccess) return set_cuda_error(ew, "rnn: cudaMemsetAsync");
+    return rnn_wide_launch(tm, p, H, stream);
+  }
   cudaError_t e = cudaMemsetAsync(d->counters, 0, sizeof(unsigned int) * d->n_groups * cfg->s, stream);
   if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaMemsetAsync");
   return launch_rnn(d->cell, *cfg, tm, p, d->n_groups * G, rnn_smem_bytes(*cfg, H, d->cell), stream);
@@ -798,6 +810,15 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
   if (cell != NNAM_CELL_LSTM && cell != NNAM_CELL_GRU && cell != NNAM_CELL_PEEPHOLE)
     return set_error(NNAM_ERR_UNSUPPORTED, "rnn: cell kind %d not implemented", cell);
   if (hidden <= 0 || hidden % 64) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: hidden size must be a multiple of 64");
+  if (batch == 128) {
+    if (!rnn_wide_applies(cell, hidden, batch, nsplit))
+      return set_error(NNAM_ERR_UNSUPPORTED, "rnn: 128 slots per batch are available for LSTM in bf16 mode only");
+    *group_ctas = 4 * hidden / 128;
+    *max_groups = sm_count() / *group_ctas;
+    if (step_cycles) *step_cycles = 10300;  // measured, profiles/r01_k3_phase_cycles.md (the L2 all-gather bounds it)
+    if (streams) *streams = 1;
+    return NNAM_OK;
+  }
   const RnnCfg* cfg = rnn_pick_cfg(cell, hidden, batch, nsplit);
   if (!cfg)
     return set_error(NNAM_ERR_UNSUPPORTED,

@@ -110,5 +110,8 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c16) {
 size_t rnn_cluster_smem_bytes(int nb, int hidden);
 int rnn_cluster_groups(int cell, int hidden, int batch, int nsplit);
 int rnn_cluster_launch(const RnnTmaps& tm, const RnnParams& p, int G, int hidden, cudaStream_t stream);
+// recurrent_wide.cu: LSTM / bf16 / 128 slots per batch
+bool rnn_wide_applies(int cell, int hidden, int batch, int nsplit);
+int rnn_wide_launch(const RnnTmaps& tm, const RnnParams& p, int hidden, cudaStream_t stream);
 
 }  // namespace nnam

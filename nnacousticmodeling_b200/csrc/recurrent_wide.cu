@@ -1,0 +1,313 @@
+// K3, "wide" LSTM variant for bf16 mode: 128 utterances per batch, utterances on the M axis of the MMA.
+//
+// Same reference semantics and same group / exchange protocol as recurrent.cu (L.LSTM via
+// scripts/common/chainer_networks.py:44-62, predict_folds.py:49-61); what changes is the shape of a step:
+//
+//   recurrent.cu      D[128 gate rows x NB utterances] = W_slice . h^T      a thread owns ONE gate row: the four gates
+//                     of a unit sit in four TMEM lanes and meet through a shuffle transpose, gx is 16-32 scalar loads
+//                     per thread, h leaves through a staging tile, and NB <= 64 because the whole h tile (NB x H) must
+//                     sit in shared memory next to the 128 KB weight slice.
+//   this kernel       D[128 utterances x 128 gate rows] = h . W_slice^T     a TMEM lane is an UTTERANCE and its columns
+//                     are [unit-major, gate-minor]: a thread reads the four gates of a unit from four adjacent
+//                     columns (no transpose), loads its gx as 4 x 128-bit, and stores its 8 new h values as ONE
+//                     128-bit store per destination.  The h tile is the A operand and is STREAMED: k-block by k-block
+//                     (128 rows x 128 B = 16 KB) through a 4-stage TMA ring straight into the MMAs, so NB = 128 fits
+//                     and a step moves twice the utterances for about the same exchange latency.
+//
+// Roles per CTA (512 threads): warp 0 = exchange wait + TMA producer, warp 1 = MMA issuer (both with all lanes, one
+// elected), then all 16 warps do the gate math: warp w owns TMEM lane quarter w & 3 (32 utterances) and columns
+// [32 * (w >> 2), +32) = 8 units.
+#include <cooperative_groups.h>
+
+#include "recurrent_common.cuh"
+
+namespace nnam {
+
+constexpr int WIDE_NB = 128;
+constexpr int WIDE_THREADS = 512;
+constexpr int WIDE_STAGES = 4;
+constexpr int WIDE_A_STAGE = WIDE_NB * 128;  // one k-block of the h tile: 128 rows x 128 B
+
+__device__ __forceinline__ float wide_sigmoid(float v) { return fmaf(tanh_fast(0.5f * v), 0.5f, 0.5f); }
+
+template <int KBT>
+__global__ void __launch_bounds__(WIDE_THREADS, 1)
+    lstm_seq_wide_kernel(const __grid_constant__ RnnTmaps tmaps, const RnnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int M_ROWS = 128;  // gate rows per CTA (the N of the MMA)
+  constexpr int UNITS = 32;
+  constexpr int NB = WIDE_NB;
+  const int group = blockIdx.x / p.group_ctas;
+  const int rank = blockIdx.x % p.group_ctas;
+  if (group >= p.n_groups) return;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  const int H = KBT > 0 ? KBT * 64 : p.hidden;
+  const int KB = KBT > 0 ? KBT : (H >> 6);
+  constexpr int W_BLOCK = M_ROWS * 128;
+  uint8_t* w_s = smem;                          // KB blocks of [128 gate rows x 128 B], SWIZZLE_128B (B operand)
+  uint8_t* a_s = w_s + KB * W_BLOCK;            // ring of WIDE_STAGES h k-blocks (A operand)
+  uint8_t* tail = a_s + WIDE_STAGES * WIDE_A_STAGE;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* bar_mma = bar_w + 1;
+  uint64_t* full_bar = bar_w + 2;               // [WIDE_STAGES]
+  uint64_t* empty_bar = full_bar + WIDE_STAGES; // [WIDE_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_bar + WIDE_STAGES);
+  int* s_len = reinterpret_cast<int*>(tmem_slot + 2);  // NB
+  int* s_base = s_len + NB;                            // RNN_BASE_SMEM + 1
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int quarter = warp & 3;
+  const int sub = warp >> 2;           // which 32 columns (8 units) of the CTA's 128
+  const int u = quarter * 32 + lane;   // my utterance slot == my TMEM lane
+  constexpr int TMEM_COLS = 128;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    for (int i = 0; i < WIDE_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_mine = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * 32);
+  const uint32_t idesc = make_idesc_bf16_f32(NB, M_ROWS);  // M = utterances, N = gate rows
+
+  const bool prof_on = p.prof != nullptr && tid == 64;  // a thread that is neither the producer nor the MMA issuer
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_t = 0;
+#define PROF_START() do { if (prof_on) prof_t = clock64(); } while (0)
+#define PROF_MARK(i) do { if (prof_on) { const long long now = clock64(); prof_acc[i] += now - prof_t; prof_t = now; } } while (0)
+
+  unsigned int steps_done = 0;
+  uint32_t w_phase = 0, mma_phase = 0;
+  int ring_stage = 0;            // producer and MMA issuer walk the ring in lock step (KB blocks per exchange)
+  uint32_t ring_phase = 0;
+  unsigned int* counter = p.counters + group;
+  int it = p.group_item_start[group];
+  const int it_end = p.group_item_start[group + 1];
+
+  for (int d = 0; d < p.n_dirs; ++d) {
+    __syncthreads();
+    if (tid == 0) {
+      mbar_expect_tx(bar_w, static_cast<uint32_t>(KB * W_BLOCK));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(w_s + kb * W_BLOCK, &tmaps.w_hi[d], bar_w, kb * 64, rank * M_ROWS);
+    }
+    mbar_wait(bar_w, w_phase);
+    w_phase ^= 1;
+    const bool bwd = d == 1;
+    const int h_col0 = d * H;
+
+    for (; it < it_end && p.item_dir[it] == d; ++it) {
+      const int b = p.item_batch[it];
+      const long long row0 = p.batch_row0[b];
+      const int T = p.batch_steps[b];
+      const int nutt = p.batch_nutt[b];
+      const int* base = p.base + p.batch_base_off[b];
+      const int* len = p.utt_len + b * NB;
+      // my 32 gate columns (8 units x [a, i, f, o]) of the bf16 input projection
+      const __nv_bfloat16* gx = reinterpret_cast<const __nv_bfloat16*>(p.gx[d]) + rank * M_ROWS + sub * 32;
+      // exchange slots are reused by the next item: wait until the whole group has finished the previous one
+      if (steps_done > 0 && warp == 0) {
+        const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
+        while (ld_acquire_gpu(counter) < target) {
+        }
+      }
+      __syncthreads();
+      if (tid < NB) s_len[tid] = tid < nutt ? len[tid] : 0;
+      const bool base_in_smem = T <= RNN_BASE_SMEM;
+      if (base_in_smem)
+        for (int i = tid; i <= T; i += WIDE_THREADS) s_base[i] = __ldg(base + i);
+      __syncthreads();
+      const int* bp = base_in_smem ? s_base : base;
+      const int my_len = s_len[u];
+
+      float c_reg[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) c_reg[j] = 0.0f;
+
+      // 32 bf16 gate pre-activations of utterance u at step s (4 x 128-bit loads); inactive lanes load nothing
+      auto load_gx = [&](int s, uint4 (&dst)[4]) {
+        if (s < my_len) {
+          const long long row = row0 + bp[bwd ? (my_len - 1 - s) : s] + u;
+          const uint4* src = reinterpret_cast<const uint4*>(gx + row * p.gx_ld);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = __ldg(src + j);
+        }
+      };
+
+      uint4 gxr[4] = {}, gxn[4] = {};
+      load_gx(0, gxr);
+      for (int s = 0; s < T; ++s) {
+        PROF_START();
+        const int n_s = bp[s + 1] - bp[s];  // active utterances = slots [0, n_s)
+        const bool active = u < n_s;        // == s < my_len (utterances are sorted by length)
+        float acc[32];
+        if (s > 0) {
+          // ---- the group's h of step s-1 streams from the exchange buffer through the ring into the MMAs
+          if (warp == 0) {
+            const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
+            while (ld_acquire_gpu(counter) < target) {
+            }
+            if (elect_one()) fence_proxy_async_all();  // peers' generic-proxy stores -> this async-proxy (TMA) read
+            __syncwarp();
+            const int xrow = (group * 4 + ((s - 1) & 1)) * NB;
+            int st = ring_stage;
+            uint32_t ph = ring_phase;
+            for (int kb = 0; kb < KB; ++kb) {
+              mbar_wait(&empty_bar[st], ph ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(&full_bar[st], WIDE_A_STAGE);
+                tma_load_2d(a_s + st * WIDE_A_STAGE, &tmaps.x_hi, &full_bar[st], kb * 64, xrow);
+              }
+              __syncwarp();
+              if (++st == WIDE_STAGES) {
+                st = 0;
+                ph ^= 1;
+              }
+            }
+          } else if (warp == 1) {
+            const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(a_s));
+            const uint64_t bdesc0 = make_sw128_kmajor_desc(smem_u32(w_s));
+            int st = ring_stage;
+            uint32_t ph = ring_phase;
+            for (int kb = 0; kb < KB; ++kb) {
+              mbar_wait(&full_bar[st], ph);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t ad = adesc0 + static_cast<uint64_t>((st * WIDE_A_STAGE) >> 4);
+                const uint64_t bd = bdesc0 + static_cast<uint64_t>((kb * W_BLOCK) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_commit(&empty_bar[st]);
+                if (kb == KB - 1) umma_commit(bar_mma);
+              }
+              __syncwarp();
+              if (++st == WIDE_STAGES) {
+                st = 0;
+                ph ^= 1;
+              }
+            }
+          }
+          // every thread advances its copy of the ring position by KB blocks
+          {
+            const int adv = ring_stage + KB;
+            ring_phase ^= static_cast<uint32_t>((adv / WIDE_STAGES) & 1);
+            ring_stage = adv % WIDE_STAGES;
+          }
+          PROF_MARK(1);
+          if (s + 1 < T) load_gx(s + 1, gxn);  // lands while the tensor core works
+          PROF_MARK(2);
+          mbar_wait(bar_mma, mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          PROF_MARK(3);
+          uint32_t r[32];
+          tmem_ld32(tmem_mine, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+          tc_fence_before();
+          PROF_MARK(4);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+          if (s + 1 < T) load_gx(s + 1, gxn);
+        }
+
+        // ---- gates and cell update for my 8 units (chainer F.lstm), h to the exchange slot and the layer output
+        if (active) {
+          const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(gxr);
+          uint32_t hp[4];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 ga = __bfloat1622float2(g2[2 * j]);      // (a, i) pre-activations from the input projection
+            const float2 gf = __bfloat1622float2(g2[2 * j + 1]);  // (f, o)
+            const float a = tanh_fast(acc[4 * j] + ga.x);
+            const float ig = wide_sigmoid(acc[4 * j + 1] + ga.y);
+            const float fg = wide_sigmoid(acc[4 * j + 2] + gf.x);
+            const float og = wide_sigmoid(acc[4 * j + 3] + gf.y);
+            c_reg[j] = fmaf(a, ig, fg * c_reg[j]);
+            const float h_new = og * tanh_fast(c_reg[j]);
+            if (j & 1)
+              hp[j >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(h_new))) << 16;
+            else
+              hp[j >> 1] = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(h_new)));
+          }
+          const uint4 hv = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          const long long xoff = (static_cast<long long>(group * 4 + (s & 1)) * NB + u) * H + rank * UNITS + sub * 8;
+          *reinterpret_cast<uint4*>(p.xchg_hi + xoff) = hv;
+          const int t_idx = bwd ? (my_len - 1 - s) : s;
+          const long long off = (row0 + bp[t_idx] + u) * p.h_ld + h_col0 + rank * UNITS + sub * 8;
+          *reinterpret_cast<uint4*>(p.h_hi + off) = hv;
+        }
+        PROF_MARK(5);
+        // ---- publish: the CTA barrier orders every thread's stores before thread 0's release
+        __syncthreads();
+        if (tid == 0) red_release_gpu_add(counter, 1u);
+        ++steps_done;
+        PROF_MARK(6);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) gxr[j] = gxn[j];
+      }
+    }
+  }
+
+  if (prof_on) {
+    prof_acc[7] = steps_done;
+    for (int i = 0; i < 8; ++i) p.prof[blockIdx.x * 8 + i] = prof_acc[i];
+  }
+#undef PROF_START
+#undef PROF_MARK
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+size_t rnn_wide_smem_bytes(int hidden) {
+  const size_t kb = hidden / 64;
+  return kb * 128 * 128 + static_cast<size_t>(WIDE_STAGES) * WIDE_A_STAGE + 8 * (2 + 2 * WIDE_STAGES) + 16 +
+         (WIDE_NB + RNN_BASE_SMEM + 1) * 4;
+}
+
+// The wide kernel applies to: LSTM, bf16 mode, 128 slots per batch, no carried state, H a multiple of 64 whose slice fits.
+bool rnn_wide_applies(int cell, int hidden, int batch, int nsplit) {
+  if (cell != NNAM_CELL_LSTM || nsplit != 1 || batch != WIDE_NB) return false;
+  if (hidden % 64 || (4 * hidden) % 128) return false;
+  if (rnn_wide_smem_bytes(hidden) > 227 * 1024) return false;
+  return sm_count() >= 4 * hidden / 128;
+}
+
+template <int KBT>
+static int launch_wide(const RnnTmaps& tm, const RnnParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = lstm_seq_wide_kernel<KBT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaFuncSetAttribute(wide)");
+  void* args[] = {const_cast<RnnTmaps*>(&tm), const_cast<RnnParams*>(&p)};
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(WIDE_THREADS), args, smem, stream);
+  if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaLaunchCooperativeKernel(wide)");
+  return NNAM_OK;
+}
+
+int rnn_wide_launch(const RnnTmaps& tm, const RnnParams& p, int hidden, cudaStream_t stream) {
+  const int grid = p.n_groups * p.group_ctas;
+  const size_t smem = rnn_wide_smem_bytes(hidden);
+  if (hidden == 512) return launch_wide<8>(tm, p, grid, smem, stream);
+  return launch_wide<0>(tm, p, grid, smem, stream);
+}
+
+}  // namespace nnam

@@ -223,7 +223,7 @@ def pick_schedule(plan, steps, device, nb=None):
     if hit is not None:
         return hit
     nsplit = 3 if plan.split else 1
-    cands = [nb] if nb else [16, 32, 64]
+    cands = [nb] if nb else [16, 32, 64, 128]
     s_sorted = -np.sort(-steps, kind="stable")
     best = None
     for cand in cands:

@@ -225,3 +225,29 @@ def test_timedelay_longer_than_some_utterances_and_empty_input(nn, network):
     assert np.array_equal(nn.predict(m, x, off, 39, network, 0, 1, td, None, progress=False, out=pinned), got)
     empty = nn.predict(m, x[:0], np.zeros(1, np.int32), 39, network, 0, 1, td, None, progress=False)
     assert empty.shape == (0, 39)
+
+
+@pytest.mark.parametrize("network,units", [("lstm", 512), ("blstm", 128), ("lstm", 192)])
+def test_wide_kernel_128_slots_per_batch(nn, network, units):
+    """The 128-slot "wide" LSTM kernel (utterances on the MMA's M axis, h streamed through a TMA ring) against the
+    oracle and against the 32-slot kernel, on more than one batch with ragged lengths."""
+    from nnacousticmodeling_b200 import recurrent_engine
+    rng = np.random.default_rng(units)
+    lens = rng.integers(1, 60, size=300).tolist()
+    off = _offsets(lens)
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    bid = network == "blstm"
+    m, p = _lstm(nn, 77, network, 40, units, 2, 39, precision="bf16", bidirectional=bid)
+    wide = np.zeros((off[-1], 39), np.float32)
+    recurrent_engine.forward_utterances(m, x, off, wide, 0, len(lens), timedelay=0, device=0, nb=128)
+    narrow = np.zeros_like(wide)
+    recurrent_engine.forward_utterances(m, x, off, narrow, 0, len(lens), timedelay=0, device=0, nb=32)
+    assert np.abs(wide - narrow).max() < 2e-2  # same bf16 arithmetic, different summation order / gx rounding points
+    pick = [0, 17, int(np.argmax(lens)), int(np.argmin(lens)), 299]
+    for u in pick:
+        xs = x[off[u]:off[u + 1]]
+        if bid:
+            want = O.log_softmax(O.birnn_forward_utterance(p, "lstm", 2, xs))
+        else:
+            want = O.log_softmax(O.rnn_forward_utterance(p, "lstm", 2, xs))
+        assert np.abs(wide[off[u]:off[u + 1]] - want).max() < 5e-2
