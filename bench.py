@@ -333,6 +333,9 @@ def run_ours(args):
                 "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step); burst peak "
                                f"{peaks['tf_burst']} -> frac {kern[dom]['tflops'] / peaks['tf_burst']:.3f}",
                 "launches_per_step": kern[dom]["launches"] // args.steps}
+        if dom == "rnn":
+            roof["note"] = ("K3 is sequential in t and bound by the per-step exchange latency, not by the tensor pipe "
+                            "(SURVEY 8d: no roofline claim); achieved = algorithmic lateral FLOP / kernel time")
     else:
         roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": kern[dom]["gbs"] / peaks["hbm"], "traffic": traffic, "peak_source": peaks["src"]}
