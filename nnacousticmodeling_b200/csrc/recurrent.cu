@@ -328,23 +328,16 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
       const bool has_h0 = p.h0_hi != nullptr;
       const int chunks_per_row = H >> 3;
 
-      // stage rows of `src` (hi/lo) of the active utterances into the swizzled B-operand tile: one warp per row,
-      // 16-byte cp.async chunks, all in flight at once.
-      // mode 0: initial-state rows; 1: rows written at the previous step; 2: rows written at this step (GRU r*h)
-      auto load_tile = [&](const __nv_bfloat16* src_hi, const __nv_bfloat16* src_lo, int n_act, int s, int mode) {
+      // Carried initial state (stateful model(x) surface only): the h0 rows of the active utterances go into the swizzled
+      // B-operand tile with 16-byte cp.async chunks, one warp per row.  Every later step gets its tile by TMA.
+      auto load_h0_tile = [&](int n_act) {
         for (int u = warp_s; u < n_act; u += WPS) {
-          long long off;
-          if (mode == 0) {
-            off = (static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0;
-          } else {
-            const int t_idx = mode == 1 ? (bwd ? (s_len[u] - s) : (s - 1)) : (bwd ? (s_len[u] - 1 - s) : s);
-            off = (row0 + bp[t_idx] + u) * p.h_ld + h_col0;
-          }
+          const long long off = (static_cast<long long>(b) * NB + u) * (H * p.n_dirs) + h_col0;
           const uint32_t row_so = static_cast<uint32_t>((u >> 3) * 1024 + (u & 7) * 128);
           for (int c = lane; c < chunks_per_row; c += 32) {
             const uint32_t so = static_cast<uint32_t>((c >> 3) * H_BLOCK) + row_so + (((c & 7) ^ (u & 7)) << 4);
-            cp_async_16(h_hi_sa + so, src_hi + off + c * 8);
-            if (NSPLIT == 3) cp_async_16(h_lo_sa + so, src_lo + off + c * 8);
+            cp_async_16(h_hi_sa + so, p.h0_hi + off + c * 8);
+            if (NSPLIT == 3) cp_async_16(h_lo_sa + so, p.h0_lo + off + c * 8);
           }
         }
       };
@@ -423,7 +416,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
           if (s > 0)
             group_fetch((s - 1) & 1);  // h of step s-1 sits in exchange slot (s-1) & 1
           else
-            load_tile(p.h0_hi, p.h0_lo, n_s, s, 0);
+            load_h0_tile(n_s);
           PROF_MARK(1);
           // the next step's input projection is requested while the h tile is still in flight and lands while the
           // tensor core works (tcgen05.mma issue back-pressures the issuing thread, so it must come last)

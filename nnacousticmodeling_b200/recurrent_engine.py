@@ -22,9 +22,9 @@ from .ops import OUT_BF16, OUT_BF16_SPLIT, OUT_F32, round_up
 
 CELL_LSTM, CELL_GRU, CELL_PEEPHOLE = 0, 1, 2
 PROFILE_CYCLES = None  # set to a list to collect per-CTA phase cycle counters of every K3 launch
-DEFAULT_BATCH = None  # None: pick 32 or 64 utterances per batch from a cost model of the schedule
-# measured SM cycles per recurrence step (profiles/r01_k3_phase_cycles.md): the step cost grows sub-linearly in the
-# batch width, but fewer/larger work items balance worse over the CTA groups
+DEFAULT_BATCH = None  # None: pick the slots per batch (16 / 32 / 64 / 128) from a cost model of the schedule: the step cost
+# (nnam_rnn_plan, measured in profiles/r01_k3_phase_cycles.md) grows sub-linearly in the batch width, but fewer and
+# larger work items balance worse over the CTA groups and lengthen the critical path of the longest utterance
 
 
 # ------------------------------------------------------------------------------------------
@@ -247,7 +247,7 @@ def pick_schedule(plan, steps, device, nb=None):
     return res
 
 
-def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=None, aux=None):
+def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=None, xchg=None):
     H, nd = plan.hidden, plan.n_dirs
     d = RnnDesc()
     d.cell, d.hidden, d.n_dirs, d.batch, d.nsplit = plan.cell, H, nd, nb, 3 if plan.split else 1
@@ -261,7 +261,7 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
     if plan.cell == CELL_PEEPHOLE:  # the peephole block travels in the direction-1 weight slot
         d.w_hi[1] = layer.lat[1][0].data_ptr()
         d.w_lo[1] = layer.lat[1][1].data_ptr() if plan.split else None
-    xh, xl = aux
+    xh, xl = xchg
     d.xchg_hi = xh.data_ptr()
     d.xchg_lo = xl.data_ptr() if xl is not None else None
     d.gx_ld = gx.stride(0)
@@ -310,13 +310,13 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
         # exchange buffer: per lane 4 slots (h parity 0/1, r*h parity 0/1) of nb rows x H; zeroed once when it is created
         x_rows = sched.n_lanes * 4 * nb
         fresh = ws.buf.get(f"{tag}.xchg.hi") is None or ws.buf[f"{tag}.xchg.hi"].numel() < x_rows * H
-        aux = (ws.get(f"{tag}.xchg.hi", x_rows, H, torch.bfloat16),
-               ws.get(f"{tag}.xchg.lo", x_rows, H, torch.bfloat16) if plan.split else None)
+        xchg = (ws.get(f"{tag}.xchg.hi", x_rows, H, torch.bfloat16),
+                ws.get(f"{tag}.xchg.lo", x_rows, H, torch.bfloat16) if plan.split else None)
         if fresh:
-            aux[0].zero_()
-            if aux[1] is not None:
-                aux[1].zero_()
-        desc = _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0, c0, c_out, aux)
+            xchg[0].zero_()
+            if xchg[1] is not None:
+                xchg[1].zero_()
+        desc = _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0, c0, c_out, xchg)
         # algorithmic lateral flops: LSTM 4 gates, GRU 3 (2 without reset gate) H x H products per frame
         n_mats = {CELL_LSTM: 4, CELL_PEEPHOLE: 7}.get(plan.cell, 3 if plan.gru_flags & 1 else 2)
         ops.rnn_seq(desc, 2.0 * rows * nd * n_mats * H * H)
