@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from nnacousticmodeling_b200 import ops
 use_bias = (sys.argv[1] if len(sys.argv) > 1 else "1") == "1"
 dev = torch.device("cuda:0")
-M, N = 65536, 2048
+M, N = int(sys.argv[2]) if len(sys.argv) > 2 else 65536, 2048
 for kind, name in ((ops.OUT_BF16, "bf16"), (ops.OUT_F32, "f32")):
     for k in (64, 128, 256, 512, 768, 1024, 2048):
         a = torch.randn((M, k), device=dev).to(torch.bfloat16)

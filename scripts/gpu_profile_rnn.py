@@ -11,7 +11,8 @@ from oracle import nnam_oracle as O
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 net = sys.argv[3] if len(sys.argv) > 3 else "lstm"
-x, off, _ = O.synth_set(1234, 1344)
+n_utt = int(sys.argv[4]) if len(sys.argv) > 4 else 1344
+x, off, _ = O.synth_set(1234, n_utt)
 p = O.init_recurrent(np.random.default_rng(1), net, 40, 512, 4, 1909)
 m = nn.get_nn(net, 4, [512], 1909, nn.F.relu, [5]); m.load_params(p); m.precision = prec
 dev = torch.device("cuda:0")
