@@ -10,6 +10,7 @@ HBM layout (per device)
 """
 from __future__ import annotations
 
+import os
 import threading
 
 import numpy as np
@@ -66,19 +67,46 @@ class LinearDev:
 
 
 class Workspace:
-    """Grow-only named device buffers (the kernels never allocate)."""
+    """Grow-only named device buffers (the kernels never allocate).
+
+    Debug aid: with ``NNAM_REDZONE=<bytes>`` in the environment every buffer gets that many guard bytes in front and
+    behind, filled with 0xA5; :meth:`check_redzones` raises if a kernel wrote into one (tests/test_gpu_redzones.py).
+    """
+
+    GUARD_BYTE = 0xA5
 
     def __init__(self, device):
         self.device = device
         self.buf = {}
+        self.redzone = int(os.environ.get("NNAM_REDZONE", "0")) // 256 * 256
+        self._raw = {}
 
     def get(self, name, rows, cols, dtype):
         t = self.buf.get(name)
         need = rows * cols
         if t is None or t.numel() < need or t.dtype != dtype:
-            t = torch.empty(need, dtype=dtype, device=self.device)
+            if self.redzone:
+                nbytes = need * torch.empty((), dtype=dtype).element_size()
+                raw = torch.full((2 * self.redzone + round_up(nbytes, 256),), self.GUARD_BYTE, dtype=torch.uint8,
+                                 device=self.device)
+                self._raw[name] = (raw, nbytes)
+                t = raw[self.redzone:self.redzone + nbytes].view(dtype)
+            else:
+                t = torch.empty(need, dtype=dtype, device=self.device)
             self.buf[name] = t
         return t[:need].view(rows, cols)
+
+    def check_redzones(self):
+        """Raise NnamError naming the first buffer whose guard bytes changed; returns the number of buffers checked."""
+        for name, (raw, nbytes) in self._raw.items():
+            front = raw[:self.redzone]
+            back = raw[self.redzone + nbytes:]
+            for where, g in (("before", front), ("after", back)):
+                bad = (g != self.GUARD_BYTE).nonzero()
+                if bad.numel():
+                    raise NnamError(f"workspace buffer '{name}' ({nbytes} bytes): {bad.numel()} guard bytes "
+                                    f"{where} it were overwritten, first at offset {int(bad[0])}")
+        return len(self._raw)
 
 
 class Plan:
