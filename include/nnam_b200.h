@@ -191,6 +191,10 @@ int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream);
  * (h exchanged through distributed shared memory; measured slower than the L2 exchange on B200).  */
 int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles,
                   int* streams);
+/* SM cycles per step of a stream whose sibling streams in the CTA group are idle (<= step_cycles of nnam_rnn_plan,
+ * which is measured with every stream busy).  A scheduler costs a two-stream group as
+ * solo * (steps of its longer lane) + (busy - solo) * (steps of the other lane).  */
+int nnam_rnn_solo_step_cycles(int cell, int hidden, int batch, int nsplit, int* cycles);
 
 #ifdef __cplusplus
 }

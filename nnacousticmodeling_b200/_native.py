@@ -101,6 +101,7 @@ _SIGNATURES = {
     "nnam_rnn_seq": (c_int, [c_void_p, c_void_p]),
     "nnam_rnn_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                               POINTER(c_int)]),
+    "nnam_rnn_solo_step_cycles": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int)]),
 }
 
 

@@ -90,6 +90,7 @@ int peephole_cell(int phase, const float* gx, long long gx_ld, const float* g1, 
                   long long p2_ld, const float* c_prev, float* c_new, void* out_hi, void* out_lo, long long out_ld, int n,
                   int H, int fast, cudaStream_t stream);
 int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream);
+int rnn_solo_step_cycles(int cell, int hidden, int batch, int nsplit, int* cycles);
 int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles,
              int* streams);
 
@@ -166,6 +167,11 @@ int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, 
                   int* streams) {
   if (!group_ctas || !max_groups) return nnam::set_error(NNAM_ERR_ARG, "rnn_plan: NULL output");
   return nnam::rnn_plan(cell, hidden, batch, nsplit, group_ctas, max_groups, step_cycles, streams);
+}
+
+int nnam_rnn_solo_step_cycles(int cell, int hidden, int batch, int nsplit, int* cycles) {
+  if (!cycles) return nnam::set_error(NNAM_ERR_ARG, "rnn_solo_step_cycles: NULL output");
+  return nnam::rnn_solo_step_cycles(cell, hidden, batch, nsplit, cycles);
 }
 
 }  // extern "C"

@@ -701,11 +701,18 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   if (d->h_ld % 8 || d->w_ld % 8) return set_error(NNAM_ERR_ARG, "rnn: h_ld and w_ld must be multiples of 8");
   const int gate_rows = 4 * H;
   // 128 slots per batch: the "wide" LSTM kernel (utterances on the MMA's M axis, h streamed through a TMA ring)
-  static const RnnCfg kWideCfg = {128, 128, 1, 0, 1, 16};
+  static const RnnCfg kWideCfg1 = {128, 128, 1, 0, 1, 16};
+  static const RnnCfg kWideCfg2 = {128, 128, 1, 0, 2, 8};
+  const RnnCfg& kWideCfg = rnn_wide_streams() == 2 ? kWideCfg2 : kWideCfg1;
   const bool wide = d->batch == 128;
   if (wide && (!rnn_wide_applies(d->cell, H, d->batch, d->nsplit) || d->h0_hi || d->c0 || d->c_out))
     return set_error(NNAM_ERR_UNSUPPORTED, "rnn: 128 slots per batch are available for LSTM in bf16 mode without "
                      "carried state only");
+  if (wide && (d->h_ld % 16 || d->gx_ld % 16 || (reinterpret_cast<uintptr_t>(d->h_hi) & 31) ||
+               (reinterpret_cast<uintptr_t>(d->xchg_hi) & 31) || (reinterpret_cast<uintptr_t>(d->gx[0]) & 31) ||
+               (d->n_dirs == 2 && (reinterpret_cast<uintptr_t>(d->gx[1]) & 31))))
+    return set_error(NNAM_ERR_ARG, "rnn: 128 slots per batch need 32-byte aligned gx / h / exchange buffers and "
+                     "gx_ld, h_ld multiples of 16 (256-bit accesses)");
   const RnnCfg* cfg = wide ? &kWideCfg : rnn_pick_cfg(d->cell, H, d->batch, d->nsplit);
   if (!cfg)
     return set_error(NNAM_ERR_UNSUPPORTED,
@@ -789,7 +796,7 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
 
   if (use_cluster) return rnn_cluster_launch(tm, p, G, H, stream);
   if (wide) {
-    cudaError_t ew = cudaMemsetAsync(d->counters, 0, sizeof(unsigned int) * d->n_groups, stream);
+    cudaError_t ew = cudaMemsetAsync(d->counters, 0, sizeof(unsigned int) * d->n_groups * cfg->s, stream);
     if (ew != cudaSuccess) return set_cuda_error(ew, "rnn: cudaMemsetAsync");
     return rnn_wide_launch(tm, p, H, stream);
   }
@@ -808,8 +815,9 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
       return set_error(NNAM_ERR_UNSUPPORTED, "rnn: 128 slots per batch are available for LSTM in bf16 mode only");
     *group_ctas = 4 * hidden / 128;
     *max_groups = sm_count() / *group_ctas;
-    if (step_cycles) *step_cycles = 10300;  // measured, profiles/r01_k3_phase_cycles.md (the L2 all-gather bounds it)
-    if (streams) *streams = 1;
+    // measured, profiles/r01_k3_phase_cycles.md: per step of ONE stream while all streams of the group are busy
+    if (step_cycles) *step_cycles = rnn_wide_streams() == 2 ? 13800 : 10300;
+    if (streams) *streams = rnn_wide_streams();
     return NNAM_OK;
   }
   const RnnCfg* cfg = rnn_pick_cfg(cell, hidden, batch, nsplit);
@@ -831,6 +839,17 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
   }
   if (step_cycles) *step_cycles = cycles;
   if (streams) *streams = cfg->s;
+  return NNAM_OK;
+}
+
+// SM cycles per step of a stream whose sibling streams in the CTA group are idle (<= the all-busy figure of rnn_plan):
+// the host's lane assignment uses the pair to cost a group as solo * longest lane + (busy - solo) * the other lane.
+int rnn_solo_step_cycles(int cell, int hidden, int batch, int nsplit, int* cycles) {
+  int g = 0, m = 0, c = 0, s = 0;
+  const int rc = rnn_plan(cell, hidden, batch, nsplit, &g, &m, &c, &s);
+  if (rc) return rc;
+  if (batch == 128 && s == 2) c = 11500;  // measured: 10.7 k with one group running, profiles/r01_k3_phase_cycles.md
+  *cycles = c;
   return NNAM_OK;
 }
 

@@ -278,6 +278,314 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1)
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Two batches ("streams") per CTA group, interleaved.  A step of the kernel above is a chain of latencies (exchange
+// wait -> two rounds of the 4-slot TMA ring -> MMA -> gate math -> publish) that leaves every unit of the SM idle most of
+// the time (profiles/r01_k3_phase_cycles.md).  Here the 16 warps split into two independent sets of 8; each set runs the
+// whole recurrence of its own batch (own TMEM accumulator, own exchange slots and counter) against the SAME resident
+// weight slice, and the two sets share one 5-slot TMA ring under a lock: a set takes the ring for the KB k-blocks of one
+// step, so the ring keeps 80 KB in flight across both streams while the other stream does its gate math or waits for
+// its peers.  A warp of a set owns TMEM lane quarter w & 3 and 64 columns (16 units), processed as two halves of 32.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int W2_STREAMS = 2;
+constexpr int W2_TPS = 256;  // threads per stream
+constexpr int W2_THREADS = W2_STREAMS * W2_TPS;
+constexpr int W2_STAGES = 5;
+constexpr int W2_BASE_SMEM = 1024;
+
+__device__ __forceinline__ int stream_of_thread() { return static_cast<int>(threadIdx.x) / W2_TPS; }
+__device__ __forceinline__ void w2_bar_sync(int stream) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + stream), "n"(W2_TPS) : "memory");
+}
+
+template <int KBT>
+__global__ void __launch_bounds__(W2_THREADS, 1)
+    lstm_seq_wide2_kernel(const __grid_constant__ RnnTmaps tmaps, const RnnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int M_ROWS = 128;
+  constexpr int UNITS = 32;
+  constexpr int NB = WIDE_NB;
+  const int group = blockIdx.x / p.group_ctas;
+  const int rank = blockIdx.x % p.group_ctas;
+  if (group >= p.n_groups) return;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  const int H = KBT > 0 ? KBT * 64 : p.hidden;
+  const int KB = KBT > 0 ? KBT : (H >> 6);
+  constexpr int W_BLOCK = M_ROWS * 128;
+  uint8_t* w_s = smem;
+  uint8_t* a_s = w_s + KB * W_BLOCK;
+  uint8_t* tail = a_s + W2_STAGES * WIDE_A_STAGE;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* bar_mma = bar_w + 1;                   // [2] a stream's accumulator is complete
+  uint64_t* bar_grant = bar_mma + W2_STREAMS;      // [2] producer -> MMA issuer: "your k-blocks start at s_f0[stream]"
+  // [2][W2_STAGES] "slot filled", one set PER STREAM although the slots are shared: a parity wait on a barrier that
+  // still carries the other stream's previous fill would see "the phase before" and pass at once.  With its own set
+  // a stream's issuer only ever waits for its own fills, in order.  The "slot free" barriers are shared.
+  uint64_t* full_bar_all = bar_grant + W2_STREAMS;
+  uint64_t* full_bar = full_bar_all + stream_of_thread() * W2_STAGES;
+  uint64_t* empty_bar = full_bar_all + W2_STREAMS * W2_STAGES;  // [W2_STAGES]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_bar + W2_STAGES);
+  unsigned int* ring_lock = tmem_slot + 2;
+  volatile unsigned int* ring_fill = ring_lock + 1;  // k-blocks pushed through the ring so far (by either stream)
+  volatile unsigned int* s_f0 = ring_lock + 2;       // [2] ring position of the first k-block of a stream's current step
+  int* s_len_all = reinterpret_cast<int*>(ring_lock + 6);    // [2][NB]
+  int* s_base_all = s_len_all + W2_STREAMS * NB;             // [2][W2_BASE_SMEM + 1]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int stream = warp >> 3;
+  const int sw = warp & 7;             // warp inside the stream
+  const int stid = tid & (W2_TPS - 1);
+  const int quarter = sw & 3;          // == warp & 3: the TMEM lane quarter this warp may read
+  const int sub = sw >> 2;             // which 64 columns (16 units) of the CTA's 128
+  const int u = quarter * 32 + lane;   // my utterance slot == my TMEM lane
+  constexpr int TMEM_COLS = W2_STREAMS * 128;
+  int* s_len = s_len_all + stream * NB;
+  int* s_base = s_base_all + stream * (W2_BASE_SMEM + 1);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    for (int i = 0; i < W2_STREAMS; ++i) {
+      mbar_init(&bar_mma[i], 1);
+      mbar_init(&bar_grant[i], 1);
+    }
+    for (int i = 0; i < W2_STREAMS * W2_STAGES; ++i) mbar_init(&full_bar_all[i], 1);
+    for (int i = 0; i < W2_STAGES; ++i) mbar_init(&empty_bar[i], 1);
+    *ring_lock = 0u;
+    *ring_fill = 0u;
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(stream * 128);
+  const uint32_t tmem_mine = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * 64);
+  const uint32_t idesc = make_idesc_bf16_f32(NB, M_ROWS);
+
+  const bool prof_on = p.prof != nullptr && tid == 64;
+  long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_t = 0;
+#define PROF_START() do { if (prof_on) prof_t = clock64(); } while (0)
+#define PROF_MARK(i) do { if (prof_on) { const long long now = clock64(); prof_acc[i] += now - prof_t; prof_t = now; } } while (0)
+
+  unsigned int steps_done = 0;
+  uint32_t w_phase = 0, mma_phase = 0, grant_phase = 0;
+  uint32_t full_parity = 0;  // bit st: parity of this stream's next fill of ring slot st
+  const int lane_id_ = group * W2_STREAMS + stream;  // (group, stream) = one lane of the schedule
+  unsigned int* counter = p.counters + lane_id_;
+  int it = p.group_item_start[lane_id_];
+  const int it_end = p.group_item_start[lane_id_ + 1];
+
+  for (int d = 0; d < p.n_dirs; ++d) {
+    __syncthreads();  // both streams are done with the previous direction's weights
+    if (tid == 0) {
+      mbar_expect_tx(bar_w, static_cast<uint32_t>(KB * W_BLOCK));
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(w_s + kb * W_BLOCK, &tmaps.w_hi[d], bar_w, kb * 64, rank * M_ROWS);
+    }
+    mbar_wait(bar_w, w_phase);
+    w_phase ^= 1;
+    const bool bwd = d == 1;
+    const int h_col0 = d * H;
+
+    for (; it < it_end && p.item_dir[it] == d; ++it) {
+      const int b = p.item_batch[it];
+      const long long row0 = p.batch_row0[b];
+      const int T = p.batch_steps[b];
+      const int nutt = p.batch_nutt[b];
+      const int* base = p.base + p.batch_base_off[b];
+      const int* len = p.utt_len + b * NB;
+      const __nv_bfloat16* gx = reinterpret_cast<const __nv_bfloat16*>(p.gx[d]) + rank * M_ROWS + sub * 64;
+      // exchange slots are reused by the next item: wait until the whole group has finished the previous one
+      if (steps_done > 0 && sw == 0) {
+        const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
+        while (ld_acquire_gpu(counter) < target) {
+        }
+      }
+      w2_bar_sync(stream);
+      if (stid < NB) s_len[stid] = stid < nutt ? len[stid] : 0;
+      const bool base_in_smem = T <= W2_BASE_SMEM;
+      if (base_in_smem)
+        for (int i = stid; i <= T; i += W2_TPS) s_base[i] = __ldg(base + i);
+      w2_bar_sync(stream);
+      const int* bp = base_in_smem ? s_base : base;
+      const int my_len = s_len[u];
+
+      float c_reg[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) c_reg[j] = 0.0f;
+
+      for (int s = 0; s < T; ++s) {
+        PROF_START();
+        const int n_s = bp[s + 1] - bp[s];
+        const bool active = u < n_s;
+        const int t_idx = bwd ? (my_len - 1 - s) : s;
+        const long long my_row = active ? row0 + bp[t_idx] + u : 0;
+        // 64 bf16 gate pre-activations of utterance u at this step: issued now, they land during the exchange
+        uint32_t gxr[4][8] = {};
+        if (active) {
+          const __nv_bfloat16* src = gx + my_row * p.gx_ld;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ldg_nc_256(src + 16 * j, gxr[j]);
+        }
+        PROF_MARK(0);
+        if (s > 0) {
+          if (sw == 0) {
+            // ---- producer: peers' h of step s-1 -> ring; the ring is taken for the KB blocks of this step
+            const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
+            while (ld_acquire_gpu(counter) < target) {
+            }
+            unsigned int f0 = 0;
+            if (lane == 0) {
+              fence_proxy_async_all();  // peers' generic-proxy stores -> this async-proxy (TMA) read
+              while (atomicCAS(ring_lock, 0u, 1u) != 0u) {
+              }
+              __threadfence_block();
+              f0 = *ring_fill;
+              s_f0[stream] = f0;
+              __threadfence_block();
+              mbar_arrive(&bar_grant[stream]);
+            }
+            f0 = __shfl_sync(0xffffffffu, f0, 0);
+            const int xrow = (lane_id_ * 4 + ((s - 1) & 1)) * NB;
+            for (int kb = 0; kb < KB; ++kb) {
+              const unsigned int f = f0 + kb;
+              const int st = static_cast<int>(f % W2_STAGES);
+              const uint32_t ph = (f / W2_STAGES) & 1u;
+              mbar_wait(&empty_bar[st], ph ^ 1);
+              if (elect_one()) {
+                mbar_expect_tx(&full_bar[st], WIDE_A_STAGE);
+                tma_load_2d(a_s + st * WIDE_A_STAGE, &tmaps.x_hi, &full_bar[st], kb * 64, xrow);
+              }
+              __syncwarp();
+            }
+            if (lane == 0) {
+              *ring_fill = f0 + KB;
+              __threadfence_block();
+              atomicExch(ring_lock, 0u);
+            }
+            __syncwarp();
+          } else if (sw == 1) {
+            // ---- MMA issuer of this stream
+            mbar_wait(&bar_grant[stream], grant_phase);
+            const unsigned int f0 = s_f0[stream];
+            const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(a_s));
+            const uint64_t bdesc0 = make_sw128_kmajor_desc(smem_u32(w_s));
+            for (int kb = 0; kb < KB; ++kb) {
+              const unsigned int f = f0 + kb;
+              const int st = static_cast<int>(f % W2_STAGES);
+              mbar_wait(&full_bar[st], (full_parity >> st) & 1u);
+              full_parity ^= 1u << st;
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t ad = adesc0 + static_cast<uint64_t>((st * WIDE_A_STAGE) >> 4);
+                const uint64_t bd = bdesc0 + static_cast<uint64_t>((kb * W_BLOCK) >> 4);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tmem_acc, ad + 2 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                umma_commit(&empty_bar[st]);
+                if (kb == KB - 1) umma_commit(&bar_mma[stream]);
+              }
+              __syncwarp();
+            }
+          }
+          grant_phase ^= 1;
+          PROF_MARK(1);
+          mbar_wait(&bar_mma[stream], mma_phase);
+          mma_phase ^= 1;
+          tc_fence_after();
+          PROF_MARK(2);
+        }
+
+        // ---- gates and cell update for my 16 units in two halves (chainer F.lstm); h leaves as one 256-bit store per
+        //      destination (every lane writes its own row: the LSU cost is per instruction, not per byte)
+        uint32_t hp[8];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float acc[32];
+          if (s > 0) {
+            uint32_t r[32];
+            tmem_ld32(tmem_mine + static_cast<uint32_t>(half * 32), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(r[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+          }
+          if (active) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // columns [unit-major, gate-minor]: 2 words (a, i), (f, o) per unit
+            const float2 ga = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gxr[2 * half + (j >> 2)][(2 * j) & 7]));
+            const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gxr[2 * half + (j >> 2)][(2 * j + 1) & 7]));
+            const float a = tanh_fast(acc[4 * j] + ga.x);
+            const float ig = wide_sigmoid(acc[4 * j + 1] + ga.y);
+            const float fg = wide_sigmoid(acc[4 * j + 2] + gf.x);
+            const float og = wide_sigmoid(acc[4 * j + 3] + gf.y);
+            float& c = c_reg[half * 8 + j];
+            c = fmaf(a, ig, fg * c);
+            const float h_new = og * tanh_fast(c);
+            const uint32_t hb = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(h_new)));
+            if (j & 1)
+              hp[half * 4 + (j >> 1)] |= hb << 16;
+            else
+              hp[half * 4 + (j >> 1)] = hb;
+          }
+          }
+        }
+        if (active) {
+          const int col = rank * UNITS + sub * 16;
+          const long long xoff = (static_cast<long long>(lane_id_ * 4 + (s & 1)) * NB + u) * H + col;
+          stg_256(p.xchg_hi + xoff, hp);
+          stg_256(p.h_hi + my_row * p.h_ld + h_col0 + col, hp);
+        }
+        tc_fence_before();
+        PROF_MARK(3);
+        // ---- publish: the stream barrier orders every thread's stores before one thread's release
+        w2_bar_sync(stream);
+        if (stid == 0) red_release_gpu_add(counter, 1u);
+        ++steps_done;
+        PROF_MARK(4);
+      }
+    }
+  }
+
+  if (prof_on) {
+    prof_acc[7] = steps_done;
+    for (int i = 0; i < 8; ++i) p.prof[blockIdx.x * 8 + i] = prof_acc[i];
+  }
+#undef PROF_START
+#undef PROF_MARK
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+size_t rnn_wide2_smem_bytes(int hidden) {
+  const size_t kb = hidden / 64;
+  return kb * 128 * 128 + static_cast<size_t>(W2_STAGES) * WIDE_A_STAGE + 8 * (1 + 2 * W2_STREAMS + (W2_STREAMS + 1) * W2_STAGES) +
+         8 * 4 + W2_STREAMS * (WIDE_NB + W2_BASE_SMEM + 1) * 4;
+}
+
+// streams per CTA group of the 128-slot kernel: 2 (default) or 1 (NNAM_RNN_WIDE_STREAMS=1, the single-batch kernel)
+int rnn_wide_streams() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NNAM_RNN_WIDE_STREAMS");
+    v = (e && atoi(e) == 1) ? 1 : 2;
+  }
+  return v;
+}
+
 size_t rnn_wide_smem_bytes(int hidden) {
   const size_t kb = hidden / 64;
   return kb * 128 * 128 + static_cast<size_t>(WIDE_STAGES) * WIDE_A_STAGE + 8 * (2 + 2 * WIDE_STAGES) + 16 +
@@ -288,7 +596,7 @@ size_t rnn_wide_smem_bytes(int hidden) {
 bool rnn_wide_applies(int cell, int hidden, int batch, int nsplit) {
   if (cell != NNAM_CELL_LSTM || nsplit != 1 || batch != WIDE_NB) return false;
   if (hidden % 64 || (4 * hidden) % 128) return false;
-  if (rnn_wide_smem_bytes(hidden) > 227 * 1024) return false;
+  if ((rnn_wide_streams() == 2 ? rnn_wide2_smem_bytes(hidden) : rnn_wide_smem_bytes(hidden)) > 227 * 1024) return false;
   return sm_count() >= 4 * hidden / 128;
 }
 
@@ -303,8 +611,24 @@ static int launch_wide(const RnnTmaps& tm, const RnnParams& p, int grid, size_t 
   return NNAM_OK;
 }
 
+template <int KBT>
+static int launch_wide2(const RnnTmaps& tm, const RnnParams& p, int grid, size_t smem, cudaStream_t stream) {
+  auto kern = lstm_seq_wide2_kernel<KBT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaFuncSetAttribute(wide2)");
+  void* args[] = {const_cast<RnnTmaps*>(&tm), const_cast<RnnParams*>(&p)};
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(W2_THREADS), args, smem, stream);
+  if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaLaunchCooperativeKernel(wide2)");
+  return NNAM_OK;
+}
+
 int rnn_wide_launch(const RnnTmaps& tm, const RnnParams& p, int hidden, cudaStream_t stream) {
   const int grid = p.n_groups * p.group_ctas;
+  if (rnn_wide_streams() == 2) {
+    const size_t smem2 = rnn_wide2_smem_bytes(hidden);
+    if (hidden == 512) return launch_wide2<8>(tm, p, grid, smem2, stream);
+    return launch_wide2<0>(tm, p, grid, smem2, stream);
+  }
   const size_t smem = rnn_wide_smem_bytes(hidden);
   if (hidden == 512) return launch_wide<8>(tm, p, grid, smem, stream);
   return launch_wide<0>(tm, p, grid, smem, stream);

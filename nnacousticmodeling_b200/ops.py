@@ -205,6 +205,13 @@ def rnn_plan(cell, hidden, batch, nsplit):
     return g.value, m.value, c.value, s.value
 
 
+def rnn_solo_step_cycles(cell, hidden, batch, nsplit):
+    """SM cycles per step of a stream whose sibling streams in the group are idle (see include/nnam_b200.h)."""
+    c = ctypes.c_int(0)
+    check(_native.lib().nnam_rnn_solo_step_cycles(cell, hidden, batch, nsplit, ctypes.byref(c)))
+    return c.value
+
+
 def rnn_seq(desc, flops):
     """K3: run one recurrent layer (all batches, one or both directions) described by an RnnDesc."""
     with _Prof("rnn", flops):

@@ -130,7 +130,7 @@ def build_plan(plan, model):
 # ------------------------------------------------------------------------------------------
 # schedule
 # ------------------------------------------------------------------------------------------
-def assign_lanes(bsteps, n_dirs, max_groups, streams):
+def assign_lanes(bsteps, n_dirs, max_groups, streams, solo_ratio=1.0):
     """Spread the (batch, direction) work items over lanes = (CTA group, stream).  Returns (items per lane, groups
     used, critical path in steps).
 
@@ -138,7 +138,10 @@ def assign_lanes(bsteps, n_dirs, max_groups, streams):
     is the sum of their step counts -- longest-processing-time-first, then moves / swaps out of the fullest group
     until nothing improves (on the test-shaped set that takes the critical path from 880 to 798 steps; the bound is
     the longest utterance, 785).  Several streams per group: per direction LPT over the lanes; the critical path
-    accounts for a group switching direction only when all of its streams are done with the current one."""
+    accounts for a group switching direction only when all of its streams are done with the current one.  Two streams
+    per group (the 128-slot kernel): see :func:`_assign_pairs`."""
+    if streams == 2:
+        return _assign_pairs(bsteps, n_dirs, max_groups, solo_ratio)
     n_batches = len(bsteps)
     bsteps = [int(t) for t in bsteps]
     n_groups = max(1, min(max_groups, (n_batches * (n_dirs if streams == 1 else 1) + streams - 1) // streams))
@@ -193,6 +196,92 @@ def assign_lanes(bsteps, n_dirs, max_groups, streams):
     return per_lane, n_groups, (int(per_group.max()) if n_batches else 0)
 
 
+def _assign_pairs(bsteps, n_dirs, max_groups, solo_ratio):
+    """Lane assignment for groups of two streams.  A step of a stream costs ``c_busy`` cycles while its sibling is
+    busy and ``c_solo = solo_ratio * c_busy`` once the sibling has run out of work, so (in units of busy steps) a
+    group needs  solo_ratio * longer lane + (1 - solo_ratio) * shorter lane  per direction, and both streams switch
+    direction together.  Greedy longest-first onto the lane that leaves its group cheapest, then moves / swaps out of
+    the most expensive group while that lowers the maximum.  Returns (items per lane, groups, critical path in busy
+    steps)."""
+    n_batches = len(bsteps)
+    bsteps = [int(t) for t in bsteps]
+    n_groups = max(1, min(max_groups, n_batches))
+    r = float(solo_ratio)
+    load = np.zeros((n_groups, 2, n_dirs), np.float64)
+    lanes = [[[] for _ in range(2)] for _ in range(n_groups)]
+
+    def gcost(g):
+        a = load[g]
+        return float((r * a.max(axis=0) + (1.0 - r) * a.min(axis=0)).sum())
+
+    def gcost_with(g, s_, d, delta):
+        load[g, s_, d] += delta
+        c = gcost(g)
+        load[g, s_, d] -= delta
+        return c
+
+    items = sorted(((bsteps[b], b, d) for b in range(n_batches) for d in range(n_dirs)), key=lambda t: -t[0])
+    for t, b, d in items:
+        best = None
+        for g in range(n_groups):
+            for s_ in range(2):
+                c = gcost_with(g, s_, d, t)
+                if best is None or c < best[0] - 1e-9:
+                    best = (c, g, s_)
+            if not load[g].any():
+                break  # all further groups are empty too: same cost
+        _, g, s_ = best
+        load[g, s_, d] += t
+        lanes[g][s_].append((t, b, d))
+    cost = [gcost(g) for g in range(n_groups)]
+    for _ in range(400):
+        gw = int(np.argmax(cost))
+        done = True
+        for sw in range(2):
+            for i, (t, b, d) in enumerate(lanes[gw][sw]):
+                for g in range(n_groups):
+                    if g == gw:
+                        continue
+                    for s_ in range(2):
+                        # move
+                        load[gw, sw, d] -= t
+                        load[g, s_, d] += t
+                        if max(gcost(gw), gcost(g)) < cost[gw] - 1e-9:
+                            lanes[g][s_].append(lanes[gw][sw].pop(i))
+                            cost[gw], cost[g] = gcost(gw), gcost(g)
+                            done = False
+                            break
+                        load[gw, sw, d] += t
+                        load[g, s_, d] -= t
+                        # swap with a shorter item of the same direction
+                        for j, (t2, b2, d2) in enumerate(lanes[g][s_]):
+                            if d2 != d or t2 >= t:
+                                continue
+                            load[gw, sw, d] += t2 - t
+                            load[g, s_, d] += t - t2
+                            if max(gcost(gw), gcost(g)) < cost[gw] - 1e-9:
+                                lanes[gw][sw][i], lanes[g][s_][j] = (t2, b2, d2), (t, b, d)
+                                cost[gw], cost[g] = gcost(gw), gcost(g)
+                                done = False
+                                break
+                            load[gw, sw, d] -= t2 - t
+                            load[g, s_, d] -= t - t2
+                        if not done:
+                            break
+                    if not done:
+                        break
+                if not done:
+                    break
+            if not done:
+                break
+        if done:
+            break
+    used = max((g + 1 for g in range(n_groups) if lanes[g][0] or lanes[g][1]), default=1)
+    per_lane = [sorted(((b, d) for _, b, d in lanes[g][s_]), key=lambda t: (t[1], -bsteps[t[0]]))
+                for g in range(used) for s_ in range(2)]
+    return per_lane, used, (int(np.ceil(max(cost))) if n_batches else 0)
+
+
 class Schedule:
     """Packed time-major schedule of a set of utterances (host arrays + device copies).
 
@@ -200,7 +289,7 @@ class Schedule:
     they are spread over LANES = (CTA group, stream): a group runs ``streams`` batches concurrently against one
     resident weight slice, so all streams of a group work on the same direction at a time (direction 0 first)."""
 
-    def __init__(self, steps, nb, n_dirs, max_groups, device, streams=1):
+    def __init__(self, steps, nb, n_dirs, max_groups, device, streams=1, solo_ratio=1.0):
         steps = np.asarray(steps, dtype=np.int64)
         n_utt = len(steps)
         self.nb, self.n_utt, self.streams = nb, n_utt, streams
@@ -236,7 +325,7 @@ class Schedule:
         self.row_step = np.concatenate(row_step) if row_step else np.zeros(0, np.int64)
         utt_len = np.zeros(n_batches * nb, np.int32)
         utt_len[:n_utt] = s_sorted
-        per_lane, self.n_groups, self.max_group_steps = assign_lanes(bsteps, n_dirs, max_groups, streams)
+        per_lane, self.n_groups, self.max_group_steps = assign_lanes(bsteps, n_dirs, max_groups, streams, solo_ratio)
         n_lanes = self.n_groups * streams
         flat = [it for ln in per_lane for it in ln]
         starts = np.concatenate([[0], np.cumsum([len(ln) for ln in per_lane])]).astype(np.int32)
@@ -253,6 +342,12 @@ class Schedule:
         self.d_base = dv(np.concatenate(bases) if bases else np.zeros(1, np.int32))
         self.d_utt_len = dv(utt_len)
         self.d_counters = torch.zeros(max(n_lanes, 1), dtype=torch.int32, device=device)
+
+
+def _solo_ratio(plan, nb, nsplit, busy_cycles, streams):
+    if streams != 2:
+        return 1.0
+    return min(1.0, ops.rnn_solo_step_cycles(plan.cell, plan.hidden, nb, nsplit) / float(busy_cycles))
 
 
 def pick_schedule(plan, steps, device, nb=None):
@@ -276,14 +371,16 @@ def pick_schedule(plan, steps, device, nb=None):
             if len(cands) == 1:
                 raise
             continue
-        _, _, crit = assign_lanes(s_sorted[::cand], plan.n_dirs, max_groups, streams)  # a batch runs as long as its
-        cost = crit * cycles                                                           # longest utterance
+        ratio = _solo_ratio(plan, cand, nsplit, cycles, streams)
+        # a batch runs as long as its longest utterance
+        _, _, crit = assign_lanes(s_sorted[::cand], plan.n_dirs, max_groups, streams, ratio)
+        cost = crit * cycles
         if best is None or cost < best[0]:
-            best = (cost, cand, max_groups, streams)
+            best = (cost, cand, max_groups, streams, ratio)
     if best is None:
         raise NnamError("no recurrent kernel configuration fits this layer size / precision")
-    _, cand, max_groups, streams = best
-    res = (Schedule(steps, cand, plan.n_dirs, max_groups, device, streams), cand)
+    _, cand, max_groups, streams, ratio = best
+    res = (Schedule(steps, cand, plan.n_dirs, max_groups, device, streams, ratio), cand)
     if len(cache) >= 8:
         cache.pop(next(iter(cache)))
     cache[key] = res

@@ -227,13 +227,15 @@ def test_timedelay_longer_than_some_utterances_and_empty_input(nn, network):
     assert empty.shape == (0, 39)
 
 
-@pytest.mark.parametrize("network,units", [("lstm", 512), ("blstm", 128), ("lstm", 192)])
-def test_wide_kernel_128_slots_per_batch(nn, network, units):
+@pytest.mark.parametrize("network,units,n_utt", [("lstm", 512, 300), ("blstm", 128, 300), ("lstm", 192, 300),
+                                                 ("lstm", 512, 2700), ("blstm", 512, 2500)])
+def test_wide_kernel_128_slots_per_batch(nn, network, units, n_utt):
     """The 128-slot "wide" LSTM kernel (utterances on the MMA's M axis, h streamed through a TMA ring) against the
     oracle and against the 32-slot kernel, on more than one batch with ragged lengths."""
     from nnacousticmodeling_b200 import recurrent_engine
     rng = np.random.default_rng(units)
-    lens = rng.integers(1, 60, size=300).tolist()
+    # 2500+ utterances: more batches than (CTA group, stream) lanes, so lanes run several items back to back
+    lens = rng.integers(1, 60 if n_utt == 300 else 45, size=n_utt).tolist()
     off = _offsets(lens)
     x = rng.standard_normal((off[-1], 40)).astype(np.float32)
     bid = network == "blstm"
@@ -243,7 +245,7 @@ def test_wide_kernel_128_slots_per_batch(nn, network, units):
     narrow = np.zeros_like(wide)
     recurrent_engine.forward_utterances(m, x, off, narrow, 0, len(lens), timedelay=0, device=0, nb=32)
     assert np.abs(wide - narrow).max() < 2e-2  # same bf16 arithmetic, different summation order / gx rounding points
-    pick = [0, 17, int(np.argmax(lens)), int(np.argmin(lens)), 299]
+    pick = [0, 17, int(np.argmax(lens)), int(np.argmin(lens)), n_utt - 1, n_utt // 2]
     for u in pick:
         xs = x[off[u]:off[u + 1]]
         if bid:
