@@ -116,7 +116,8 @@ int nnam_head_scatter(const float* const* logits_host, const float* weights_host
  * ivec[row_map[r]].  Replaces the per-utterance `np.pad(..., mode="edge")` + applyKaldiFeatureTransform + padded
  * (U, Lmax+timedelay, D) batch assembly of predict_folds.py:34-43 / evaluateModelForTest.py:57-59: row_map lists,
  * in time-major packed order, the source frame of every (utterance, step), repeating the last frame `timedelay`
- * times.  add_shift/rescale have `dim` entries (the shift-0 block) or are NULL.  Output bf16 / bf16 split / f32.  */
+ * times.  add_shift/rescale have `dim` entries (the shift-0 block) or are NULL.  Output bf16 / bf16 split / f32.
+ * A map entry outside [0, n_src) produces a zero row.  */
 int nnam_gather_transform(const float* x, long long n_src, int dim, const float* add_shift, const float* rescale,
                           const float* ivec, int ivec_dim, const int* row_map, long long n_rows, void* out_hi,
                           void* out_lo, long long ldo, int out_kind, void* stream);

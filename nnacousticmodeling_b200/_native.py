@@ -14,7 +14,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libnnam_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_cluster.cu", "recurrent_wide.cu", "peephole.cu"]
+SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_cluster.cu", "recurrent_wide.cu", "recurrent_wide_gru.cu", "peephole.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",

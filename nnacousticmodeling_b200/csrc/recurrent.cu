@@ -699,15 +699,23 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   if (d->n_items <= 0) return NNAM_OK;
   if (d->nsplit == 3 && (d->h_lo == nullptr)) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs h_lo");
   if (d->h_ld % 8 || d->w_ld % 8) return set_error(NNAM_ERR_ARG, "rnn: h_ld and w_ld must be multiples of 8");
-  const int gate_rows = 4 * H;
-  // 128 slots per batch: the "wide" LSTM kernel (utterances on the MMA's M axis, h streamed through a TMA ring)
+  // 128 slots per batch: the "wide" kernels (utterances on the MMA's M axis, h streamed through a TMA ring).  The GRU
+  // family variant takes gate-blocked rows without padding: 32 * n_gates rows per CTA (recurrent_wide_gru.cu)
   static const RnnCfg kWideCfg1 = {128, 128, 1, 0, 1, 16};
   static const RnnCfg kWideCfg2 = {128, 128, 1, 0, 2, 8};
-  const RnnCfg& kWideCfg = rnn_wide_streams() == 2 ? kWideCfg2 : kWideCfg1;
+  static const RnnCfg kWideGru3 = {96, 128, 1, 0, 2, 8};
+  static const RnnCfg kWideGru2 = {64, 128, 1, 0, 2, 8};
   const bool wide = d->batch == 128;
-  if (wide && (!rnn_wide_applies(d->cell, H, d->batch, d->nsplit) || d->h0_hi || d->c0 || d->c_out))
-    return set_error(NNAM_ERR_UNSUPPORTED, "rnn: 128 slots per batch are available for LSTM in bf16 mode without "
-                     "carried state only");
+  const bool wide_gru = wide && d->cell == NNAM_CELL_GRU;
+  const int gru_gates = (d->flags & 1) ? 3 : 2;
+  const RnnCfg& kWideCfg = wide_gru ? (gru_gates == 3 ? kWideGru3 : kWideGru2)
+                                    : (rnn_wide_streams() == 2 ? kWideCfg2 : kWideCfg1);
+  const int gate_rows = wide_gru ? gru_gates * H : 4 * H;
+  if (wide && (d->h0_hi || d->c0 || d->c_out ||
+               !(wide_gru ? rnn_wide_gru_applies(H, d->nsplit, gru_gates)
+                          : rnn_wide_applies(d->cell, H, d->batch, d->nsplit))))
+    return set_error(NNAM_ERR_UNSUPPORTED, "rnn: 128 slots per batch are available for LSTM and the GRU family in "
+                     "bf16 mode without carried state only");
   if (wide && (d->h_ld % 16 || d->gx_ld % 16 || (reinterpret_cast<uintptr_t>(d->h_hi) & 31) ||
                (reinterpret_cast<uintptr_t>(d->xchg_hi) & 31) || (reinterpret_cast<uintptr_t>(d->gx[0]) & 31) ||
                (d->n_dirs == 2 && (reinterpret_cast<uintptr_t>(d->gx[1]) & 31))))
@@ -798,6 +806,7 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   if (wide) {
     cudaError_t ew = cudaMemsetAsync(d->counters, 0, sizeof(unsigned int) * d->n_groups * cfg->s, stream);
     if (ew != cudaSuccess) return set_cuda_error(ew, "rnn: cudaMemsetAsync");
+    if (wide_gru) return rnn_wide_gru_launch(tm, p, H, gru_gates, stream);
     return rnn_wide_launch(tm, p, H, stream);
   }
   cudaError_t e = cudaMemsetAsync(d->counters, 0, sizeof(unsigned int) * d->n_groups * cfg->s, stream);
@@ -810,9 +819,20 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
   if (cell != NNAM_CELL_LSTM && cell != NNAM_CELL_GRU && cell != NNAM_CELL_PEEPHOLE)
     return set_error(NNAM_ERR_UNSUPPORTED, "rnn: cell kind %d not implemented", cell);
   if (hidden <= 0 || hidden % 64) return set_error(NNAM_ERR_UNSUPPORTED, "rnn: hidden size must be a multiple of 64");
+  if (batch == 128 && cell == NNAM_CELL_GRU) {
+    // gate-blocked rows, 32 units per CTA (recurrent_wide_gru.cu); figures for the reset-gate variant (two exchanges)
+    if (!rnn_wide_gru_applies(hidden, nsplit, 3))
+      return set_error(NNAM_ERR_UNSUPPORTED, "rnn: 128 slots per batch need bf16 mode and a slice that fits");
+    *group_ctas = hidden / 32;
+    *max_groups = sm_count() / *group_ctas;
+    if (step_cycles) *step_cycles = 21500;  // measured, reset-gate variant (11 k without reset gate)
+    if (streams) *streams = 2;
+    return NNAM_OK;
+  }
   if (batch == 128) {
     if (!rnn_wide_applies(cell, hidden, batch, nsplit))
-      return set_error(NNAM_ERR_UNSUPPORTED, "rnn: 128 slots per batch are available for LSTM in bf16 mode only");
+      return set_error(NNAM_ERR_UNSUPPORTED, "rnn: 128 slots per batch are available for LSTM and the GRU family in "
+                       "bf16 mode only");
     *group_ctas = 4 * hidden / 128;
     *max_groups = sm_count() / *group_ctas;
     // measured, profiles/r01_k3_phase_cycles.md: per step of ONE stream while all streams of the group are busy
@@ -848,7 +868,7 @@ int rnn_solo_step_cycles(int cell, int hidden, int batch, int nsplit, int* cycle
   int g = 0, m = 0, c = 0, s = 0;
   const int rc = rnn_plan(cell, hidden, batch, nsplit, &g, &m, &c, &s);
   if (rc) return rc;
-  if (batch == 128 && s == 2) c = 11500;  // measured: 10.7 k with one group running, profiles/r01_k3_phase_cycles.md
+  if (batch == 128 && s == 2) c = cell == NNAM_CELL_GRU ? 17700 : 11500;  // measured: 10.7 k with one group running, profiles/r01_k3_phase_cycles.md
   *cycles = c;
   return NNAM_OK;
 }

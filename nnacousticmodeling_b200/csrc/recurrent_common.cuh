@@ -107,6 +107,9 @@ int rnn_cluster_launch(const RnnTmaps& tm, const RnnParams& p, int G, int hidden
 // recurrent_wide.cu: LSTM / bf16 / 128 slots per batch
 bool rnn_wide_applies(int cell, int hidden, int batch, int nsplit);
 int rnn_wide_launch(const RnnTmaps& tm, const RnnParams& p, int hidden, cudaStream_t stream);
-int rnn_wide_streams();  // batches a CTA group of the 128-slot kernel runs concurrently (2, or 1 with NNAM_RNN_WIDE_STREAMS=1)
+int rnn_wide_streams();
+// recurrent_wide_gru.cu: GRU family / bf16 / 128 slots per batch, gate-blocked weight rows (n_gates = 3 with reset gate)
+bool rnn_wide_gru_applies(int hidden, int nsplit, int n_gates);
+int rnn_wide_gru_launch(const RnnTmaps& tm, const RnnParams& p, int hidden, int n_gates, cudaStream_t stream);  // batches a CTA group of the 128-slot kernel runs concurrently (2, or 1 with NNAM_RNN_WIDE_STREAMS=1)
 
 }  // namespace nnam

@@ -427,13 +427,18 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
         const bool active = u < n_s;
         const int t_idx = bwd ? (my_len - 1 - s) : s;
         const long long my_row = active ? row0 + bp[t_idx] + u : 0;
-        // 64 bf16 gate pre-activations of utterance u at this step: issued now, they land during the exchange
+        // 64 bf16 gate pre-activations of utterance u at this step.  Every lane reads its own row, so the four loads
+        // cost ~1-2 k cycles of LSU issue per warp: the six plain warps issue them now (they land during the exchange);
+        // the producer and the MMA issuer first start the h stream, which is the critical path of the step.
         uint32_t gxr[4][8] = {};
-        if (active) {
-          const __nv_bfloat16* src = gx + my_row * p.gx_ld;
+        auto load_gx = [&]() {
+          if (active) {
+            const __nv_bfloat16* src = gx + my_row * p.gx_ld;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) ldg_nc_256(src + 16 * j, gxr[j]);
-        }
+            for (int j = 0; j < 4; ++j) ldg_nc_256(src + 16 * j, gxr[j]);
+          }
+        };
+        if (s == 0 || sw >= 2) load_gx();
         PROF_MARK(0);
         if (s > 0) {
           if (sw == 0) {
@@ -454,6 +459,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
             }
             f0 = __shfl_sync(0xffffffffu, f0, 0);
             const int xrow = (lane_id_ * 4 + ((s - 1) & 1)) * NB;
+
             for (int kb = 0; kb < KB; ++kb) {
               const unsigned int f = f0 + kb;
               const int st = static_cast<int>(f % W2_STAGES);
@@ -471,6 +477,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
               atomicExch(ring_lock, 0u);
             }
             __syncwarp();
+            load_gx();
           } else if (sw == 1) {
             // ---- MMA issuer of this stream
             mbar_wait(&bar_grant[stream], grant_phase);
@@ -492,6 +499,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
                 if (kb == KB - 1) umma_commit(&bar_mma[stream]);
               }
               __syncwarp();
+              if (kb == 0) load_gx();  // behind the first k-block: the next ones are still in flight
             }
           }
           grant_phase ^= 1;

@@ -300,7 +300,7 @@ template <int OUT_KIND>
 __global__ void gather_transform_kernel(const float* __restrict__ x, int dim, const float* __restrict__ add,
                                         const float* __restrict__ mul, const float* __restrict__ ivec, int ivec_dim,
                                         const int* __restrict__ row_map, long long n_rows, void* out_hi_v,
-                                        void* out_lo_v, long long ldo) {
+                                        void* out_lo_v, long long ldo, long long n_src) {
   const long long vpr = ldo >> 3;
   const long long total = n_rows * vpr;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -308,11 +308,14 @@ __global__ void gather_transform_kernel(const float* __restrict__ x, int dim, co
     const long long r = i / vpr;
     const int c = static_cast<int>(i - r * vpr) << 3;
     const long long src = __ldg(row_map + r);
+    const bool in_range = src >= 0 && src < n_src;  // a map entry outside the source gives a zero row, never a stray read
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int cc = c + j;
-      if (cc < dim) {
+      if (!in_range) {
+        v[j] = 0.0f;
+      } else if (cc < dim) {
         float t = __ldg(x + src * dim + cc);
         if (add != nullptr) t = __fmul_rn(__fadd_rn(t, __ldg(add + cc)), __ldg(mul + cc));
         v[j] = t;
@@ -362,16 +365,16 @@ int gather_transform(const float* x, long long n_src, int dim, const float* add_
   switch (out_kind) {
     case NNAM_OUT_F32:
       gather_transform_kernel<NNAM_OUT_F32><<<g, 256, 0, stream>>>(x, dim, add_shift, rescale, ivec, ivec_dim, row_map,
-                                                                  n_rows, out_hi, out_lo, ldo);
+                                                                  n_rows, out_hi, out_lo, ldo, n_src);
       break;
     case NNAM_OUT_BF16:
       gather_transform_kernel<NNAM_OUT_BF16><<<g, 256, 0, stream>>>(x, dim, add_shift, rescale, ivec, ivec_dim,
-                                                                   row_map, n_rows, out_hi, out_lo, ldo);
+                                                                   row_map, n_rows, out_hi, out_lo, ldo, n_src);
       break;
     case NNAM_OUT_BF16_SPLIT:
       if (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 15)) return set_error(NNAM_ERR_ARG, "gather: out_lo");
       gather_transform_kernel<NNAM_OUT_BF16_SPLIT><<<g, 256, 0, stream>>>(x, dim, add_shift, rescale, ivec, ivec_dim,
-                                                                         row_map, n_rows, out_hi, out_lo, ldo);
+                                                                         row_map, n_rows, out_hi, out_lo, ldo, n_src);
       break;
     default:
       return set_error(NNAM_ERR_ARG, "gather: unknown out_kind %d", out_kind);

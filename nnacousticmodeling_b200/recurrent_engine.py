@@ -127,6 +127,47 @@ def build_plan(plan, model):
     plan.out = LinearDev(p["out/W"], p["out/b"], dev, split)
 
 
+def _block32(blocks, h):
+    """Gate-blocked row order of the 128-slot GRU kernel: for every 32 units the rows of gate 0, then gate 1, ..."""
+    cols = blocks[0].shape[1:]
+    a = np.stack([np.asarray(b, dtype=np.float32).reshape((h // 32, 32) + cols) for b in blocks], axis=1)
+    return np.ascontiguousarray(a.reshape((len(blocks) * h,) + cols))
+
+
+def gru_wide_layers(plan, model):
+    """Second packing of a GRU-family net for the 128-slot kernel (csrc/recurrent_wide_gru.cu): rows / gx columns
+    [z(32) | r(32) | cand(32)] per 32 units (no reset gate: [z | cand]), and the U biases folded into the projection
+    bias (the kernel takes them out again at step 0, where MGRU.py:70-83 has no U terms).  Built on first use."""
+    layers = plan.__dict__.get("_gru_wide_layers")
+    if layers is not None:
+        return layers
+    p, dev, h = model.params, plan.device, plan.hidden
+    reset = bool(plan.gru_flags & 1)
+    dirs = ("fwd/", "bwd/") if model.bidirectional else ("",)
+    names = ["z", "r", ""] if reset else ["z", ""]
+
+    def key(pre, mat, g):
+        return f"{pre}{mat}_{g}" if g else f"{pre}{mat}"
+
+    layers = []
+    for l in range(model.layers):
+        L = RecLayer()
+        ups, upb, L.lat, L.u_bias = [], [], [], []
+        for d in dirs:
+            pre = f"layer_{l}/{d}"
+            ub = _block32([p[key(pre, "U", g) + "/b"][:, None] for g in names], h)[:, 0]
+            ups.append(_block32([p[key(pre, "W", g) + "/W"] for g in names], h))
+            upb.append(_block32([p[key(pre, "W", g) + "/b"][:, None] for g in names], h)[:, 0] + ub)
+            L.lat.append(ops.convert_f32(torch.from_numpy(_block32([p[key(pre, "U", g) + "/W"] for g in names], h)).to(dev),
+                                         OUT_BF16))
+            L.u_bias.append(torch.from_numpy(np.ascontiguousarray(ub)).to(dev))
+        L.upward = LinearDev(np.concatenate(ups, axis=0), np.concatenate(upb, axis=0), dev, False)
+        L.gate_cols = len(names) * h
+        layers.append(L)
+    plan._gru_wide_layers = layers
+    return layers
+
+
 # ------------------------------------------------------------------------------------------
 # schedule
 # ------------------------------------------------------------------------------------------
@@ -394,7 +435,7 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
     d.streams = sched.streams
     d.flags = plan.gru_flags
     for k in range(nd):
-        d.gx[k] = gx.data_ptr() + gx.element_size() * k * 4 * H
+        d.gx[k] = gx.data_ptr() + gx.element_size() * k * getattr(layer, "gate_cols", 4 * H)
         d.w_hi[k] = layer.lat[k][0].data_ptr()
         d.w_lo[k] = layer.lat[k][1].data_ptr() if plan.split else None
         d.u_bias[k] = layer.u_bias[k].data_ptr() if layer.u_bias[k] is not None else None
@@ -431,13 +472,17 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
     ws = ws or plan.ws
     H, nd = plan.hidden, plan.n_dirs
     state_out = []
-    for l, layer in enumerate(plan.rec_layers):
+    rec_layers = plan.rec_layers
+    if nb == 128 and plan.cell == CELL_GRU:  # the 128-slot GRU kernel takes gate-blocked rows
+        rec_layers = gru_wide_layers(plan, model)
+    for l, layer in enumerate(rec_layers):
         # input projection of every frame: fp32 in the fp32-accurate mode, bf16 in bf16 mode
+        gate_cols = getattr(layer, "gate_cols", 4 * H)
         if plan.split:
             gx = ws.get(f"{tag}.gx", rows, nd * 4 * H, torch.float32)
             layer.upward(a_hi, a_lo, rows, "identity", OUT_F32, out=(gx, None))
         else:
-            gx = ws.get(f"{tag}.gx16", rows, nd * 4 * H, torch.bfloat16)
+            gx = ws.get(f"{tag}.gx16", rows, nd * gate_cols, torch.bfloat16)
             layer.upward(a_hi, a_lo, rows, "identity", OUT_BF16, out=(gx, None))
         slot = l if want_state else l % 2  # a carried state needs every layer's h kept
         h_hi = ws.get(f"{tag}.h{slot}.hi", rows, nd * H, torch.bfloat16)

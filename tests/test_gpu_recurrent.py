@@ -253,3 +253,30 @@ def test_wide_kernel_128_slots_per_batch(nn, network, units, n_utt):
         else:
             want = O.log_softmax(O.rnn_forward_utterance(p, "lstm", 2, xs))
         assert np.abs(wide[off[u]:off[u + 1]] - want).max() < 5e-2
+
+
+@pytest.mark.parametrize("network,units,n_utt", [("gru", 512, 300), ("mgrurelu", 512, 300), ("mgrurelur", 128, 300),
+                                                 ("bgru", 192, 300), ("gru", 512, 2700), ("mgrurelu", 256, 2600)])
+def test_wide_gru_kernel_128_slots_per_batch(nn, network, units, n_utt):
+    """The 128-slot GRU-family kernel (gate-blocked rows, two exchanges per step with the reset gate) against the
+    32-slot kernel on the whole set and against the oracle on a few utterances."""
+    from nnacousticmodeling_b200 import recurrent_engine
+    rng = np.random.default_rng(units + n_utt)
+    lens = rng.integers(1, 60 if n_utt == 300 else 45, size=n_utt).tolist()
+    off = _offsets(lens)
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    bid = network == "bgru"
+    m, p = _gru(nn, 91, network, 40, units, 2, 39, precision="bf16", bidirectional=bid)
+    wide = np.zeros((off[-1], 39), np.float32)
+    recurrent_engine.forward_utterances(m, x, off, wide, 0, len(lens), timedelay=0, device=0, nb=128)
+    narrow = np.zeros_like(wide)
+    recurrent_engine.forward_utterances(m, x, off, narrow, 0, len(lens), timedelay=0, device=0, nb=32)
+    assert np.abs(wide - narrow).max() < 3e-2
+    base = "gru" if bid else network
+    for u in [0, 17, int(np.argmax(lens)), int(np.argmin(lens)), n_utt - 1, n_utt // 2]:
+        xs = x[off[u]:off[u + 1]]
+        if bid:
+            want = O.log_softmax(O.birnn_forward_utterance(p, "gru", 2, xs))
+        else:
+            want = O.log_softmax(O.rnn_forward_utterance(p, base, 2, xs))
+        assert np.abs(wide[off[u]:off[u + 1]] - want).max() < 5e-2
