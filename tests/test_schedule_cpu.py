@@ -61,3 +61,35 @@ def test_schedule_single_and_equal_lengths():
     s = Schedule([1] * 40, 32, 1, 9, torch.device("cpu"))
     assert s.n_rows == 40 and np.array_equal(s.order, np.arange(40))  # stable sort keeps input order
     assert s.d_row0.tolist() == [0, 32]
+
+
+def test_pair_assignment_covers_every_item_once_and_costs_solo_tail():
+    """Two-stream groups (the 128-slot kernels): every (batch, direction) item lands on exactly one lane, lanes are
+    direction-sorted, and the reported critical path follows  solo * longer lane + (1 - solo) * shorter lane."""
+    from nnacousticmodeling_b200.recurrent_engine import assign_lanes
+    rng = np.random.default_rng(3)
+    for n_dirs in (1, 2):
+        for n_batches in (1, 2, 7, 29, 60):
+            bsteps = np.sort(rng.integers(5, 800, n_batches))[::-1]
+            for ratio in (1.0, 0.8):
+                per_lane, n_groups, crit = assign_lanes(bsteps, n_dirs, 9, 2, ratio)
+                assert len(per_lane) == 2 * n_groups and 1 <= n_groups <= 9
+                flat = [it for ln in per_lane for it in ln]
+                assert sorted(flat) == sorted((b, d) for b in range(n_batches) for d in range(n_dirs))
+                worst = 0.0
+                for g in range(n_groups):
+                    cost = 0.0
+                    for d in range(n_dirs):
+                        a, b = (sum(int(bsteps[i]) for i, dd in per_lane[2 * g + s] if dd == d) for s in range(2))
+                        cost += ratio * max(a, b) + (1 - ratio) * min(a, b)
+                    worst = max(worst, cost)
+                    for s in range(2):
+                        dirs = [dd for _, dd in per_lane[2 * g + s]]
+                        assert dirs == sorted(dirs)
+                assert abs(crit - np.ceil(worst)) <= 1
+                # never worse than the trivial bounds
+                assert crit >= ratio * int(bsteps[0]) - 1
+    # a lone long batch is cheaper next to an idle sibling than the all-busy figure
+    _, _, busy = assign_lanes([785, 100, 90], 1, 9, 2, 1.0)
+    _, _, solo = assign_lanes([785, 100, 90], 1, 9, 2, 0.8)
+    assert solo < busy
