@@ -141,7 +141,9 @@ typedef struct NnamRnnDesc {
   int cell;    /* NNAM_CELL_* */
   int hidden;  /* H (multiple of 64) */
   int n_dirs;  /* 1, or 2 = bidirectional: direction 1 walks every utterance backwards */
-  int batch;   /* utterance slots per batch (= per stream): 16, 32, 64, or 128 (LSTM in bf16 mode: the "wide" kernel) */
+  int batch;   /* utterance slots per batch (= per stream): 16, 32, 64, or 128 (LSTM and the GRU family in bf16 mode
+                  without carried state: the "wide" kernels, utterances on the MMA's M axis, two streams per group;
+                  they need 32-byte aligned gx / h / xchg buffers and gx_ld, h_ld multiples of 16) */
   int streams; /* independent batches a CTA group runs concurrently (from nnam_rnn_plan) */
   int nsplit;  /* 1 = bf16 operands, 3 = bf16x3 (needs the _lo buffers) */
   int flags;   /* GRU family: bit 0 = reset gate, bits 1-2 = candidate activation (NNAM_ACT_*) */
@@ -152,7 +154,11 @@ typedef struct NnamRnnDesc {
   const void* w_hi[2]; /* per direction: lateral weights (4H, H) bf16 K-major.  LSTM: Chainer lateral/W as is.
                           GRU family: rows interleaved per unit [U_z, U_r (or 0), U, 0]; gx and u_bias likewise.
                           PEEPHOLE (unidirectional): [0] = lateral/W, [1] = peephole block, rows per unit
-                          [0, peep_i, peep_f, peep_o] (L.StatefulPeepholeLSTM, chainer_networks.py:103-121) */
+                          [0, peep_i, peep_f, peep_o] (L.StatefulPeepholeLSTM, chainer_networks.py:103-121).
+                          GRU family with batch == 128: gate-BLOCKED rows without padding, (n_g * H, H) with n_g = 3
+                          (reset gate) or 2: for every 32 units the 32 rows of U_z, then U_r (if any), then U; gx
+                          columns and u_bias in the same order, gx_ld >= n_dirs * n_g * H, and the projection bias
+                          already holds W_b + U_b (the kernel subtracts u_bias again at step 0) */
   const void* w_lo[2];
   long long w_ld;
   const float* u_bias[2]; /* GRU family: hidden-side biases, applied from the second step on (MGRU.py:70-83) */
