@@ -91,7 +91,10 @@ __device__ __forceinline__ void stage_row_128B(uint8_t* box, int lane, const uin
 // stream in the shadow of the GEMMs.
 constexpr int GEMM_MAX_REGS = 184;
 
-template <int OUT_KIND>
+// ST: stages of the operand ring; NBOX: staging boxes per epilogue warp = TMA stores it keeps in flight.  Layers with
+// short K are bound by the output stream, and that stream by the bytes of stores in flight per SM (32 KB gave
+// 3.3 TB/s): they run with 3 stages and 4 boxes per warp.
+template <int OUT_KIND, int ST, int NBOX>
 __global__ void __maxnreg__(GEMM_MAX_REGS)
     gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                          const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
@@ -99,12 +102,12 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
                          const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024 B alignment (checked below)
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* smem_epi = smem_b + STAGES * B_STAGE_BYTES;
-  float* smem_bias = reinterpret_cast<float*>(smem_epi + EPI_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + EPI_BYTES + BIAS_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint8_t* smem_b = smem + ST * A_STAGE_BYTES;
+  uint8_t* smem_epi = smem_b + ST * B_STAGE_BYTES;
+  float* smem_bias = reinterpret_cast<float*>(smem_epi + (4 * NBOX * EPI_BOX_BYTES));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_epi + (4 * NBOX * EPI_BOX_BYTES) + BIAS_BYTES);
+  uint64_t* empty_bar = full_bar + ST;
+  uint64_t* tfull_bar = empty_bar + ST;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
@@ -125,7 +128,7 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
     if (OUT_KIND == NNAM_OUT_BF16_SPLIT) prefetch_tmap(&tm_o_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) {
+    for (int s = 0; s < ST; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -168,7 +171,7 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
             tma_load_2d(smem_b + stage * B_STAGE_BYTES, mw, &full_bar[stage], kb * BK, n_blk * p.bn);
           }
           __syncwarp();
-          if (++stage == STAGES) {
+          if (++stage == ST) {
             stage = 0;
             phase ^= 1;
           }
@@ -203,7 +206,7 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
           if (it == k_iters - 1) umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
-        if (++stage == STAGES) {
+        if (++stage == ST) {
           stage = 0;
           phase ^= 1;
         }
@@ -216,7 +219,7 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
     // TMEM -> registers (tcgen05.ld 32x32b.x32) -> + bias, activation, (hi/lo split) -> swizzled smem box -> TMA store
     constexpr int BOX_COLS = OUT_KIND == NNAM_OUT_F32 ? 32 : 64;  // 128 B of output per row and box
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    uint8_t* boxes = smem_epi + q * 2 * EPI_BOX_BYTES;
+    uint8_t* boxes = smem_epi + q * NBOX * EPI_BOX_BYTES;
     int box_sel = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -286,7 +289,7 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
                                      pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
           }
           uint8_t* box = boxes + box_sel * EPI_BOX_BYTES;
-          if (lane == 0) tma_store_wait_read<1>();  // the store issued from this box two boxes ago has read it
+          if (lane == 0) tma_store_wait_read<NBOX - 1>();  // the store issued from this box NBOX boxes ago has read it
           __syncwarp();
           stage_row_128B(box, lane, chunks);
           fence_proxy_async_smem();
@@ -295,7 +298,7 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
             tma_store_2d(o == 0 ? &tm_o_hi : &tm_o_lo, box, col, row0);
             tma_store_commit();
           }
-          box_sel ^= 1;
+          box_sel = box_sel + 1 == NBOX ? 0 : box_sel + 1;
         }
       }
       tc_fence_before();
@@ -436,7 +439,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
       const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(smem_a));
       const uint64_t bdesc0 = make_sw128_kmajor_desc(smem_u32(smem_b));
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        mbar_wait_cluster_acquire(&tempty_bar[acc], acc_phase ^ 1);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);  // no data crosses here: plain wait, tcgen05 fences order the rest
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * MAX_BN);
         for (int it = 0; it < k_iters; ++it) {
@@ -543,7 +546,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster_release(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
+      if (lane == 0) mbar_arrive_remote(mapa_shared(smem_u32(&tempty_bar[acc]), 0));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -600,29 +603,50 @@ static bool use_2sm(int M, int N, int K) {
     const char* v = getenv("NNAM_GEMM_2SM");
     env = (v != nullptr && v[0] == '0') ? 0 : 1;
   }
-  // short-K shapes are bound by the output stream, where the pair kernel measured slower (cfg3 upward 512 -> 2048)
+  // K <= 256 is bound by the output stream in either kernel (80-86 us for a 65,536 x 2048 bf16 output); from K = 512
+  // on the pair kernel wins (108.9 vs 123 us) since the accumulator hand-off between the CTAs stopped using
+  // cluster-scope release / acquire (MEMBAR.ALL + ERRBAR per epilogue warp and CCTL.IVALL per tile)
   static int min_k = -1;
   if (min_k < 0) {
     const char* v = getenv("NNAM_GEMM_2SM_MINK");  // tuning aid
-    min_k = v != nullptr ? atoi(v) : 1024;
+    min_k = v != nullptr ? atoi(v) : 384;
   }
   return env == 1 && M >= 4096 && N >= 128 && K >= min_k;
 }
 
-template <int OUT_KIND>
-static int launch_gemm(const CUtensorMap (&tm)[6], const GemmParams& p, int grid, cudaStream_t stream) {
+constexpr int gemm_smem_bytes(int st, int nbox) {
+  return st * (A_STAGE_BYTES + B_STAGE_BYTES) + 4 * nbox * EPI_BOX_BYTES + BIAS_BYTES + 256;
+}
+
+template <int OUT_KIND, int ST, int NBOX>
+static int launch_gemm_variant(const CUtensorMap (&tm)[6], const GemmParams& p, int grid, cudaStream_t stream) {
   static bool attr_set[64] = {false};
+  constexpr int smem = gemm_smem_bytes(ST, NBOX);
+  static_assert(smem <= 227 * 1024, "GEMM shared memory over budget");
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel<OUT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GEMM_SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel<OUT_KIND, ST, NBOX>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute");
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  gemm_bias_act_kernel<OUT_KIND><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
-                                                                                  tm[5], p);
+  gemm_bias_act_kernel<OUT_KIND, ST, NBOX><<<grid, GEMM_THREADS, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
+                                                                                 tm[5], p);
   return check_launch("gemm_bias_act_kernel");
+}
+
+// short K: the output stream bounds the layer -> more stores in flight, one stage less (NNAM_GEMM_EPI_MAXK tunes the
+// switch; 0 = always the 4-stage / 2-box variant)
+template <int OUT_KIND>
+static int launch_gemm(const CUtensorMap (&tm)[6], const GemmParams& p, int grid, cudaStream_t stream) {
+  static int max_k = -1;
+  if (max_k < 0) {
+    const char* v = getenv("NNAM_GEMM_EPI_MAXK");
+    max_k = v != nullptr ? atoi(v) : 768;
+  }
+  if (p.K * p.nsplit <= max_k) return launch_gemm_variant<OUT_KIND, 3, 4>(tm, p, grid, stream);
+  return launch_gemm_variant<OUT_KIND, STAGES, 2>(tm, p, grid, stream);
 }
 
 int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,

@@ -190,6 +190,13 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, const uint4
 __device__ __forceinline__ void mbar_arrive_cluster_release(uint32_t cluster_bar_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
+// Arrive on a peer CTA's mbarrier without cluster-scope release semantics (the default .release.cta): for hand-offs
+// that carry no generic-proxy data, e.g. "this CTA's epilogue has drained its TMEM accumulator" -- the tcgen05 fences
+// order the tensor-core side.  The .release.cluster form costs MEMBAR.ALL + ERRBAR per arrive, the matching
+// .acquire.cluster wait a CCTL.IVALL (L1 invalidate) per success.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
 __device__ __forceinline__ void mbar_wait_cluster_acquire(uint64_t* bar, uint32_t parity) {
   uint32_t ok = 0;
   while (!ok) {
