@@ -91,9 +91,7 @@ __device__ __forceinline__ void stage_row_128B(uint8_t* box, int lane, const uin
 // stream in the shadow of the GEMMs.
 constexpr int GEMM_MAX_REGS = 184;
 
-// ST: stages of the operand ring; NBOX: staging boxes per epilogue warp = TMA stores it keeps in flight.  Layers with
-// short K are bound by the output stream, and that stream by the bytes of stores in flight per SM (32 KB gave
-// 3.3 TB/s): they run with 3 stages and 4 boxes per warp.
+// ST: stages of the operand ring; NBOX: staging boxes per epilogue warp = TMA stores it keeps in flight.
 template <int OUT_KIND, int ST, int NBOX>
 __global__ void __maxnreg__(GEMM_MAX_REGS)
     gemm_bias_act_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -636,14 +634,15 @@ static int launch_gemm_variant(const CUtensorMap (&tm)[6], const GemmParams& p, 
   return check_launch("gemm_bias_act_kernel");
 }
 
-// short K: the output stream bounds the layer -> more stores in flight, one stage less (NNAM_GEMM_EPI_MAXK tunes the
-// switch; 0 = always the 4-stage / 2-box variant)
+// Experiment kept behind NNAM_GEMM_EPI_MAXK=<K>: layers with K <= that value run with 3 stages and 4 store boxes per
+// epilogue warp (twice the TMA stores in flight).  Measured no change (K <= 256: 80.5 vs 80.4 us per 65,536 x 2048
+// bf16 output), so the output-bound floor is not the number of stores in flight; default off.
 template <int OUT_KIND>
 static int launch_gemm(const CUtensorMap (&tm)[6], const GemmParams& p, int grid, cudaStream_t stream) {
   static int max_k = -1;
   if (max_k < 0) {
     const char* v = getenv("NNAM_GEMM_EPI_MAXK");
-    max_k = v != nullptr ? atoi(v) : 768;
+    max_k = v != nullptr ? atoi(v) : 0;
   }
   if (p.K * p.nsplit <= max_k) return launch_gemm_variant<OUT_KIND, 3, 4>(tm, p, grid, stream);
   return launch_gemm_variant<OUT_KIND, STAGES, 2>(tm, p, grid, stream);
