@@ -243,13 +243,15 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
         const int col = n_blk * p.bn + c0;
         if (col >= p.N || row0 >= p.M) break;  // warp-uniform; the TMA store clips partial boxes
         float v[BOX_COLS];
+        {
+          // both 32-column loads of a bf16 box are issued before the one wait (a single epilogue warp per scheduler
+          // has nothing else to hide the TMEM latency behind)
+          uint32_t r[BOX_COLS / 32][32];
 #pragma unroll
-        for (int j0 = 0; j0 < BOX_COLS; j0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0 + j0, r);
+          for (int j0 = 0; j0 < BOX_COLS / 32; ++j0) tmem_ld32(taddr + c0 + 32 * j0, r[j0]);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j0 + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < BOX_COLS; ++j) v[j] = __uint_as_float(r[j >> 5][j & 31]);
         }
         if (p.bias != nullptr) {
           const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);  // broadcast reads of the staged slice
@@ -490,13 +492,15 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
         const int col = n_blk * p.bn + c0;
         if (col >= p.N || row0 >= p.M) break;
         float v[BOX_COLS];
+        {
+          // both 32-column loads of a bf16 box are issued before the one wait (a single epilogue warp per scheduler
+          // has nothing else to hide the TMEM latency behind)
+          uint32_t r[BOX_COLS / 32][32];
 #pragma unroll
-        for (int j0 = 0; j0 < BOX_COLS; j0 += 32) {
-          uint32_t r[32];
-          tmem_ld32(taddr + c0 + j0, r);
+          for (int j0 = 0; j0 < BOX_COLS / 32; ++j0) tmem_ld32(taddr + c0 + 32 * j0, r[j0]);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j0 + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < BOX_COLS; ++j) v[j] = __uint_as_float(r[j >> 5][j & 31]);
         }
         if (p.bias != nullptr) {
           const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);  // broadcast reads of the staged slice

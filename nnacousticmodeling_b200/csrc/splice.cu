@@ -31,6 +31,7 @@ struct SpliceParams {
   void* out_lo;
   long long ldo;
   int spl_cols;  // winlen * dim
+  int tile_f;    // frames per CTA (<= SPLICE_TILE_F), chosen per launch so that the grid fills whole waves
 };
 
 // value of output column c for tile-local frame r (raw rows staged at s_x, transform at s_add / s_mul)
@@ -49,33 +50,84 @@ __device__ __forceinline__ float splice_elem(const SpliceParams& p, const float*
 template <int OUT_KIND, bool VEC>
 __global__ void __launch_bounds__(SPLICE_THREADS) splice_transform_kernel(const SpliceParams p) {
   extern __shared__ __align__(16) float s_mem[];
-  const int halo_rows = SPLICE_TILE_F + 2 * p.splice;
+  const int halo_rows = p.tile_f + 2 * p.splice;
   float* s_x = s_mem;                        // halo_rows * dim
   float* s_add = s_x + halo_rows * p.dim;    // spl_cols (only when a transform is given)
   float* s_mul = s_add + p.spl_cols;
-  float* s_iv = s_mul + p.spl_cols;          // VEC only: the tile's i-vector rows, SPLICE_TILE_F x ivec_dim
+  float* s_iv = s_mul + p.spl_cols;          // VEC only: the tile's i-vector rows, tile_f x ivec_dim
   const bool has_ft = p.add_shift != nullptr;
-  const long long tile_f0 = p.f0 + static_cast<long long>(blockIdx.x) * SPLICE_TILE_F;
-  const int tile_n = static_cast<int>(min(static_cast<long long>(SPLICE_TILE_F), p.f1 - tile_f0));
+  const long long tile_f0 = p.f0 + static_cast<long long>(blockIdx.x) * p.tile_f;
+  const int tile_n = static_cast<int>(min(static_cast<long long>(p.tile_f), p.f1 - tile_f0));
   const int need_rows = tile_n + 2 * p.splice;
 
-  // ---- stage raw rows (clamped to the whole array) and the transform vectors
+  // ---- stage raw rows (clamped to the whole array), the tile's i-vector rows and the transform vectors
   if (VEC) {
+    // Every thread first ISSUES all the loads of its share (feature rows, i-vector rows, transform) and only then
+    // stores them: written as plain copy loops, each load -> store pair waited for its own DRAM round trip (13 of them
+    // back to back per thread), and that latency chain, not bandwidth, set the kernel's duration.
+    constexpr int UX = 4, UI = 8, UT = 2;
+    const int tid = threadIdx.x;
     const int vpr = p.dim >> 2;
-    for (int i = threadIdx.x; i < need_rows * vpr; i += SPLICE_THREADS) {
+    const int nx4 = need_rows * vpr;
+    const int n4 = p.ivec_dim > 0 ? (tile_n * p.ivec_dim) >> 2 : 0;
+    // i-vector rows of the tile are contiguous in global memory
+    const float4* iv4 = reinterpret_cast<const float4*>(p.ivec + (tile_f0 - p.f0) * p.ivec_dim);
+    auto x_src = [&](int i) {
       const int row = i / vpr, v = i - row * vpr;
       long long g = tile_f0 - p.splice + row;
       g = g < 0 ? 0 : (g >= p.n_total ? p.n_total - 1 : g);
-      const float4 val = __ldg(reinterpret_cast<const float4*>(p.x + (g - p.x_row0) * p.dim) + v);
-      reinterpret_cast<float4*>(s_x)[i] = val;
+      return reinterpret_cast<const float4*>(p.x + (g - p.x_row0) * p.dim) + v;
+    };
+    float4 xr[UX], ir[UI];
+    float ar[UT], mr[UT];
+#pragma unroll
+    for (int u = 0; u < UX; ++u) {
+      const int i = tid + u * SPLICE_THREADS;
+      if (i < nx4) xr[u] = __ldg(x_src(i));
     }
-    // i-vector rows of the tile are contiguous in global memory: stage them with the same wide, independent loads
-    // (reading them inside the emit loop made a few threads walk 16 dependent global loads per block, which alone set
-    // the kernel's duration: fp32 and bf16 outputs took the same 40-46 us)
-    if (p.ivec_dim > 0) {
-      const float4* iv4 = reinterpret_cast<const float4*>(p.ivec + (tile_f0 - p.f0) * p.ivec_dim);
-      const int n4 = (tile_n * p.ivec_dim) >> 2;
-      for (int i = threadIdx.x; i < n4; i += SPLICE_THREADS) reinterpret_cast<float4*>(s_iv)[i] = __ldg(iv4 + i);
+#pragma unroll
+    for (int u = 0; u < UI; ++u) {
+      const int i = tid + u * SPLICE_THREADS;
+      if (i < n4) ir[u] = __ldg(iv4 + i);
+    }
+    if (has_ft) {
+#pragma unroll
+      for (int u = 0; u < UT; ++u) {
+        const int i = tid + u * SPLICE_THREADS;
+        if (i < p.spl_cols) {
+          ar[u] = __ldg(p.add_shift + i);
+          mr[u] = __ldg(p.rescale + i);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UX; ++u) {
+      const int i = tid + u * SPLICE_THREADS;
+      if (i < nx4) reinterpret_cast<float4*>(s_x)[i] = xr[u];
+    }
+#pragma unroll
+    for (int u = 0; u < UI; ++u) {
+      const int i = tid + u * SPLICE_THREADS;
+      if (i < n4) reinterpret_cast<float4*>(s_iv)[i] = ir[u];
+    }
+    if (has_ft) {
+#pragma unroll
+      for (int u = 0; u < UT; ++u) {
+        const int i = tid + u * SPLICE_THREADS;
+        if (i < p.spl_cols) {
+          s_add[i] = ar[u];
+          s_mul[i] = mr[u];
+        }
+      }
+    }
+    // whatever does not fit the first round (wide windows, long i-vectors)
+    for (int i = tid + UX * SPLICE_THREADS; i < nx4; i += SPLICE_THREADS) reinterpret_cast<float4*>(s_x)[i] = __ldg(x_src(i));
+    for (int i = tid + UI * SPLICE_THREADS; i < n4; i += SPLICE_THREADS) reinterpret_cast<float4*>(s_iv)[i] = __ldg(iv4 + i);
+    if (has_ft) {
+      for (int i = tid + UT * SPLICE_THREADS; i < p.spl_cols; i += SPLICE_THREADS) {
+        s_add[i] = __ldg(p.add_shift + i);
+        s_mul[i] = __ldg(p.rescale + i);
+      }
     }
   } else {
     for (int i = threadIdx.x; i < need_rows * p.dim; i += SPLICE_THREADS) {
@@ -84,11 +136,11 @@ __global__ void __launch_bounds__(SPLICE_THREADS) splice_transform_kernel(const 
       g = g < 0 ? 0 : (g >= p.n_total ? p.n_total - 1 : g);
       s_x[i] = __ldg(p.x + (g - p.x_row0) * p.dim + d);
     }
-  }
-  if (has_ft) {
-    for (int i = threadIdx.x; i < p.spl_cols; i += SPLICE_THREADS) {
-      s_add[i] = __ldg(p.add_shift + i);
-      s_mul[i] = __ldg(p.rescale + i);
+    if (has_ft) {
+      for (int i = threadIdx.x; i < p.spl_cols; i += SPLICE_THREADS) {
+        s_add[i] = __ldg(p.add_shift + i);
+        s_mul[i] = __ldg(p.rescale + i);
+      }
     }
   }
   __syncthreads();
@@ -211,14 +263,47 @@ __global__ void __launch_bounds__(SPLICE_THREADS) splice_transform_kernel(const 
   }
 }
 
+static size_t splice_smem_bytes(const SpliceParams& p, bool vec, int tile_f) {
+  return (static_cast<size_t>(tile_f + 2 * p.splice) * p.dim + 2 * static_cast<size_t>(p.spl_cols) +
+          (vec ? static_cast<size_t>(tile_f) * p.ivec_dim : 0)) *
+         sizeof(float);
+}
+
 template <int OUT_KIND>
-static int launch_splice(const SpliceParams& p, bool vec, cudaStream_t stream) {
+static int launch_splice(const SpliceParams& p_in, bool vec, cudaStream_t stream) {
+  SpliceParams p = p_in;
   const long long frames = p.f1 - p.f0;
-  const long long blocks = (frames + SPLICE_TILE_F - 1) / SPLICE_TILE_F;
+  // Frames per CTA: the kernel is one pass over HBM, so a partly filled last wave costs its full duration (64-frame
+  // tiles on a 65,536-frame chunk: 1024 CTAs on 740 resident slots = 1.38 waves, 31 % of the second one idle).  Pick
+  // the tile that fills whole waves best, preferring larger tiles (less halo and transform staging per frame).
+  int best_tile = SPLICE_TILE_F;
+  double best_score = -1.0;
+  for (int t = SPLICE_TILE_F; t >= 16; t -= 4) {
+    const size_t sm = splice_smem_bytes(p, vec, t);
+    if (sm > 200 * 1024) continue;
+    int occ = 0;
+    cudaError_t eo = vec ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, splice_transform_kernel<OUT_KIND, true>,
+                                                                         SPLICE_THREADS, sm)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, splice_transform_kernel<OUT_KIND, false>,
+                                                                         SPLICE_THREADS, sm);
+    if (eo != cudaSuccess || occ <= 0) {
+      cudaGetLastError();
+      continue;
+    }
+    const long long slots = static_cast<long long>(occ) * sm_count();
+    const long long tiles = (frames + t - 1) / t;
+    const long long waves = (tiles + slots - 1) / slots;
+    const double eff = static_cast<double>(tiles) / static_cast<double>(waves * slots);
+    const double score = eff * t / (t + 4.0);
+    if (score > best_score) {
+      best_score = score;
+      best_tile = t;
+    }
+  }
+  p.tile_f = best_tile;
+  const long long blocks = (frames + p.tile_f - 1) / p.tile_f;
   if (blocks > 0x7fffffffLL) return set_error(NNAM_ERR_ARG, "splice: too many frames for one launch");
-  const size_t smem = (static_cast<size_t>(SPLICE_TILE_F + 2 * p.splice) * p.dim + 2 * static_cast<size_t>(p.spl_cols) +
-                       (vec ? static_cast<size_t>(SPLICE_TILE_F) * p.ivec_dim : 0)) *
-                      sizeof(float);
+  const size_t smem = splice_smem_bytes(p, vec, p.tile_f);
   if (smem > 200 * 1024) return set_error(NNAM_ERR_UNSUPPORTED, "splice: window too large for shared memory");
   if (smem > 48 * 1024) {
     cudaError_t e;
