@@ -11,6 +11,7 @@ on finished utterances.
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -330,7 +331,7 @@ class Schedule:
     they are spread over LANES = (CTA group, stream): a group runs ``streams`` batches concurrently against one
     resident weight slice, so all streams of a group work on the same direction at a time (direction 0 first)."""
 
-    def __init__(self, steps, nb, n_dirs, max_groups, device, streams=1, solo_ratio=1.0):
+    def __init__(self, steps, nb, n_dirs, max_groups, device, streams=1, solo_ratio=1.0, row_offset=0):
         steps = np.asarray(steps, dtype=np.int64)
         n_utt = len(steps)
         self.nb, self.n_utt, self.streams = nb, n_utt, streams
@@ -344,7 +345,7 @@ class Schedule:
         bases = []
         # per packed row: sorted-utterance index and step
         row_utt, row_step = [], []
-        r = 0
+        r = int(row_offset)  # first packed row of this schedule (a MixedSchedule packs its parts one after the other)
         off = 0
         for b in range(n_batches):
             ls = s_sorted[b * nb:(b + 1) * nb]
@@ -359,7 +360,7 @@ class Schedule:
             row_step.append(tt)
             r += int(base[-1])
             off += len(base)
-        self.n_rows = r
+        self.n_rows = r - int(row_offset)
         self.n_batches = n_batches
         self.h_base = bases  # host copies of the per-batch prefix-sum tables
         self.row_sorted_utt = np.concatenate(row_utt) if row_utt else np.zeros(0, np.int64)
@@ -385,18 +386,75 @@ class Schedule:
         self.d_counters = torch.zeros(max(n_lanes, 1), dtype=torch.int32, device=device)
 
 
+class MixedSchedule:
+    """Two schedules over one packed row space, run as two concurrent cooperative launches on disjoint SM sets: the
+    longest utterances in the low-latency 32-slot kernel (one batch per CTA group; they are the critical path of a
+    layer: 785 steps x 6.5 k cycles against 10 k in the 128-slot kernel), everything else in the 128-slot
+    two-stream kernel on the remaining groups.  Exposes the attributes forward_utterances() reads from a Schedule."""
+
+    def __init__(self, steps, k_long, groups_long, nb_long, streams_long, nb_bulk, groups_bulk, streams_bulk,
+                 ratio_bulk, n_dirs, device):
+        steps = np.asarray(steps, dtype=np.int64)
+        by_len = np.argsort(-steps, kind="stable")
+        idx_a, idx_b = by_len[:k_long], by_len[k_long:]
+        sa = Schedule(steps[idx_a], nb_long, n_dirs, groups_long, device, streams_long)
+        sb = Schedule(steps[idx_b], nb_bulk, n_dirs, groups_bulk, device, streams_bulk, ratio_bulk, row_offset=sa.n_rows)
+        self.parts = [(sa, nb_long), (sb, nb_bulk)]
+        self.nb = ("mixed", int(k_long), int(groups_long))
+        self.n_utt = len(steps)
+        self.n_rows = sa.n_rows + sb.n_rows
+        self.order = np.concatenate([idx_a[sa.order], idx_b[sb.order]])
+        self.row_sorted_utt = np.concatenate([sa.row_sorted_utt, sb.row_sorted_utt + len(idx_a)])
+        self.row_step = np.concatenate([sa.row_step, sb.row_step])
+        self.streams = None
+        self._cuda_streams = None
+
+    def cuda_streams(self):
+        if self._cuda_streams is None:
+            self._cuda_streams = [torch.cuda.Stream() for _ in self.parts]
+        return self._cuda_streams
+
+
+def _mixed_candidate(plan, steps, s_sorted, nsplit, best_cost):
+    """Cost of the best long / bulk split (None if the plain schedules win or the kernels do not apply)."""
+    if os.environ.get("NNAM_RNN_MIXED", "1") == "0" or plan.cell != CELL_LSTM or nsplit != 1:
+        return None
+    try:
+        _, max_a, cyc_a, streams_a = ops.rnn_plan(plan.cell, plan.hidden, 32, nsplit)
+        _, max_b, cyc_b, streams_b = ops.rnn_plan(plan.cell, plan.hidden, 128, nsplit)
+    except NnamError:
+        return None
+    if streams_a != 1 or streams_b != 2 or max_a != max_b or len(steps) < 32 * 4:
+        return None
+    ratio = _solo_ratio(plan, 128, nsplit, cyc_b, streams_b)
+    best = None
+    forced = os.environ.get("NNAM_RNN_MIXED_GROUPS")  # tuning aid
+    for g_a in ((int(forced),) if forced else (1, 2, 3)):
+        if max_b - g_a < 1:
+            break
+        k = 32 * g_a
+        cost_a = int(s_sorted[0]) * plan.n_dirs * cyc_a  # one batch per group: the first group holds the longest one
+        _, _, crit_b = assign_lanes(s_sorted[k::128], plan.n_dirs, max_b - g_a, streams_b, ratio)
+        cost = max(cost_a, crit_b * cyc_b)
+        if best is None or cost < best[0]:
+            best = (cost, k, g_a, streams_a, max_b - g_a, streams_b, ratio)
+    if best is None or (best[0] > 0.95 * best_cost and os.environ.get("NNAM_RNN_MIXED") != "force"):
+        return None
+    return best
+
+
 def _solo_ratio(plan, nb, nsplit, busy_cycles, streams):
     if streams != 2:
         return 1.0
     return min(1.0, ops.rnn_solo_step_cycles(plan.cell, plan.hidden, nb, nsplit) / float(busy_cycles))
 
 
-def pick_schedule(plan, steps, device, nb=None):
+def pick_schedule(plan, steps, device, nb=None, allow_mixed=True):
     """Build the packed schedule; with nb=None choose the slots-per-stream (16 x 4 streams, 32 x 2, 64 x 1) that
     minimises the critical path (longest group) under the measured per-step cost.  The schedule depends only on the
     utterance lengths, so it is cached on the plan (a repeated call on the same data set re-uses it)."""
     steps = np.asarray(steps, dtype=np.int64)
-    key = (steps.tobytes(), nb, plan.n_dirs)
+    key = (steps.tobytes(), nb, plan.n_dirs, bool(allow_mixed))
     cache = plan.__dict__.setdefault("_sched_cache", {})
     hit = cache.get(key)
     if hit is not None:
@@ -420,8 +478,14 @@ def pick_schedule(plan, steps, device, nb=None):
             best = (cost, cand, max_groups, streams, ratio)
     if best is None:
         raise NnamError("no recurrent kernel configuration fits this layer size / precision")
-    _, cand, max_groups, streams, ratio = best
-    res = (Schedule(steps, cand, plan.n_dirs, max_groups, device, streams, ratio), cand)
+    mixed = _mixed_candidate(plan, steps, s_sorted, nsplit, best[0]) if (nb is None and allow_mixed) else None
+    if mixed is not None:
+        _, k, g_a, streams_a, g_b, streams_b, ratio_b = mixed
+        ms = MixedSchedule(steps, k, g_a, 32, streams_a, 128, g_b, streams_b, ratio_b, plan.n_dirs, device)
+        res = (ms, ms.nb)
+    else:
+        _, cand, max_groups, streams, ratio = best
+        res = (Schedule(steps, cand, plan.n_dirs, max_groups, device, streams, ratio), cand)
     if len(cache) >= 8:
         cache.pop(next(iter(cache)))
     cache[key] = res
@@ -466,11 +530,44 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
     return d
 
 
+def _run_layers_mixed(plan, sched, a_hi, a_lo, rows, tag, ws):
+    """run_layers for a MixedSchedule (bf16 LSTM, no carried state): per layer one projection GEMM over all rows, then
+    the two recurrence launches side by side on their own CUDA streams."""
+    H, nd = plan.hidden, plan.n_dirs
+    main = torch.cuda.current_stream()
+    side = sched.cuda_streams()
+    for l, layer in enumerate(plan.rec_layers):
+        gx = ws.get(f"{tag}.gx16", rows, nd * 4 * H, torch.bfloat16)
+        layer.upward(a_hi, a_lo, rows, "identity", OUT_BF16, out=(gx, None))
+        h_hi = ws.get(f"{tag}.h{l % 2}.hi", rows, nd * H, torch.bfloat16)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for pi, ((part, nb), st) in enumerate(zip(sched.parts, side)):
+            x_rows = part.n_lanes * 4 * nb
+            name = f"{tag}.xchg{pi}.hi"
+            fresh = ws.buf.get(name) is None or ws.buf[name].numel() < x_rows * H
+            xchg = (ws.get(name, x_rows, H, torch.bfloat16), None)
+            if fresh:
+                xchg[0].zero_()
+                ready.record(main)
+            desc = _fill_desc(plan, part, layer, gx, h_hi, None, nb, xchg=xchg)
+            with torch.cuda.stream(st):
+                st.wait_event(ready)
+                ops.rnn_seq(desc, 2.0 * part.n_rows * nd * 4 * H * H)
+                done = torch.cuda.Event()
+                done.record(st)
+            main.wait_event(done)
+        a_hi, a_lo = h_hi, None
+    return a_hi, a_lo, []
+
+
 def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_state=False, tag="rnn", ws=None):
     """All recurrent layers on packed rows; returns (h_hi, h_lo) of the last layer and the new state.
     ``ws``: workspace to use (ensembles share the first member's buffers; launches are stream-ordered)."""
     ws = ws or plan.ws
     H, nd = plan.hidden, plan.n_dirs
+    if isinstance(sched, MixedSchedule):
+        return _run_layers_mixed(plan, sched, a_hi, a_lo, rows, tag, ws)
     state_out = []
     rec_layers = plan.rec_layers
     if nb == 128 and plan.cell == CELL_GRU:  # the 128-slot GRU kernel takes gate-blocked rows
@@ -542,7 +639,7 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
             nb = len(lens)
             sched = Schedule(lens + timedelay, nb, 1, 1, device, 1)
         else:
-            sched, nb = pick_schedule(plan, lens + timedelay, device, nb)
+            sched, nb = pick_schedule(plan, lens + timedelay, device, nb, allow_mixed=len(models) == 1)
         scheds = {(plan.cell, plan.hidden, plan.n_dirs): sched}
         rows = sched.n_rows
         # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1); like the schedule

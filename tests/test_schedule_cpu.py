@@ -93,3 +93,23 @@ def test_pair_assignment_covers_every_item_once_and_costs_solo_tail():
     _, _, busy = assign_lanes([785, 100, 90], 1, 9, 2, 1.0)
     _, _, solo = assign_lanes([785, 100, 90], 1, 9, 2, 0.8)
     assert solo < busy
+
+
+def test_mixed_schedule_packs_every_frame_once():
+    """MixedSchedule (long utterances in the 32-slot kernel, the rest in the 128-slot kernel): one packed row space,
+    every (utterance, step) exactly once, part B's rows start where part A's end."""
+    from nnacousticmodeling_b200.recurrent_engine import MixedSchedule
+    rng = np.random.default_rng(11)
+    lens = rng.integers(1, 300, 500)
+    ms = MixedSchedule(lens, 64, 2, 32, 1, 128, 7, 2, 0.8, 2, torch.device("cpu"))
+    (sa, nb_a), (sb, nb_b) = ms.parts
+    assert (nb_a, nb_b) == (32, 128) and ms.n_rows == int(lens.sum()) == sa.n_rows + sb.n_rows
+    assert sorted(ms.order.tolist()) == list(range(500))
+    assert int(sa.d_row0[0]) == 0 and int(sb.d_row0[0]) == sa.n_rows
+    utt = ms.order[ms.row_sorted_utt]
+    pairs = set(zip(utt.tolist(), ms.row_step.tolist()))
+    assert len(pairs) == ms.n_rows
+    assert np.all(ms.row_step < lens[utt])
+    # the long part holds exactly the 64 longest utterances
+    assert sorted(lens[ms.order[:64]].tolist(), reverse=True) == sorted(lens.tolist(), reverse=True)[:64]
+    assert sa.n_groups <= 2 and sb.n_groups <= 7
