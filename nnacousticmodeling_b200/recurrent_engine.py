@@ -429,13 +429,15 @@ def _mixed_candidate(plan, steps, s_sorted, nsplit, best_cost):
     ratio = _solo_ratio(plan, 128, nsplit, cyc_b, streams_b)
     best = None
     forced = os.environ.get("NNAM_RNN_MIXED_GROUPS")  # tuning aid
-    for g_a in ((int(forced),) if forced else (1, 2, 3)):
+    for g_a in ((int(forced),) if forced else (1, 2, 3, 4)):
         if max_b - g_a < 1:
             break
-        k = 32 * g_a
-        cost_a = int(s_sorted[0]) * plan.n_dirs * cyc_a  # one batch per group: the first group holds the longest one
+        # one 32-slot batch per group; a bidirectional net needs a group per direction of a batch to keep the two
+        # passes over its longest utterance side by side
+        k = 32 * max(1, g_a // plan.n_dirs)
+        _, _, crit_a = assign_lanes(s_sorted[:k:32], plan.n_dirs, g_a, streams_a)
         _, _, crit_b = assign_lanes(s_sorted[k::128], plan.n_dirs, max_b - g_a, streams_b, ratio)
-        cost = max(cost_a, crit_b * cyc_b)
+        cost = max(crit_a * cyc_a, crit_b * cyc_b)
         if best is None or cost < best[0]:
             best = (cost, k, g_a, streams_a, max_b - g_a, streams_b, ratio)
     if best is None or (best[0] > 0.95 * best_cost and os.environ.get("NNAM_RNN_MIXED") != "force"):

@@ -234,3 +234,25 @@ def test_recurrent_engines_keep_inside_their_workspaces(monkeypatch, network, un
     else:
         want = O.predict(O.RecurrentNet(p, network, 2), x, off, network, 1, td, None)
     assert np.abs(got - want).max() < (1e-3 if precision == "fp32" else 5e-2)
+
+
+def test_mixed_schedule_keeps_inside_its_workspaces(monkeypatch):
+    """Two concurrent recurrence launches over one packed row space (MixedSchedule), guard bytes around every buffer."""
+    import nnacousticmodeling_b200 as nn
+    from nnacousticmodeling_b200 import recurrent_engine
+    _fresh(nn, monkeypatch)
+    monkeypatch.setenv("NNAM_RNN_MIXED", "force")
+    rng = np.random.default_rng(21)
+    lens = np.concatenate([rng.integers(90, 130, size=40), rng.integers(1, 50, size=300)])
+    off = _offsets(lens)
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    p = O.init_recurrent(np.random.default_rng(6), "lstm", 40, 512, 2, 39)
+    m = nn.get_nn("lstm", 2, [512], 39, nn.F.relu, [5])
+    m.load_params(p)
+    m.precision = "bf16"
+    got = nn.predict(m, x, off, 39, "lstm", 0, 1, 2, None, progress=False)
+    plan = next(iter(m._plans.values()))
+    assert any(isinstance(v[0], recurrent_engine.MixedSchedule) for v in plan._sched_cache.values())
+    _check_plans(m)
+    want = O.predict(O.RecurrentNet(p, "lstm", 2), x, off, "lstm", 1, 2, None)
+    assert np.abs(got - want).max() < 5e-2
