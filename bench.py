@@ -227,8 +227,8 @@ def run_ours(args):
     from nnacousticmodeling_b200 import engine, ops
 
     from nnacousticmodeling_b200 import dist_util
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner out of stdout: rank 0 prints ONE JSON line
+    # keep NCCL's version banner (printed at VERSION and WARN level) out of stdout: rank 0 prints ONE JSON line there
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     world, rank, local = dist_util.env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)

@@ -703,13 +703,15 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   // family variant takes gate-blocked rows without padding: 32 * n_gates rows per CTA (recurrent_wide_gru.cu)
   static const RnnCfg kWideCfg1 = {128, 128, 1, 0, 1, 16};
   static const RnnCfg kWideCfg2 = {128, 128, 1, 0, 2, 8};
+  static const RnnCfg kWideCfg3 = {128, 128, 1, 0, 3, 4};
   static const RnnCfg kWideGru3 = {96, 128, 1, 0, 2, 8};
   static const RnnCfg kWideGru2 = {64, 128, 1, 0, 2, 8};
   const bool wide = d->batch == 128;
   const bool wide_gru = wide && d->cell == NNAM_CELL_GRU;
   const int gru_gates = (d->flags & 1) ? 3 : 2;
   const RnnCfg& kWideCfg = wide_gru ? (gru_gates == 3 ? kWideGru3 : kWideGru2)
-                                    : (rnn_wide_streams() == 2 ? kWideCfg2 : kWideCfg1);
+                                    : (rnn_wide_streams() == 3 ? kWideCfg3
+                                                               : (rnn_wide_streams() == 2 ? kWideCfg2 : kWideCfg1));
   const int gate_rows = wide_gru ? gru_gates * H : 4 * H;
   if (wide && (d->h0_hi || d->c0 || d->c_out ||
                !(wide_gru ? rnn_wide_gru_applies(H, d->nsplit, gru_gates)
@@ -836,7 +838,7 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
     *group_ctas = 4 * hidden / 128;
     *max_groups = sm_count() / *group_ctas;
     // measured, profiles/r01_k3_phase_cycles.md: per step of ONE stream while all streams of the group are busy
-    if (step_cycles) *step_cycles = rnn_wide_streams() == 2 ? 13800 : 10300;
+    if (step_cycles) *step_cycles = rnn_wide_streams() == 3 ? 15000 : (rnn_wide_streams() == 2 ? 13800 : 10300);
     if (streams) *streams = rnn_wide_streams();
     return NNAM_OK;
   }
@@ -868,7 +870,7 @@ int rnn_solo_step_cycles(int cell, int hidden, int batch, int nsplit, int* cycle
   int g = 0, m = 0, c = 0, s = 0;
   const int rc = rnn_plan(cell, hidden, batch, nsplit, &g, &m, &c, &s);
   if (rc) return rc;
-  if (batch == 128 && s == 2) c = cell == NNAM_CELL_GRU ? 17700 : 11500;  // measured: 10.7 k with one group running, profiles/r01_k3_phase_cycles.md
+  if (batch == 128 && s >= 2) c = cell == NNAM_CELL_GRU ? 17700 : 11500;  // measured: 10.7 k with one group running, profiles/r01_k3_phase_cycles.md
   *cycles = c;
   return NNAM_OK;
 }

@@ -293,13 +293,15 @@ constexpr int W2_THREADS = W2_STREAMS * W2_TPS;
 constexpr int W2_STAGES = 5;
 constexpr int W2_BASE_SMEM = 1024;
 
-__device__ __forceinline__ int stream_of_thread() { return static_cast<int>(threadIdx.x) / W2_TPS; }
+template <int TPS>
 __device__ __forceinline__ void w2_bar_sync(int stream) {
-  asm volatile("bar.sync %0, %1;" ::"r"(1 + stream), "n"(W2_TPS) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + stream), "n"(TPS) : "memory");
 }
 
-template <int KBT>
-__global__ void __launch_bounds__(W2_THREADS, 1)
+// S streams of WPS warps each: (2, 8) -- a thread owns 64 columns (16 units) -- or (3, 4) -- a thread owns all 128
+// columns (32 units) of its utterance, processed in four chunks of 32; three chains of latencies overlap instead of two.
+template <int KBT, int S, int WPS>
+__global__ void __launch_bounds__(S * WPS * 32, 1)
     lstm_seq_wide2_kernel(const __grid_constant__ RnnTmaps tmaps, const RnnParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int M_ROWS = 128;
@@ -318,40 +320,44 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
   uint8_t* tail = a_s + W2_STAGES * WIDE_A_STAGE;
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(tail);
   uint64_t* bar_mma = bar_w + 1;                   // [2] a stream's accumulator is complete
-  uint64_t* bar_grant = bar_mma + W2_STREAMS;      // [2] producer -> MMA issuer: "your k-blocks start at s_f0[stream]"
+  constexpr int TPS = WPS * 32;            // threads per stream
+  constexpr int COLS = 128 / (WPS / 4);    // accumulator columns per thread
+  constexpr int CHUNKS = COLS / 32;
+  constexpr int BASE_SMEM = S == 2 ? W2_BASE_SMEM : 768;
+  uint64_t* bar_grant = bar_mma + S;      // [2] producer -> MMA issuer: "your k-blocks start at s_f0[stream]"
   // [2][W2_STAGES] "slot filled", one set PER STREAM although the slots are shared: a parity wait on a barrier that
   // still carries the other stream's previous fill would see "the phase before" and pass at once.  With its own set
   // a stream's issuer only ever waits for its own fills, in order.  The "slot free" barriers are shared.
-  uint64_t* full_bar_all = bar_grant + W2_STREAMS;
-  uint64_t* full_bar = full_bar_all + stream_of_thread() * W2_STAGES;
-  uint64_t* empty_bar = full_bar_all + W2_STREAMS * W2_STAGES;  // [W2_STAGES]
+  uint64_t* full_bar_all = bar_grant + S;
+  uint64_t* full_bar = full_bar_all + (static_cast<int>(threadIdx.x) / TPS) * W2_STAGES;
+  uint64_t* empty_bar = full_bar_all + S * W2_STAGES;  // [W2_STAGES]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(empty_bar + W2_STAGES);
   unsigned int* ring_lock = tmem_slot + 2;
   volatile unsigned int* ring_fill = ring_lock + 1;  // k-blocks pushed through the ring so far (by either stream)
-  volatile unsigned int* s_f0 = ring_lock + 2;       // [2] ring position of the first k-block of a stream's current step
-  int* s_len_all = reinterpret_cast<int*>(ring_lock + 6);    // [2][NB]
-  int* s_base_all = s_len_all + W2_STREAMS * NB;             // [2][W2_BASE_SMEM + 1]
+  volatile unsigned int* s_f0 = ring_lock + 2;       // [S] ring position of the first k-block of a stream's current step
+  int* s_len_all = reinterpret_cast<int*>(ring_lock + 6);    // [S][NB]
+  int* s_base_all = s_len_all + S * NB;                      // [S][BASE_SMEM + 1]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int stream = warp >> 3;
-  const int sw = warp & 7;             // warp inside the stream
-  const int stid = tid & (W2_TPS - 1);
+  const int stream = warp / WPS;
+  const int sw = warp - stream * WPS;  // warp inside the stream
+  const int stid = tid - stream * TPS;
   const int quarter = sw & 3;          // == warp & 3: the TMEM lane quarter this warp may read
-  const int sub = sw >> 2;             // which 64 columns (16 units) of the CTA's 128
+  const int sub = sw >> 2;             // which COLS columns of the CTA's 128
   const int u = quarter * 32 + lane;   // my utterance slot == my TMEM lane
-  constexpr int TMEM_COLS = W2_STREAMS * 128;
+  constexpr int TMEM_COLS = S == 2 ? 256 : 512;
   int* s_len = s_len_all + stream * NB;
-  int* s_base = s_base_all + stream * (W2_BASE_SMEM + 1);
+  int* s_base = s_base_all + stream * (BASE_SMEM + 1);
 
   if (tid == 0) {
     mbar_init(bar_w, 1);
-    for (int i = 0; i < W2_STREAMS; ++i) {
+    for (int i = 0; i < S; ++i) {
       mbar_init(&bar_mma[i], 1);
       mbar_init(&bar_grant[i], 1);
     }
-    for (int i = 0; i < W2_STREAMS * W2_STAGES; ++i) mbar_init(&full_bar_all[i], 1);
+    for (int i = 0; i < S * W2_STAGES; ++i) mbar_init(&full_bar_all[i], 1);
     for (int i = 0; i < W2_STAGES; ++i) mbar_init(&empty_bar[i], 1);
     *ring_lock = 0u;
     *ring_fill = 0u;
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(stream * 128);
-  const uint32_t tmem_mine = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * 64);
+  const uint32_t tmem_mine = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * COLS);
   const uint32_t idesc = make_idesc_bf16_f32(NB, M_ROWS);
 
   const bool prof_on = p.prof != nullptr && tid == 64;
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
   unsigned int steps_done = 0;
   uint32_t w_phase = 0, mma_phase = 0, grant_phase = 0;
   uint32_t full_parity = 0;  // bit st: parity of this stream's next fill of ring slot st
-  const int lane_id_ = group * W2_STREAMS + stream;  // (group, stream) = one lane of the schedule
+  const int lane_id_ = group * S + stream;  // (group, stream) = one lane of the schedule
   unsigned int* counter = p.counters + lane_id_;
   int it = p.group_item_start[lane_id_];
   const int it_end = p.group_item_start[lane_id_ + 1];
@@ -401,25 +407,25 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
       const int nutt = p.batch_nutt[b];
       const int* base = p.base + p.batch_base_off[b];
       const int* len = p.utt_len + b * NB;
-      const __nv_bfloat16* gx = reinterpret_cast<const __nv_bfloat16*>(p.gx[d]) + rank * M_ROWS + sub * 64;
+      const __nv_bfloat16* gx = reinterpret_cast<const __nv_bfloat16*>(p.gx[d]) + rank * M_ROWS + sub * COLS;
       // exchange slots are reused by the next item: wait until the whole group has finished the previous one
       if (steps_done > 0 && sw == 0) {
         const unsigned int target = steps_done * static_cast<unsigned int>(p.group_ctas);
         while (ld_acquire_gpu(counter) < target) {
         }
       }
-      w2_bar_sync(stream);
+      w2_bar_sync<TPS>(stream);
       if (stid < NB) s_len[stid] = stid < nutt ? len[stid] : 0;
-      const bool base_in_smem = T <= W2_BASE_SMEM;
+      const bool base_in_smem = T <= BASE_SMEM;
       if (base_in_smem)
-        for (int i = stid; i <= T; i += W2_TPS) s_base[i] = __ldg(base + i);
-      w2_bar_sync(stream);
+        for (int i = stid; i <= T; i += TPS) s_base[i] = __ldg(base + i);
+      w2_bar_sync<TPS>(stream);
       const int* bp = base_in_smem ? s_base : base;
       const int my_len = s_len[u];
 
-      float c_reg[16];
+      float c_reg[COLS / 4];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) c_reg[j] = 0.0f;
+      for (int j = 0; j < COLS / 4; ++j) c_reg[j] = 0.0f;
 
       for (int s = 0; s < T; ++s) {
         PROF_START();
@@ -430,12 +436,12 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
         // 64 bf16 gate pre-activations of utterance u at this step.  Every lane reads its own row, so the four loads
         // cost ~1-2 k cycles of LSU issue per warp: the six plain warps issue them now (they land during the exchange);
         // the producer and the MMA issuer first start the h stream, which is the critical path of the step.
-        uint32_t gxr[4][8] = {};
+        uint32_t gxr[COLS / 16][8] = {};
         auto load_gx = [&]() {
           if (active) {
             const __nv_bfloat16* src = gx + my_row * p.gx_ld;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) ldg_nc_256(src + 16 * j, gxr[j]);
+            for (int j = 0; j < COLS / 16; ++j) ldg_nc_256(src + 16 * j, gxr[j]);
           }
         };
         if (s == 0 || sw >= 2) load_gx();
@@ -510,11 +516,11 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
           PROF_MARK(2);
         }
 
-        // ---- gates and cell update for my 16 units in two halves (chainer F.lstm); h leaves as one 256-bit store per
-        //      destination (every lane writes its own row: the LSU cost is per instruction, not per byte)
-        uint32_t hp[8];
+        // ---- gates and cell update for my units in chunks of 8 (chainer F.lstm); h leaves as one 256-bit store per
+        //      16 units and destination (every lane writes its own row: the LSU cost is per instruction, not per byte)
+        uint32_t hp[CHUNKS * 4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < CHUNKS; ++half) {
           float acc[32];
           if (s > 0) {
             uint32_t r[32];
@@ -548,15 +554,21 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
           }
         }
         if (active) {
-          const int col = rank * UNITS + sub * 16;
+          const int col = rank * UNITS + sub * (COLS / 4);
           const long long xoff = (static_cast<long long>(lane_id_ * 4 + (s & 1)) * NB + u) * H + col;
-          stg_256(p.xchg_hi + xoff, hp);
-          stg_256(p.h_hi + my_row * p.h_ld + h_col0 + col, hp);
+#pragma unroll
+          for (int q = 0; q < CHUNKS / 2; ++q) {
+            uint32_t v8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v8[j] = hp[8 * q + j];
+            stg_256(p.xchg_hi + xoff + 16 * q, v8);
+            stg_256(p.h_hi + my_row * p.h_ld + h_col0 + col + 16 * q, v8);
+          }
         }
         tc_fence_before();
         PROF_MARK(3);
         // ---- publish: the stream barrier orders every thread's stores before one thread's release
-        w2_bar_sync(stream);
+        w2_bar_sync<TPS>(stream);
         if (stid == 0) red_release_gpu_add(counter, 1u);
         ++steps_done;
         PROF_MARK(4);
@@ -578,18 +590,22 @@ __global__ void __launch_bounds__(W2_THREADS, 1)
   }
 }
 
-size_t rnn_wide2_smem_bytes(int hidden) {
+size_t rnn_wide2_smem_bytes(int hidden, int streams) {
   const size_t kb = hidden / 64;
-  return kb * 128 * 128 + static_cast<size_t>(W2_STAGES) * WIDE_A_STAGE + 8 * (1 + 2 * W2_STREAMS + (W2_STREAMS + 1) * W2_STAGES) +
-         8 * 4 + W2_STREAMS * (WIDE_NB + W2_BASE_SMEM + 1) * 4;
+  const size_t base_smem = streams == 2 ? W2_BASE_SMEM : 768;
+  return kb * 128 * 128 + static_cast<size_t>(W2_STAGES) * WIDE_A_STAGE + 8 * (1 + 2 * streams + (streams + 1) * W2_STAGES) +
+         8 * 4 + streams * (WIDE_NB + base_smem + 1) * 4;
 }
 
-// streams per CTA group of the 128-slot kernel: 2 (default) or 1 (NNAM_RNN_WIDE_STREAMS=1, the single-batch kernel)
+// streams per CTA group of the 128-slot LSTM kernel: 2 (default); NNAM_RNN_WIDE_STREAMS=1 selects the single-batch
+// kernel, =3 three streams of four warps (27 % more utterance-steps per cycle when every stream is busy, but a stream's
+// own step gets longer -- 14.7 k cycles busy, 11.2 k alone -- and the BASELINE sets are bound by their longest batch:
+// cfg3t 5.2 ms per layer against 4.5 ms with two streams; profiles/r01_k3_phase_cycles.md)
 int rnn_wide_streams() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("NNAM_RNN_WIDE_STREAMS");
-    v = (e && atoi(e) == 1) ? 1 : 2;
+    v = (e && atoi(e) >= 1 && atoi(e) <= 3) ? atoi(e) : 2;
   }
   return v;
 }
@@ -604,7 +620,8 @@ size_t rnn_wide_smem_bytes(int hidden) {
 bool rnn_wide_applies(int cell, int hidden, int batch, int nsplit) {
   if (cell != NNAM_CELL_LSTM || nsplit != 1 || batch != WIDE_NB) return false;
   if (hidden % 64 || (4 * hidden) % 128) return false;
-  if ((rnn_wide_streams() == 2 ? rnn_wide2_smem_bytes(hidden) : rnn_wide_smem_bytes(hidden)) > 227 * 1024) return false;
+  if ((rnn_wide_streams() >= 2 ? rnn_wide2_smem_bytes(hidden, rnn_wide_streams()) : rnn_wide_smem_bytes(hidden)) > 227 * 1024)
+    return false;
   return sm_count() >= 4 * hidden / 128;
 }
 
@@ -619,23 +636,28 @@ static int launch_wide(const RnnTmaps& tm, const RnnParams& p, int grid, size_t 
   return NNAM_OK;
 }
 
-template <int KBT>
+template <int KBT, int S, int WPS>
 static int launch_wide2(const RnnTmaps& tm, const RnnParams& p, int grid, size_t smem, cudaStream_t stream) {
-  auto kern = lstm_seq_wide2_kernel<KBT>;
+  auto kern = lstm_seq_wide2_kernel<KBT, S, WPS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaFuncSetAttribute(wide2)");
   void* args[] = {const_cast<RnnTmaps*>(&tm), const_cast<RnnParams*>(&p)};
-  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(W2_THREADS), args, smem, stream);
+  e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(S * WPS * 32), args, smem, stream);
   if (e != cudaSuccess) return set_cuda_error(e, "rnn: cudaLaunchCooperativeKernel(wide2)");
   return NNAM_OK;
 }
 
 int rnn_wide_launch(const RnnTmaps& tm, const RnnParams& p, int hidden, cudaStream_t stream) {
   const int grid = p.n_groups * p.group_ctas;
+  if (rnn_wide_streams() == 3) {
+    const size_t smem3 = rnn_wide2_smem_bytes(hidden, 3);
+    if (hidden == 512) return launch_wide2<8, 3, 4>(tm, p, grid, smem3, stream);
+    return launch_wide2<0, 3, 4>(tm, p, grid, smem3, stream);
+  }
   if (rnn_wide_streams() == 2) {
-    const size_t smem2 = rnn_wide2_smem_bytes(hidden);
-    if (hidden == 512) return launch_wide2<8>(tm, p, grid, smem2, stream);
-    return launch_wide2<0>(tm, p, grid, smem2, stream);
+    const size_t smem2 = rnn_wide2_smem_bytes(hidden, 2);
+    if (hidden == 512) return launch_wide2<8, 2, 8>(tm, p, grid, smem2, stream);
+    return launch_wide2<0, 2, 8>(tm, p, grid, smem2, stream);
   }
   const size_t smem = rnn_wide_smem_bytes(hidden);
   if (hidden == 512) return launch_wide<8>(tm, p, grid, smem, stream);

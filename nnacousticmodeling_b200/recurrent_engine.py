@@ -182,8 +182,8 @@ def assign_lanes(bsteps, n_dirs, max_groups, streams, solo_ratio=1.0):
     the longest utterance, 785).  Several streams per group: per direction LPT over the lanes; the critical path
     accounts for a group switching direction only when all of its streams are done with the current one.  Two streams
     per group (the 128-slot kernel): see :func:`_assign_pairs`."""
-    if streams == 2:
-        return _assign_pairs(bsteps, n_dirs, max_groups, solo_ratio)
+    if streams in (2, 3):
+        return _assign_pairs(bsteps, n_dirs, max_groups, solo_ratio, streams)
     n_batches = len(bsteps)
     bsteps = [int(t) for t in bsteps]
     n_groups = max(1, min(max_groups, (n_batches * (n_dirs if streams == 1 else 1) + streams - 1) // streams))
@@ -238,23 +238,25 @@ def assign_lanes(bsteps, n_dirs, max_groups, streams, solo_ratio=1.0):
     return per_lane, n_groups, (int(per_group.max()) if n_batches else 0)
 
 
-def _assign_pairs(bsteps, n_dirs, max_groups, solo_ratio):
-    """Lane assignment for groups of two streams.  A step of a stream costs ``c_busy`` cycles while its sibling is
+def _assign_pairs(bsteps, n_dirs, max_groups, solo_ratio, streams=2):
+    """Lane assignment for groups of two (or three) streams.  A step of a stream costs ``c_busy`` cycles while its sibling is
     busy and ``c_solo = solo_ratio * c_busy`` once the sibling has run out of work, so (in units of busy steps) a
-    group needs  solo_ratio * longer lane + (1 - solo_ratio) * shorter lane  per direction, and both streams switch
-    direction together.  Greedy longest-first onto the lane that leaves its group cheapest, then moves / swaps out of
+    group needs  solo_ratio * longest lane + (1 - solo_ratio) * mean of the other lanes  per direction, and all streams
+    switch direction together.  Greedy longest-first onto the lane that leaves its group cheapest, then moves / swaps out of
     the most expensive group while that lowers the maximum.  Returns (items per lane, groups, critical path in busy
     steps)."""
     n_batches = len(bsteps)
     bsteps = [int(t) for t in bsteps]
     n_groups = max(1, min(max_groups, n_batches))
     r = float(solo_ratio)
-    load = np.zeros((n_groups, 2, n_dirs), np.float64)
-    lanes = [[[] for _ in range(2)] for _ in range(n_groups)]
+    S = int(streams)
+    load = np.zeros((n_groups, S, n_dirs), np.float64)
+    lanes = [[[] for _ in range(S)] for _ in range(n_groups)]
 
     def gcost(g):
         a = load[g]
-        return float((r * a.max(axis=0) + (1.0 - r) * a.min(axis=0)).sum())
+        top = a.max(axis=0)
+        return float((r * top + (1.0 - r) * (a.sum(axis=0) - top) / (S - 1)).sum())
 
     def gcost_with(g, s_, d, delta):
         load[g, s_, d] += delta
@@ -266,7 +268,7 @@ def _assign_pairs(bsteps, n_dirs, max_groups, solo_ratio):
     for t, b, d in items:
         best = None
         for g in range(n_groups):
-            for s_ in range(2):
+            for s_ in range(S):
                 c = gcost_with(g, s_, d, t)
                 if best is None or c < best[0] - 1e-9:
                     best = (c, g, s_)
@@ -279,12 +281,12 @@ def _assign_pairs(bsteps, n_dirs, max_groups, solo_ratio):
     for _ in range(400):
         gw = int(np.argmax(cost))
         done = True
-        for sw in range(2):
+        for sw in range(S):
             for i, (t, b, d) in enumerate(lanes[gw][sw]):
                 for g in range(n_groups):
                     if g == gw:
                         continue
-                    for s_ in range(2):
+                    for s_ in range(S):
                         # move
                         load[gw, sw, d] -= t
                         load[g, s_, d] += t
@@ -318,9 +320,9 @@ def _assign_pairs(bsteps, n_dirs, max_groups, solo_ratio):
                 break
         if done:
             break
-    used = max((g + 1 for g in range(n_groups) if lanes[g][0] or lanes[g][1]), default=1)
+    used = max((g + 1 for g in range(n_groups) if any(lanes[g])), default=1)
     per_lane = [sorted(((b, d) for _, b, d in lanes[g][s_]), key=lambda t: (t[1], -bsteps[t[0]]))
-                for g in range(used) for s_ in range(2)]
+                for g in range(used) for s_ in range(S)]
     return per_lane, used, (int(np.ceil(max(cost))) if n_batches else 0)
 
 
@@ -424,7 +426,7 @@ def _mixed_candidate(plan, steps, s_sorted, nsplit, best_cost):
         _, max_b, cyc_b, streams_b = ops.rnn_plan(plan.cell, plan.hidden, 128, nsplit)
     except NnamError:
         return None
-    if streams_a != 1 or streams_b != 2 or max_a != max_b or len(steps) < 32 * 4:
+    if streams_a != 1 or streams_b not in (2, 3) or max_a != max_b or len(steps) < 32 * 4:
         return None
     ratio = _solo_ratio(plan, 128, nsplit, cyc_b, streams_b)
     best = None
@@ -446,7 +448,7 @@ def _mixed_candidate(plan, steps, s_sorted, nsplit, best_cost):
 
 
 def _solo_ratio(plan, nb, nsplit, busy_cycles, streams):
-    if streams != 2:
+    if streams not in (2, 3) or nb != 128:
         return 1.0
     return min(1.0, ops.rnn_solo_step_cycles(plan.cell, plan.hidden, nb, nsplit) / float(busy_cycles))
 
