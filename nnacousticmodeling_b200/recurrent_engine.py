@@ -402,7 +402,7 @@ class MixedSchedule:
         sa = Schedule(steps[idx_a], nb_long, n_dirs, groups_long, device, streams_long)
         sb = Schedule(steps[idx_b], nb_bulk, n_dirs, groups_bulk, device, streams_bulk, ratio_bulk, row_offset=sa.n_rows)
         self.parts = [(sa, nb_long), (sb, nb_bulk)]
-        self.nb = ("mixed", int(k_long), int(groups_long))
+        self.nb = ("mixed", int(k_long), int(groups_long), int(nb_long))
         self.n_utt = len(steps)
         self.n_rows = sa.n_rows + sb.n_rows
         self.order = np.concatenate([idx_a[sa.order], idx_b[sb.order]])
@@ -418,30 +418,40 @@ class MixedSchedule:
 
 
 def _mixed_candidate(plan, steps, s_sorted, nsplit, best_cost):
-    """Cost of the best long / bulk split (None if the plain schedules win or the kernels do not apply)."""
+    """Cost of the best long / bulk split (None if the plain schedules win or the kernels do not apply):
+    (cost, utterances in the long part, its groups, its slots per batch, its streams, bulk groups, bulk streams,
+    bulk solo ratio)."""
     if os.environ.get("NNAM_RNN_MIXED", "1") == "0" or plan.cell != CELL_LSTM or nsplit != 1:
         return None
     try:
-        _, max_a, cyc_a, streams_a = ops.rnn_plan(plan.cell, plan.hidden, 32, nsplit)
         _, max_b, cyc_b, streams_b = ops.rnn_plan(plan.cell, plan.hidden, 128, nsplit)
     except NnamError:
         return None
-    if streams_a != 1 or streams_b not in (2, 3) or max_a != max_b or len(steps) < 32 * 4:
+    if streams_b not in (2, 3) or len(steps) < 32 * 4:
         return None
     ratio = _solo_ratio(plan, 128, nsplit, cyc_b, streams_b)
     best = None
     forced = os.environ.get("NNAM_RNN_MIXED_GROUPS")  # tuning aid
-    for g_a in ((int(forced),) if forced else (1, 2, 3, 4)):
-        if max_b - g_a < 1:
-            break
-        # one 32-slot batch per group; a bidirectional net needs a group per direction of a batch to keep the two
-        # passes over its longest utterance side by side
-        k = 32 * max(1, g_a // plan.n_dirs)
-        _, _, crit_a = assign_lanes(s_sorted[:k:32], plan.n_dirs, g_a, streams_a)
-        _, _, crit_b = assign_lanes(s_sorted[k::128], plan.n_dirs, max_b - g_a, streams_b, ratio)
-        cost = max(crit_a * cyc_a, crit_b * cyc_b)
-        if best is None or cost < best[0]:
-            best = (cost, k, g_a, streams_a, max_b - g_a, streams_b, ratio)
+    for nb_a in (32, 64):
+        try:
+            _, max_a, cyc_a, streams_a = ops.rnn_plan(plan.cell, plan.hidden, nb_a, nsplit)
+        except NnamError:
+            continue
+        if streams_a != 1 or max_a != max_b:
+            continue
+        for g_a in ((int(forced),) if forced else (1, 2, 3, 4)):
+            if max_b - g_a < 1:
+                break
+            # one batch per group; a bidirectional net needs a group per direction of a batch to keep the two passes
+            # over its longest utterance side by side
+            k = nb_a * max(1, g_a // plan.n_dirs)
+            if len(steps) - k < 128:
+                continue
+            _, _, crit_a = assign_lanes(s_sorted[:k:nb_a], plan.n_dirs, g_a, streams_a)
+            _, _, crit_b = assign_lanes(s_sorted[k::128], plan.n_dirs, max_b - g_a, streams_b, ratio)
+            cost = max(crit_a * cyc_a, crit_b * cyc_b)
+            if best is None or cost < best[0]:
+                best = (cost, k, g_a, nb_a, streams_a, max_b - g_a, streams_b, ratio)
     if best is None or (best[0] > 0.95 * best_cost and os.environ.get("NNAM_RNN_MIXED") != "force"):
         return None
     return best
@@ -484,8 +494,8 @@ def pick_schedule(plan, steps, device, nb=None, allow_mixed=True):
         raise NnamError("no recurrent kernel configuration fits this layer size / precision")
     mixed = _mixed_candidate(plan, steps, s_sorted, nsplit, best[0]) if (nb is None and allow_mixed) else None
     if mixed is not None:
-        _, k, g_a, streams_a, g_b, streams_b, ratio_b = mixed
-        ms = MixedSchedule(steps, k, g_a, 32, streams_a, 128, g_b, streams_b, ratio_b, plan.n_dirs, device)
+        _, k, g_a, nb_a, streams_a, g_b, streams_b, ratio_b = mixed
+        ms = MixedSchedule(steps, k, g_a, nb_a, streams_a, 128, g_b, streams_b, ratio_b, plan.n_dirs, device)
         res = (ms, ms.nb)
     else:
         _, cand, max_groups, streams, ratio = best

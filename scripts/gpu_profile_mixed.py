@@ -32,6 +32,7 @@ R.ops.rnn_seq = timed
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record(); R.forward_utterances(m, xd, off, out, 0, len(off) - 1, timedelay=5, device=0); e.record()
 torch.cuda.synchronize()
-print(f"n_utt={n_utt} long groups={g_a}: pass {s.elapsed_time(e):.2f} ms")
+plan = next(iter(m._plans.values()))
+print(f"n_utt={n_utt} long groups={g_a}: pass {s.elapsed_time(e):.2f} ms, schedule {[v[1] for v in plan._sched_cache.values()]}")
 for b, g, a, z in marks:
     print(f"   K3 launch: {b:3d} slots x {g} groups: {a.elapsed_time(z):.2f} ms")
