@@ -421,7 +421,7 @@ def _mixed_candidate(plan, steps, s_sorted, nsplit, best_cost):
     """Cost of the best long / bulk split (None if the plain schedules win or the kernels do not apply):
     (cost, utterances in the long part, its groups, its slots per batch, its streams, bulk groups, bulk streams,
     bulk solo ratio)."""
-    if os.environ.get("NNAM_RNN_MIXED", "1") == "0" or plan.cell != CELL_LSTM or nsplit != 1:
+    if os.environ.get("NNAM_RNN_MIXED", "1") == "0" or plan.cell not in (CELL_LSTM, CELL_GRU) or nsplit != 1:
         return None
     try:
         _, max_b, cyc_b, streams_b = ops.rnn_plan(plan.cell, plan.hidden, 128, nsplit)
@@ -544,16 +544,37 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
     return d
 
 
-def _run_layers_mixed(plan, sched, a_hi, a_lo, rows, tag, ws):
-    """run_layers for a MixedSchedule (bf16 LSTM, no carried state): per layer one projection GEMM over all rows, then
-    the two recurrence launches side by side on their own CUDA streams."""
+def _run_layers_mixed(model, plan, sched, a_hi, a_lo, rows, tag, ws):
+    """run_layers for a MixedSchedule (bf16 mode, no carried state): per layer the input projection over all rows, then
+    the two recurrence launches side by side on their own CUDA streams.  LSTM: both kernels read the same projection.
+    GRU family: the 128-slot kernel takes gate-blocked columns, so each part gets its own projection GEMM over its own
+    row range."""
     H, nd = plan.hidden, plan.n_dirs
     main = torch.cuda.current_stream()
     side = sched.cuda_streams()
-    for l, layer in enumerate(plan.rec_layers):
-        gx = ws.get(f"{tag}.gx16", rows, nd * 4 * H, torch.bfloat16)
-        layer.upward(a_hi, a_lo, rows, "identity", OUT_BF16, out=(gx, None))
+    n_mats = 4 if plan.cell == CELL_LSTM else (3 if plan.gru_flags & 1 else 2)
+    row_lo = 0
+    ranges = []
+    for part, _ in sched.parts:
+        ranges.append((row_lo, row_lo + part.n_rows))
+        row_lo += part.n_rows
+    for l in range(len(plan.rec_layers)):
         h_hi = ws.get(f"{tag}.h{l % 2}.hi", rows, nd * H, torch.bfloat16)
+        part_layers, part_gx = [], []
+        for pi, (part, nb) in enumerate(sched.parts):
+            layer = (gru_wide_layers(plan, model) if (plan.cell == CELL_GRU and nb == 128) else plan.rec_layers)[l]
+            part_layers.append(layer)
+            if pi > 0 and layer is part_layers[0]:
+                part_gx.append(part_gx[0])  # same weights, same layout: one GEMM over all rows (below)
+                continue
+            gate_cols = getattr(layer, "gate_cols", 4 * H)
+            shared = all(((gru_wide_layers(plan, model) if (plan.cell == CELL_GRU and nb2 == 128)
+                           else plan.rec_layers)[l]) is layer for _, nb2 in sched.parts)
+            gx = ws.get(f"{tag}.gx16" if shared else f"{tag}.gx16.p{pi}", rows, nd * gate_cols, torch.bfloat16)
+            r0, r1 = (0, rows) if shared else ranges[pi]
+            if r1 > r0:
+                layer.upward(a_hi[r0:r1], None, r1 - r0, "identity", OUT_BF16, out=(gx[r0:r1], None))
+            part_gx.append(gx)
         ready = torch.cuda.Event()
         ready.record(main)
         for pi, ((part, nb), st) in enumerate(zip(sched.parts, side)):
@@ -564,10 +585,10 @@ def _run_layers_mixed(plan, sched, a_hi, a_lo, rows, tag, ws):
             if fresh:
                 xchg[0].zero_()
                 ready.record(main)
-            desc = _fill_desc(plan, part, layer, gx, h_hi, None, nb, xchg=xchg)
+            desc = _fill_desc(plan, part, part_layers[pi], part_gx[pi], h_hi, None, nb, xchg=xchg)
             with torch.cuda.stream(st):
                 st.wait_event(ready)
-                ops.rnn_seq(desc, 2.0 * part.n_rows * nd * 4 * H * H)
+                ops.rnn_seq(desc, 2.0 * part.n_rows * nd * n_mats * H * H)
                 done = torch.cuda.Event()
                 done.record(st)
             main.wait_event(done)
@@ -581,7 +602,7 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
     ws = ws or plan.ws
     H, nd = plan.hidden, plan.n_dirs
     if isinstance(sched, MixedSchedule):
-        return _run_layers_mixed(plan, sched, a_hi, a_lo, rows, tag, ws)
+        return _run_layers_mixed(model, plan, sched, a_hi, a_lo, rows, tag, ws)
     state_out = []
     rec_layers = plan.rec_layers
     if nb == 128 and plan.cell == CELL_GRU:  # the 128-slot GRU kernel takes gate-blocked rows

@@ -1,13 +1,16 @@
 #!/usr/bin/env python3
 """Timing of the two concurrent recurrence launches of a MixedSchedule (cfg3 geometry).
-usage: gpu_profile_mixed.py [n_utt] [long groups: 0 = plain schedule, 1-3]"""
+usage: gpu_profile_mixed.py [n_utt] [long groups: 0 = plain schedule, -1 = cost model, 1-4] [lstm|gru|blstm|bgru]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 n_utt = int(sys.argv[1]) if len(sys.argv) > 1 else 3696
 g_a = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+net = sys.argv[3] if len(sys.argv) > 3 else "lstm"
 if g_a == 0:
     os.environ["NNAM_RNN_MIXED"] = "0"
+elif g_a < 0:
+    pass  # the cost model decides
 else:
     os.environ["NNAM_RNN_MIXED"] = "force"
     os.environ["NNAM_RNN_MIXED_GROUPS"] = str(g_a)
@@ -15,12 +18,14 @@ import nnacousticmodeling_b200 as nn
 from nnacousticmodeling_b200 import recurrent_engine as R, ops
 from oracle import nnam_oracle as O
 x, off, _ = O.synth_set(1234, n_utt)
-p = O.init_recurrent(np.random.default_rng(1), "lstm", 40, 512, 4, 1909)
-m = nn.get_nn("lstm", 4, [512], 1909, nn.F.relu, [5]); m.load_params(p); m.precision = "bf16"
+bid = net in ("blstm", "bgru")
+p = O.init_recurrent(np.random.default_rng(1), {"blstm": "lstm", "bgru": "gru"}.get(net, net), 40, 512, 4, 1909, bidirectional=bid)
+m = nn.get_nn(net, 4, [512], 1909, nn.F.relu, [5]); m.load_params(p); m.precision = "bf16"
+td = 0 if bid else 5
 dev = torch.device("cuda:0")
 xd = torch.from_numpy(x).to(dev); out = torch.empty((len(x), 1909), device=dev)
 for _ in range(2):
-    R.forward_utterances(m, xd, off, out, 0, len(off) - 1, timedelay=5, device=0)
+    R.forward_utterances(m, xd, off, out, 0, len(off) - 1, timedelay=td, device=0)
 marks = []
 orig = ops.rnn_seq
 def timed(desc, flops):
@@ -30,7 +35,7 @@ def timed(desc, flops):
 ops.rnn_seq = timed
 R.ops.rnn_seq = timed
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-s.record(); R.forward_utterances(m, xd, off, out, 0, len(off) - 1, timedelay=5, device=0); e.record()
+s.record(); R.forward_utterances(m, xd, off, out, 0, len(off) - 1, timedelay=td, device=0); e.record()
 torch.cuda.synchronize()
 plan = next(iter(m._plans.values()))
 print(f"n_utt={n_utt} long groups={g_a}: pass {s.elapsed_time(e):.2f} ms, schedule {[v[1] for v in plan._sched_cache.values()]}")

@@ -282,7 +282,7 @@ def test_wide_gru_kernel_128_slots_per_batch(nn, network, units, n_utt):
         assert np.abs(wide[off[u]:off[u + 1]] - want).max() < 5e-2
 
 
-@pytest.mark.parametrize("network,units", [("lstm", 512), ("blstm", 512)])
+@pytest.mark.parametrize("network,units", [("lstm", 512), ("blstm", 512), ("gru", 512), ("bgru", 512), ("mgrurelu", 512)])
 def test_mixed_schedule_long_utterances_in_the_32_slot_kernel(nn, network, units, monkeypatch):
     """MixedSchedule: the longest utterances run in the 32-slot kernel, the rest in the 128-slot kernel, as two
     concurrent launches over one packed row space; same outputs as the plain 32-slot schedule."""
@@ -292,8 +292,11 @@ def test_mixed_schedule_long_utterances_in_the_32_slot_kernel(nn, network, units
     rng.shuffle(lens)
     off = _offsets(lens.tolist())
     x = rng.standard_normal((off[-1], 40)).astype(np.float32)
-    bid = network == "blstm"
-    m, p = _lstm(nn, 78, network, 40, units, 2, 39, precision="bf16", bidirectional=bid)
+    bid = network in ("blstm", "bgru")
+    if "lstm" in network:
+        m, p = _lstm(nn, 78, network, 40, units, 2, 39, precision="bf16", bidirectional=bid)
+    else:
+        m, p = _gru(nn, 78, network, 40, units, 2, 39, precision="bf16", bidirectional=bid)
     monkeypatch.setenv("NNAM_RNN_MIXED", "force")
     mixed = np.zeros((off[-1], 39), np.float32)
     recurrent_engine.forward_utterances(m, x, off, mixed, 0, len(lens), timedelay=3 if not bid else 0, device=0)
@@ -301,5 +304,5 @@ def test_mixed_schedule_long_utterances_in_the_32_slot_kernel(nn, network, units
     assert any(isinstance(v[0], recurrent_engine.MixedSchedule) for v in plan._sched_cache.values())
     narrow = np.zeros_like(mixed)
     recurrent_engine.forward_utterances(m, x, off, narrow, 0, len(lens), timedelay=3 if not bid else 0, device=0, nb=32)
-    assert np.abs(mixed - narrow).max() < 2e-2
+    assert np.abs(mixed - narrow).max() < 3e-2
     assert np.array_equal(mixed == 0, narrow == 0)  # the same rows stay unwritten (quirk Q4)
