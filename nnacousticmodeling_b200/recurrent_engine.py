@@ -674,7 +674,10 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
             nb = len(lens)
             sched = Schedule(lens + timedelay, nb, 1, 1, device, 1)
         else:
-            sched, nb = pick_schedule(plan, lens + timedelay, device, nb, allow_mixed=len(models) == 1)
+            # members of one architecture (the usual fold ensemble) share the schedule, mixed or not; a heterogeneous
+            # ensemble re-packs per architecture with a fixed batch width, which a mixed schedule does not have
+            homog = all((p_.cell, p_.hidden, p_.n_dirs) == (plan.cell, plan.hidden, plan.n_dirs) for p_ in plans)
+            sched, nb = pick_schedule(plan, lens + timedelay, device, nb, allow_mixed=homog)
         scheds = {(plan.cell, plan.hidden, plan.n_dirs): sched}
         rows = sched.n_rows
         # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1); like the schedule
