@@ -216,7 +216,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -227,8 +227,6 @@ def run_ours(args):
     from nnacousticmodeling_b200 import engine, ops
 
     from nnacousticmodeling_b200 import dist_util
-    # keep NCCL's version banner (printed at VERSION and WARN level) out of stdout: rank 0 prints ONE JSON line there
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     world, rank, local = dist_util.env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -382,12 +380,33 @@ def run_ours(args):
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     dist_util.finalize()
     return 0
 
 
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """Rank 0 prints ONE JSON line on stdout.  Libraries also write there (NCCL prints its version banner from C code
+    at communicator creation, whatever NCCL_DEBUG_FILE says), so the real stdout is kept aside for the result line and
+    file descriptor 1 points at stderr for everything else."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
