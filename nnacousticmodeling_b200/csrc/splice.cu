@@ -10,6 +10,8 @@
 // simply smem[(f - f0) * dim + c]: every output row is produced with 128-bit shared loads and coalesced
 // 128-bit global stores.  Algorithmic traffic: read dim*4 (+ivec) and write (winlen*dim + ivec)*elem bytes
 // per frame.
+#include <stdlib.h>
+
 #include "ptx.cuh"
 #include "nnam_internal.h"
 
@@ -263,6 +265,206 @@ __global__ void __launch_bounds__(SPLICE_THREADS) splice_transform_kernel(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Streaming variant for the product path (bf16 / bf16 hi+lo output, dim and ivec_dim multiples of 4, spliced width a
+// multiple of 8): persistent CTAs walk tiles of `tile_f` frames; the raw rows of a tile (+ halo) and its i-vector rows
+// are two contiguous spans of global memory, so ONE thread fetches them with two bulk copies (cp.async.bulk) into a
+// double buffer while the block emits the previous tile.  Everything that depends only on a thread's output column --
+// its transform values, which kind of column it is, its pointers' strides -- is set up once per CTA instead of once
+// per tile (ncu on the tile-per-CTA kernel: 75 % of its 16 M warp instructions were such set-up and staging copies).
+// Tiles that touch the ends of the whole array (clamped rows, quirk Q1) are staged by the threads themselves.
+constexpr int STREAM_THREADS = 256;
+
+template <int OUT_KIND>
+__global__ void __launch_bounds__(STREAM_THREADS) splice_stream_kernel(const SpliceParams p, const int n_tiles) {
+  extern __shared__ __align__(128) uint8_t s_raw[];
+  const int halo_rows = p.tile_f + 2 * p.splice;
+  const int x_floats = (halo_rows * p.dim + 31) & ~31;          // keep every region 128-byte aligned
+  const int iv_floats = (p.tile_f * p.ivec_dim + 31) & ~31;
+  const int t_floats = (p.spl_cols + 31) & ~31;
+  float* s_add = reinterpret_cast<float*>(s_raw);
+  float* s_mul = s_add + t_floats;
+  float* s_x0 = s_mul + t_floats;            // two buffers of x_floats
+  float* s_iv0 = s_x0 + 2 * x_floats;        // two buffers of iv_floats
+  uint64_t* full = reinterpret_cast<uint64_t*>(s_iv0 + 2 * iv_floats);  // [2]
+  const int tid = static_cast<int>(threadIdx.x);
+  const bool has_ft = p.add_shift != nullptr;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+  }
+  if (has_ft) {
+    for (int i = tid; i < p.spl_cols; i += STREAM_THREADS) {
+      s_add[i] = __ldg(p.add_shift + i);
+      s_mul[i] = __ldg(p.rescale + i);
+    }
+  }
+  __syncthreads();
+
+  // ---- per-thread column set-up (once per CTA)
+  const int vpr = static_cast<int>(p.ldo >> 3);   // 16-byte chunks per output row (<= STREAM_THREADS, checked by the host)
+  const int lanes_r = STREAM_THREADS / vpr;       // rows per sweep of the block
+  const bool active = tid < vpr * lanes_r;
+  const int cc = tid % vpr;
+  const int r_first = tid / vpr;
+  const int c = cc << 3;
+  // 0: spliced + transformed columns, 1: i-vector columns, 2: i-vector tail and zero padding (element-wise)
+  const int kind = c + 8 <= p.spl_cols ? 0 : (c + 8 <= p.spl_cols + p.ivec_dim ? 1 : 2);
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, m0 = make_float4(1.f, 1.f, 1.f, 1.f), m1 = m0;
+  if (kind == 0 && has_ft) {
+    a0 = *reinterpret_cast<const float4*>(s_add + c);
+    a1 = *reinterpret_cast<const float4*>(s_add + c + 4);
+    m0 = *reinterpret_cast<const float4*>(s_mul + c);
+    m1 = *reinterpret_cast<const float4*>(s_mul + c + 4);
+  }
+  const long long row_step = static_cast<long long>(lanes_r) * p.ldo;
+  const int src_off = kind == 0 ? r_first * p.dim + c : r_first * p.ivec_dim + (c - p.spl_cols);
+  const int src_step = lanes_r * (kind == 0 ? p.dim : p.ivec_dim);
+
+  auto tile_is_edge = [&](long long tf0, int tn) {
+    return tf0 - p.splice < 0 || tf0 + tn + p.splice > p.n_total;
+  };
+  // one thread: both spans of tile `t` into buffer `b`
+  auto issue = [&](int t, int b) {
+    const long long tf0 = p.f0 + static_cast<long long>(t) * p.tile_f;
+    const int tn = static_cast<int>(min(static_cast<long long>(p.tile_f), p.f1 - tf0));
+    if (tile_is_edge(tf0, tn)) return;  // staged synchronously by the whole block when its turn comes
+    const uint32_t bx = static_cast<uint32_t>((tn + 2 * p.splice) * p.dim) * 4u;
+    const uint32_t bi = static_cast<uint32_t>(tn * p.ivec_dim) * 4u;
+    fence_proxy_async_smem();  // the buffer's previous contents were read (or, for an edge tile, written) by threads
+    mbar_expect_tx(&full[b], bx + bi);
+    bulk_load_1d(s_x0 + b * x_floats, p.x + (tf0 - p.splice - p.x_row0) * p.dim, bx, &full[b]);
+    if (bi) bulk_load_1d(s_iv0 + b * iv_floats, p.ivec + (tf0 - p.f0) * p.ivec_dim, bi, &full[b]);
+  };
+
+  uint32_t phase = 0u;  // bit b: parity of buffer b's next fill
+  int b = 0;
+  if (tid == 0 && static_cast<int>(blockIdx.x) < n_tiles) issue(static_cast<int>(blockIdx.x), 0);
+  for (int t = static_cast<int>(blockIdx.x); t < n_tiles; t += static_cast<int>(gridDim.x), b ^= 1) {
+    const long long tf0 = p.f0 + static_cast<long long>(t) * p.tile_f;
+    const int tn = static_cast<int>(min(static_cast<long long>(p.tile_f), p.f1 - tf0));
+    const int t_next = t + static_cast<int>(gridDim.x);
+    if (tid == 0 && t_next < n_tiles) issue(t_next, b ^ 1);  // buffer b ^ 1 was released by the barrier below
+    float* xb = s_x0 + b * x_floats;
+    float* ivb = s_iv0 + b * iv_floats;
+    if (tile_is_edge(tf0, tn)) {
+      const int vx = p.dim >> 2;
+      for (int i = tid; i < (tn + 2 * p.splice) * vx; i += STREAM_THREADS) {
+        const int row = i / vx, v = i - row * vx;
+        long long g = tf0 - p.splice + row;
+        g = g < 0 ? 0 : (g >= p.n_total ? p.n_total - 1 : g);
+        reinterpret_cast<float4*>(xb)[i] = __ldg(reinterpret_cast<const float4*>(p.x + (g - p.x_row0) * p.dim) + v);
+      }
+      const float4* iv4 = reinterpret_cast<const float4*>(p.ivec + (tf0 - p.f0) * p.ivec_dim);
+      for (int i = tid; i < (tn * p.ivec_dim) >> 2; i += STREAM_THREADS) reinterpret_cast<float4*>(ivb)[i] = __ldg(iv4 + i);
+      __syncthreads();
+    } else {
+      mbar_wait(&full[b], (phase >> b) & 1u);
+      phase ^= 1u << b;
+    }
+
+    if (active) {
+      __nv_bfloat16* dh = static_cast<__nv_bfloat16*>(p.out_hi) + (tf0 - p.f0 + r_first) * p.ldo + c;
+      __nv_bfloat16* dl = OUT_KIND == NNAM_OUT_BF16_SPLIT
+                              ? static_cast<__nv_bfloat16*>(p.out_lo) + (tf0 - p.f0 + r_first) * p.ldo + c
+                              : nullptr;
+      auto emit = [&](const float4& v0, const float4& v1) {
+        *reinterpret_cast<uint4*>(dh) = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w),
+                                                   pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+        dh += row_step;
+        if (OUT_KIND == NNAM_OUT_BF16_SPLIT) {
+          *reinterpret_cast<uint4*>(dl) = make_uint4(
+              pack_bf16x2(v0.x - bf16_round(v0.x), v0.y - bf16_round(v0.y)),
+              pack_bf16x2(v0.z - bf16_round(v0.z), v0.w - bf16_round(v0.w)),
+              pack_bf16x2(v1.x - bf16_round(v1.x), v1.y - bf16_round(v1.y)),
+              pack_bf16x2(v1.z - bf16_round(v1.z), v1.w - bf16_round(v1.w)));
+          dl += row_step;
+        }
+      };
+      if (kind == 0) {
+        const float* src = xb + src_off;
+        if (has_ft) {
+#pragma unroll 2
+          for (int r = r_first; r < tn; r += lanes_r, src += src_step) {
+            float4 v0 = *reinterpret_cast<const float4*>(src), v1 = *reinterpret_cast<const float4*>(src + 4);
+            v0.x = __fmul_rn(__fadd_rn(v0.x, a0.x), m0.x);
+            v0.y = __fmul_rn(__fadd_rn(v0.y, a0.y), m0.y);
+            v0.z = __fmul_rn(__fadd_rn(v0.z, a0.z), m0.z);
+            v0.w = __fmul_rn(__fadd_rn(v0.w, a0.w), m0.w);
+            v1.x = __fmul_rn(__fadd_rn(v1.x, a1.x), m1.x);
+            v1.y = __fmul_rn(__fadd_rn(v1.y, a1.y), m1.y);
+            v1.z = __fmul_rn(__fadd_rn(v1.z, a1.z), m1.z);
+            v1.w = __fmul_rn(__fadd_rn(v1.w, a1.w), m1.w);
+            emit(v0, v1);
+          }
+        } else {
+#pragma unroll 2
+          for (int r = r_first; r < tn; r += lanes_r, src += src_step)
+            emit(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4));
+        }
+      } else if (kind == 1) {
+        const float* src = ivb + src_off;
+#pragma unroll 2
+        for (int r = r_first; r < tn; r += lanes_r, src += src_step)
+          emit(*reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4));
+      } else {
+        const int n_iv = p.spl_cols + p.ivec_dim - c;  // i-vector elements left in this chunk (may be <= 0: all padding)
+        const float* src = ivb + src_off;
+        for (int r = r_first; r < tn; r += lanes_r, src += src_step) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = j < n_iv ? src[j] : 0.0f;
+          emit(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]));
+        }
+      }
+    }
+    __syncthreads();  // buffer b may be refilled (by the issue at the top of the next-but-one iteration)
+  }
+}
+
+static size_t splice_stream_smem(const SpliceParams& p, int tile_f) {
+  const size_t x_floats = (static_cast<size_t>(tile_f + 2 * p.splice) * p.dim + 31) & ~static_cast<size_t>(31);
+  const size_t iv_floats = (static_cast<size_t>(tile_f) * p.ivec_dim + 31) & ~static_cast<size_t>(31);
+  const size_t t_floats = (static_cast<size_t>(p.spl_cols) + 31) & ~static_cast<size_t>(31);
+  return (2 * t_floats + 2 * x_floats + 2 * iv_floats) * sizeof(float) + 16;
+}
+
+// true if the streaming kernel applies (the caller has checked the 16-byte alignment of x / ivec / out)
+static bool splice_stream_applies(const SpliceParams& p) {
+  if (getenv("NNAM_SPLICE_STREAM") && getenv("NNAM_SPLICE_STREAM")[0] == '0') return false;
+  if (p.dim % 4 || p.ivec_dim % 4 || p.spl_cols % 8 || p.ldo % 8) return false;
+  const long long vpr = p.ldo >> 3;
+  return vpr >= 1 && vpr <= STREAM_THREADS;
+}
+
+template <int OUT_KIND>
+static int launch_splice_stream(const SpliceParams& p_in, cudaStream_t stream) {
+  SpliceParams p = p_in;
+  const long long frames = p.f1 - p.f0;
+  p.tile_f = 32;
+  const size_t smem = splice_stream_smem(p, p.tile_f);
+  if (smem > 100 * 1024) return -1;  // caller falls back to the tile-per-CTA kernel
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(splice_stream_kernel<OUT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_set = true;
+  }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, splice_stream_kernel<OUT_KIND>, STREAM_THREADS, smem) !=
+          cudaSuccess || occ <= 0) {
+    cudaGetLastError();
+    return -1;
+  }
+  const long long n_tiles = (frames + p.tile_f - 1) / p.tile_f;
+  if (n_tiles > 0x7fffffffLL) return -1;
+  const long long slots = static_cast<long long>(occ) * sm_count();
+  const unsigned grid = static_cast<unsigned>(n_tiles < slots ? n_tiles : slots);
+  splice_stream_kernel<OUT_KIND><<<grid, STREAM_THREADS, smem, stream>>>(p, static_cast<int>(n_tiles));
+  return check_launch("splice_stream_kernel");
+}
+
 static size_t splice_smem_bytes(const SpliceParams& p, bool vec, int tile_f) {
   return (static_cast<size_t>(tile_f + 2 * p.splice) * p.dim + 2 * static_cast<size_t>(p.spl_cols) +
           (vec ? static_cast<size_t>(tile_f) * p.ivec_dim : 0)) *
@@ -369,7 +571,15 @@ int splice_transform(const float* x, long long x_row0, long long x_rows, long lo
       if (out_kind == NNAM_OUT_BF16_SPLIT) {
         if (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 15))
           return set_error(NNAM_ERR_ARG, "splice: split output needs an aligned out_lo");
+        if (aligned_in && splice_stream_applies(p)) {
+          const int rc = launch_splice_stream<NNAM_OUT_BF16_SPLIT>(p, stream);
+          if (rc >= 0) return rc;
+        }
         return launch_splice<NNAM_OUT_BF16_SPLIT>(p, aligned_in, stream);
+      }
+      if (aligned_in && splice_stream_applies(p)) {
+        const int rc = launch_splice_stream<NNAM_OUT_BF16>(p, stream);
+        if (rc >= 0) return rc;
       }
       return launch_splice<NNAM_OUT_BF16>(p, aligned_in, stream);
     }
