@@ -412,6 +412,11 @@ __global__ void __launch_bounds__(STREAM_THREADS) splice_stream_kernel(const Spl
       } else {
         const int n_iv = p.spl_cols + p.ivec_dim - c;  // i-vector elements left in this chunk (may be <= 0: all padding)
         const float* src = ivb + src_off;
+        if (n_iv == 4 || n_iv <= 0) {  // ivec_dim % 4 == 0: the tail is one aligned float4 or nothing
+          const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int r = r_first; r < tn; r += lanes_r, src += src_step)
+            emit(n_iv == 4 ? *reinterpret_cast<const float4*>(src) : zero, zero);
+        } else
         for (int r = r_first; r < tn; r += lanes_r, src += src_step) {
           float v[8];
 #pragma unroll
