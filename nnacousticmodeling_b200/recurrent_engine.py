@@ -643,6 +643,96 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
     return a_hi, a_lo, state_out
 
 
+def _phase_split(lens):
+    """Utterance subsets (indices into the shard, ascending) that are computed one after the other so that the
+    device->host copy of a finished subset overlaps the computation of the next one.  Results only exist after the last
+    layer, and a layer's time is set by its longest utterance, so the first subset takes the SHORTEST utterances (about
+    30 % of the frames: quick to compute, and long enough on the wire to cover the second subset's computation).  Small
+    shards and NNAM_RNN_PHASES=1 keep one subset."""
+    n = len(lens)
+    total = int(lens.sum())
+    if os.environ.get("NNAM_RNN_PHASES", "2") == "1" or n < 256 or total < 150000:
+        return [np.arange(n)]
+    by_len = np.argsort(lens, kind="stable")
+    csum = np.cumsum(lens[by_len])
+    k = int(np.searchsorted(csum, 0.3 * total))
+    k = max(128, min(k, n - 128))
+    return [np.sort(by_len[:k]), np.sort(by_len[k:])]
+
+
+def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, out_dev, timedelay, fix_timedelay_tail,
+                   nb, device, stepwise):
+    """One subset of utterances (start frame relative to the shard and length of each) through the whole net:
+    packed gather -> layers -> output GEMM -> head, which scatters the rows into ``out_dev`` (all frames of the shard)."""
+    plan = plans[0]
+    ws = plan.ws
+    split = plan.split
+    if stepwise:  # time-step launches over ONE batch holding every utterance of the subset
+        nb = len(lens)
+        sched = Schedule(lens + timedelay, nb, 1, 1, device, 1)
+    else:
+        # members of one architecture (the usual fold ensemble) share the schedule, mixed or not; a heterogeneous
+        # ensemble re-packs per architecture with a fixed batch width, which a mixed schedule does not have
+        homog = all((p_.cell, p_.hidden, p_.n_dirs) == (plan.cell, plan.hidden, plan.n_dirs) for p_ in plans)
+        sched, nb = pick_schedule(plan, lens + timedelay, device, nb, allow_mixed=homog)
+    scheds = {(plan.cell, plan.hidden, plan.n_dirs): sched}
+    rows = sched.n_rows
+    # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1); like the schedule
+    # these maps depend only on where the utterances lie, and are cached with it
+    maps = plan.__dict__.setdefault("_map_cache", {})
+    mkey = (starts.tobytes(), lens.tobytes(), timedelay, bool(fix_timedelay_tail), nb)
+    if mkey not in maps:
+        utt = sched.order[sched.row_sorted_utt]  # utterance index inside the subset
+        step = sched.row_step
+        l_row = lens[utt]
+        start = starts[utt]
+        src = start + np.minimum(step, l_row - 1)
+        dst = start + step - timedelay
+        keep = step >= timedelay
+        dst = np.where(keep, dst, -1)
+        if not fix_timedelay_tail:
+            # predict_folds.py:50,60-61: rows are written only while utt_len > t (quirk Q4), so the last `timedelay`
+            # frames of every utterance stay 0; the head zero-fills exactly those rows (entry -2 - row) and every
+            # output row is written once -- no separate memset of the (N, C) matrix
+            dst = np.where(keep & (step >= l_row), -2 - dst, dst)
+        if len(maps) >= 8:
+            maps.pop(next(iter(maps)))
+        maps[mkey] = (torch.from_numpy(src.astype(np.int32)).to(device),
+                      torch.from_numpy(dst.astype(np.int32)).to(device))
+    d_src, d_dst = maps[mkey]
+
+    d_in = models[0].in_size
+    ld_in = round_up(d_in, 8)
+    a_hi = ws.get("rnn.a.hi", rows, ld_in, torch.bfloat16)
+    a_lo = ws.get("rnn.a.lo", rows, ld_in, torch.bfloat16) if split else None
+    ops.gather_transform(x_dev, d_src, add, mul, iv_dev, out_kind=plan.act_kind, ldo=ld_in, out=(a_hi, a_lo))
+    n_out = models[0].n_out
+    logits = []
+    for k, (m, pl) in enumerate(zip(models, plans)):
+        if m.in_size != d_in or m.n_out != n_out:
+            raise NnamError("forward_utterances: ensemble members must share input and output sizes")
+        key = (pl.cell, pl.hidden, pl.n_dirs)
+        pl_stepwise = pl.cell == CELL_PEEPHOLE and not pl.peep_persistent
+        if pl_stepwise != stepwise:
+            raise NnamError("forward_utterances: time-step and persistent nets cannot share one ensemble pass")
+        if pl_stepwise:
+            from . import peephole_engine
+            h_hi, h_lo = peephole_engine.run_layers(m, pl, sched, a_hi, a_lo, rows, ws=ws)
+        else:
+            if key not in scheds:  # same utterances and batch width => same packed row order, other grouping
+                scheds[key], _ = pick_schedule(pl, lens + timedelay, device, nb)
+            h_hi, h_lo, _ = run_layers(m, pl, scheds[key], a_hi, a_lo, rows, nb, ws=ws)
+        lg = ws.get(f"rnn.logits{k}", rows, round_up(n_out, 16), torch.float32)
+        pl.out(h_hi, h_lo, rows, "identity", OUT_F32, out=(lg, None))
+        logits.append(lg)
+    for u in np.nonzero(lens < timedelay)[0]:  # utterances shorter than the delay have rows no packed row maps to
+        out_dev[int(starts[u]):int(starts[u] + lens[u])].zero_()
+    prior = _dev_vec(head.prior, device)
+    rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
+    ops.head(logits, n_out, rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
+             prior_scale=head.prior_scale, final_normalize=head.final_normalize, out=out_dev, out_row_map=d_dst)
+
+
 def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, timedelay=0, device=0, head=None,
                        fix_timedelay_tail=False, nb=DEFAULT_BATCH):
     """Recurrent hot path on ONE device for utterances [u0, u1) (predict_folds.py:28-68 semantics).
@@ -651,6 +741,8 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
     x / ivectors: (N, dim) / (N, I) float32, host arrays or CUDA tensors; out: (N, C) float32 host array or CUDA
     tensor, rows [offsets[u0], offsets[u1]) are written.  Output frame f of an utterance is the network output at
     step f + timedelay; like the reference, the last ``timedelay`` frames stay 0 unless fix_timedelay_tail.
+    With a host ``out`` a large shard is computed in two subsets of utterances (:func:`_phase_split`) and the copy of
+    the first one to the host runs under the computation of the second.
     """
     models = list(model) if isinstance(model, (list, tuple)) else [model]
     device = _device(device)
@@ -660,49 +752,16 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         return out
     f_lo, f_hi = int(offsets[u0]), int(offsets[u1])
     lens = (offsets[u0 + 1:u1 + 1] - offsets[u0:u1]).astype(np.int64)
+    starts = (offsets[u0:u1] - f_lo).astype(np.int64)
     if np.any(lens <= 0):
         raise NnamError("forward_utterances: empty utterance in offsets")
     with torch.cuda.device(device):
         plans = [get_plan(m, device) for m in models]
         plan = plans[0]
         ws = plan.ws
-        split = plan.split
-        if any(p.split != split for p in plans):
+        if any(p.split != plan.split for p in plans):
             raise NnamError("forward_utterances: all ensemble members must use the same precision mode")
         stepwise = plan.cell == CELL_PEEPHOLE and not plan.peep_persistent
-        if stepwise:  # time-step launches over ONE batch holding every utterance of the shard
-            nb = len(lens)
-            sched = Schedule(lens + timedelay, nb, 1, 1, device, 1)
-        else:
-            # members of one architecture (the usual fold ensemble) share the schedule, mixed or not; a heterogeneous
-            # ensemble re-packs per architecture with a fixed batch width, which a mixed schedule does not have
-            homog = all((p_.cell, p_.hidden, p_.n_dirs) == (plan.cell, plan.hidden, plan.n_dirs) for p_ in plans)
-            sched, nb = pick_schedule(plan, lens + timedelay, device, nb, allow_mixed=homog)
-        scheds = {(plan.cell, plan.hidden, plan.n_dirs): sched}
-        rows = sched.n_rows
-        # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1); like the schedule
-        # these maps depend only on the utterance lengths and are cached with it
-        maps = plan.__dict__.setdefault("_map_cache", {})
-        mkey = (lens.tobytes(), timedelay, bool(fix_timedelay_tail), nb)
-        if mkey not in maps:
-            utt = sched.order[sched.row_sorted_utt]  # original utterance (shard-relative)
-            step = sched.row_step
-            l_row = lens[utt]
-            start = offsets[u0:u1][utt] - f_lo
-            src = start + np.minimum(step, l_row - 1)
-            dst = start + step - timedelay
-            keep = step >= timedelay
-            dst = np.where(keep, dst, -1)
-            if not fix_timedelay_tail:
-                # predict_folds.py:50,60-61: rows are written only while utt_len > t (quirk Q4), so the last `timedelay`
-                # frames of every utterance stay 0; the head zero-fills exactly those rows (entry -2 - row) and every
-                # output row is written once -- no separate memset of the (N, C) matrix
-                dst = np.where(keep & (step >= l_row), -2 - dst, dst)
-            if len(maps) >= 8:
-                maps.pop(next(iter(maps)))
-            maps[mkey] = (torch.from_numpy(src.astype(np.int32)).to(device),
-                          torch.from_numpy(dst.astype(np.int32)).to(device))
-        d_src, d_dst = maps[mkey]
 
         if isinstance(x, torch.Tensor) and x.is_cuda:
             x_dev = x[f_lo:f_hi]
@@ -725,40 +784,38 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         if d_in != x.shape[1] + (0 if ivectors is None else ivectors.shape[1]):
             raise NnamError(f"forward_utterances: model expects {d_in} inputs, data provides "
                             f"{x.shape[1] + (0 if ivectors is None else ivectors.shape[1])}")
-        ld_in = round_up(d_in, 8)
-        a_hi = ws.get("rnn.a.hi", rows, ld_in, torch.bfloat16)
-        a_lo = ws.get("rnn.a.lo", rows, ld_in, torch.bfloat16) if split else None
-        ops.gather_transform(x_dev, d_src, add, mul, iv_dev, out_kind=plan.act_kind, ldo=ld_in, out=(a_hi, a_lo))
         n_out = models[0].n_out
-        logits = []
-        for k, (m, pl) in enumerate(zip(models, plans)):
-            if m.in_size != d_in or m.n_out != n_out:
-                raise NnamError("forward_utterances: ensemble members must share input and output sizes")
-            key = (pl.cell, pl.hidden, pl.n_dirs)
-            pl_stepwise = pl.cell == CELL_PEEPHOLE and not pl.peep_persistent
-            if pl_stepwise != stepwise:
-                raise NnamError("forward_utterances: time-step and persistent nets cannot share one ensemble pass")
-            if pl_stepwise:
-                from . import peephole_engine
-                h_hi, h_lo = peephole_engine.run_layers(m, pl, sched, a_hi, a_lo, rows, ws=ws)
-            else:
-                if key not in scheds:  # same utterances and batch width => same packed row order, other grouping
-                    scheds[key], _ = pick_schedule(pl, lens + timedelay, device, nb)
-                h_hi, h_lo, _ = run_layers(m, pl, scheds[key], a_hi, a_lo, rows, nb, ws=ws)
-            lg = ws.get(f"rnn.logits{k}", rows, round_up(n_out, 16), torch.float32)
-            pl.out(h_hi, h_lo, rows, "identity", OUT_F32, out=(lg, None))
-            logits.append(lg)
         on_dev = isinstance(out, torch.Tensor) and out.is_cuda
         out_dev = out[f_lo:f_hi] if on_dev else ws.get("rnn.out", f_hi - f_lo, n_out, torch.float32)
-        if np.any(lens < timedelay):  # utterances shorter than the delay have rows no packed row maps to
-            out_dev.zero_()
-        prior = _dev_vec(head.prior, device)
-        rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
-        ops.head(logits, n_out, rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
-                 prior_scale=head.prior_scale, final_normalize=head.final_normalize, out=out_dev, out_row_map=d_dst)
-        if not on_dev:
-            _as_host_tensor(out)[f_lo:f_hi].copy_(out_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        phases = [np.arange(len(lens))] if (on_dev or stepwise) else _phase_split(lens)
+        main = torch.cuda.current_stream()
+        side = None
+        for idx in phases:
+            whole = len(idx) == len(lens)
+            _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts if whole else starts[idx],
+                           lens if whole else lens[idx], out_dev, timedelay, fix_timedelay_tail, nb, device, stepwise)
+            if on_dev:
+                continue
+            out_host = _as_host_tensor(out)
+            if len(phases) == 1:
+                out_host[f_lo:f_hi].copy_(out_dev, non_blocking=True)
+                continue
+            # rows of this subset, as maximal runs of neighbouring utterances, on the copy stream
+            if side is None:
+                side = plan.__dict__.get("_d2h_stream")
+                if side is None:
+                    side = plan._d2h_stream = torch.cuda.Stream()
+            done = torch.cuda.Event()
+            done.record(main)
+            brk = np.nonzero(np.diff(idx) != 1)[0] + 1
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                for run in np.split(idx, brk):
+                    r0, r1 = int(starts[run[0]]), int(starts[run[-1]] + lens[run[-1]])
+                    out_host[f_lo + r0:f_lo + r1].copy_(out_dev[r0:r1], non_blocking=True)
+        main.synchronize()
+        if side is not None:
+            side.synchronize()
     return out
 
 

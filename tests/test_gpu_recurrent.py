@@ -306,3 +306,35 @@ def test_mixed_schedule_long_utterances_in_the_32_slot_kernel(nn, network, units
     recurrent_engine.forward_utterances(m, x, off, narrow, 0, len(lens), timedelay=3 if not bid else 0, device=0, nb=32)
     assert np.abs(mixed - narrow).max() < 3e-2
     assert np.array_equal(mixed == 0, narrow == 0)  # the same rows stay unwritten (quirk Q4)
+
+
+@pytest.mark.parametrize("network", ["lstm", "bgru"])
+def test_two_phase_forward_equals_single_phase(nn, network, monkeypatch):
+    """Large shards with a host output are computed in two subsets of utterances (shortest first) so that the first
+    subset's device->host copy overlaps the second's computation: bit-identical to the single-phase result, including
+    quirk Q4 rows and utterances shorter than the time delay."""
+    from nnacousticmodeling_b200 import recurrent_engine
+    rng = np.random.default_rng(17)
+    lens = rng.integers(350, 750, size=300)
+    lens[[5, 77, 123]] = [2, 1, 3]  # shorter than / equal to the delay
+    rng.shuffle(lens)
+    off = _offsets(lens.tolist())
+    assert off[-1] >= 150000
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    bid = network == "bgru"
+    td = 0 if bid else 3
+    if network == "lstm":
+        m, _ = _lstm(nn, 5, network, 40, 64, 2, 39, precision="bf16")
+    else:
+        m, _ = _gru(nn, 5, network, 40, 64, 2, 39, precision="bf16", bidirectional=True)
+    assert len(recurrent_engine._phase_split(lens)) == 2
+    two = np.full((off[-1], 39), 7.0, np.float32)
+    recurrent_engine.forward_utterances(m, x, off, two, 0, len(lens), timedelay=td, device=0)
+    monkeypatch.setenv("NNAM_RNN_PHASES", "1")
+    assert len(recurrent_engine._phase_split(lens)) == 1
+    one = np.full((off[-1], 39), 7.0, np.float32)
+    recurrent_engine.forward_utterances(m, x, off, one, 0, len(lens), timedelay=td, device=0)
+    assert np.array_equal(two, one)
+    if td:
+        for u in (int(np.argmin(lens)), 0):
+            assert np.all(two[off[u + 1] - min(td, lens[u]):off[u + 1]] == 0)
