@@ -113,3 +113,23 @@ def test_mixed_schedule_packs_every_frame_once():
     # the long part holds exactly the 64 longest utterances
     assert sorted(lens[ms.order[:64]].tolist(), reverse=True) == sorted(lens.tolist(), reverse=True)[:64]
     assert sa.n_groups <= 2 and sb.n_groups <= 7
+
+
+def test_phase_split_covers_every_utterance_once(monkeypatch):
+    """Two-subset forward: every utterance in exactly one subset, the first holds the shortest ones (about 30 % of the
+    frames), small shards stay whole, NNAM_RNN_PHASES=1 switches it off."""
+    from nnacousticmodeling_b200.recurrent_engine import _phase_split
+    rng = np.random.default_rng(5)
+    lens = rng.integers(100, 800, 1344)
+    parts = _phase_split(lens)
+    assert len(parts) == 2
+    both = np.concatenate(parts)
+    assert sorted(both.tolist()) == list(range(1344))
+    assert all(np.all(np.diff(p) > 0) for p in parts)
+    assert lens[parts[0]].max() <= lens[parts[1]].min()
+    frac = lens[parts[0]].sum() / lens.sum()
+    assert 0.2 < frac < 0.4
+    assert len(_phase_split(lens[:200])) == 1          # few utterances
+    assert len(_phase_split(np.full(400, 100))) == 1   # few frames
+    monkeypatch.setenv("NNAM_RNN_PHASES", "1")
+    assert len(_phase_split(lens)) == 1
