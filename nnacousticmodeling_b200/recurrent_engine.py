@@ -651,13 +651,21 @@ def _phase_split(lens):
     shards and NNAM_RNN_PHASES=1 keep one subset."""
     n = len(lens)
     total = int(lens.sum())
-    if os.environ.get("NNAM_RNN_PHASES", "2") == "1" or n < 256 or total < 150000:
+    n_ph = int(os.environ.get("NNAM_RNN_PHASES", "2"))
+    if n_ph <= 1 or n < 256 or total < 150000:
         return [np.arange(n)]
     by_len = np.argsort(lens, kind="stable")
     csum = np.cumsum(lens[by_len])
-    k = int(np.searchsorted(csum, 0.3 * total))
-    k = max(128, min(k, n - 128))
-    return [np.sort(by_len[:k]), np.sort(by_len[k:])]
+    cuts = [0.3] if n_ph == 2 else [0.15, 0.45]  # cumulative frame fractions at which a new subset starts
+    bounds = [0]
+    for c in cuts:
+        k = int(np.searchsorted(csum, c * total))
+        k = max(bounds[-1] + 128, min(k, n - 128))
+        if k >= n - 127 or k <= bounds[-1]:
+            break
+        bounds.append(k)
+    bounds.append(n)
+    return [np.sort(by_len[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
 
 
 def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, out_dev, timedelay, fix_timedelay_tail,
