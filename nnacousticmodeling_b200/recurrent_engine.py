@@ -10,7 +10,6 @@ on finished utterances.
 """
 from __future__ import annotations
 
-import ctypes
 import os
 
 import numpy as np
