@@ -156,7 +156,6 @@ def main(arg_list=None):
     device, evaluate.py:163-171), model / NNWithRPL construction (:101-138), then evaluateModelTestTri.  Extensions:
     ``--precision bf16|fp32`` and ``--tmp-dir`` for the .lab directory (the reference hard-codes 'lab')."""
     import argparse
-    import sys
 
     from . import functions as F
     from .features import adapt_transform, loadKaldiFeatureTransform, splice_and_transform
