@@ -14,9 +14,11 @@
 //                     (128 rows x 128 B = 16 KB) through a 4-stage TMA ring straight into the MMAs, so NB = 128 fits
 //                     and a step moves twice the utterances for about the same exchange latency.
 //
-// Roles per CTA (512 threads): warp 0 = exchange wait + TMA producer, warp 1 = MMA issuer (both with all lanes, one
+// Two kernels live here.  lstm_seq_wide_kernel (one batch per CTA group, kept for A/B runs, NNAM_RNN_WIDE_STREAMS=1):
+// roles per CTA (512 threads): warp 0 = exchange wait + TMA producer, warp 1 = MMA issuer (both with all lanes, one
 // elected), then all 16 warps do the gate math: warp w owns TMEM lane quarter w & 3 (32 utterances) and columns
-// [32 * (w >> 2), +32) = 8 units.
+// [32 * (w >> 2), +32) = 8 units.  lstm_seq_wide2_kernel (the default, further down): S interleaved batches per group
+// sharing one TMA ring -- its header comment has the protocol.
 #include <cooperative_groups.h>
 
 #include "recurrent_common.cuh"
