@@ -358,7 +358,7 @@ def run_ours(args):
     line = {
         "metric": "acoustic-model frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3(fp32-accurate)",
+        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "bf16x3(fp32-accurate)"}.get(args.precision, args.precision),
         "data": "synthetic",
         "config": {"workload": w["desc"], "frames_per_gpu": n, "precision": args.precision,
                    "l2": "inputs+activations larger than L2 (no flush needed)", "parallelism": f"dp{world} utterance shards, no collective",
@@ -412,7 +412,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16",
+                    help="bf16 | fp16 | fp32 (bf16x3) | bf16+a[:layers][+w[:layers]] -- see engine.Precision")
     ap.add_argument("--cpu-sample", type=int, default=None,
                     help="frames of the workload timed on the CPU (default: ~10-30 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -11,7 +11,8 @@
  *   - every function returns 0 on success or a negative NNAM_ERR_* code; nnam_last_error() returns a
  *     thread-local human-readable message for the last failure;
  *   - re-entrant across streams and devices (one host thread per GPU is the intended use).
- *   - bf16 matrices are row-major with a leading dimension in ELEMENTS that is a multiple of 8.
+ *   - 16-bit matrices (bf16 or fp16, see NNAM_ELEM_*) are row-major with a leading dimension in ELEMENTS that is a
+ *     multiple of 8.
  */
 #ifndef NNAM_B200_H_
 #define NNAM_B200_H_
@@ -22,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NNAM_ABI_VERSION 1
+#define NNAM_ABI_VERSION 2
 
 /* error codes */
 #define NNAM_OK 0
@@ -40,6 +41,20 @@ extern "C" {
 #define NNAM_OUT_BF16 0       /* bf16 (hi only) */
 #define NNAM_OUT_BF16_SPLIT 1 /* bf16 hi + bf16 lo, hi + lo ~= fp32 value (16 mantissa bits) */
 #define NNAM_OUT_F32 2        /* fp32 */
+#define NNAM_OUT_F16 3        /* IEEE fp16 (hi only), saturating conversion */
+
+/* 16-bit element type of GEMM / recurrence operands.  Both feed tcgen05.mma kind::f16 at the same rate; fp16 carries an
+ * 11-bit significand against bf16's 8 (8x smaller rounding error per operand) over a narrower range (|v| <= 65504,
+ * conversions saturate), which is what lets the single-pass mode meet north_star's >= 99.5 % frame-argmax agreement.
+ * The hi/lo split planes of the fp32-accurate mode are always bf16.  */
+#define NNAM_ELEM_BF16 0
+#define NNAM_ELEM_F16 1
+
+/* operand passes of nnam_linear_bias_act (`nsplit`): A = A_hi + A_lo, W = W_hi + W_lo, fp32 accumulation in TMEM */
+#define NNAM_SPLIT_NONE 1 /* A_hi.W_hi                              (one tensor pass) */
+#define NNAM_SPLIT_A 2    /* A_hi.W_hi + A_lo.W_hi                  (activations carry 16 mantissa bits; needs a_lo) */
+#define NNAM_SPLIT_AW 3   /* A_hi.W_hi + A_hi.W_lo + A_lo.W_hi      ("bf16x3", fp32-accurate; needs a_lo and w_lo) */
+#define NNAM_SPLIT_W 4    /* A_hi.W_hi + A_hi.W_lo                  (weights carry 16 mantissa bits; needs w_lo) */
 
 /* recurrent cell kinds for nnam_rnn_seq */
 #define NNAM_CELL_LSTM 0     /* L.LSTM / L.StatefulZoneoutLSTM at inference (chainer_networks.py:44-101) */
@@ -78,13 +93,14 @@ int nnam_convert_f32(const float* src, long long rows, int cols, long long lds, 
 
 /* K2 -- out = act(A . W^T + bias): every L.Linear of chainer_networks.py (F.linear: x.dot(W.T) + b) and the
  * batched `upward` / `W_*` projections of the recurrent links.  A [M,K] (lda), W [N,K] (ldw) bf16 K-major.
- * nsplit 1: bf16; nsplit 3: bf16x3 fp32-accurate mode (needs a_lo, w_lo).  bias may be NULL.
- * out_kind selects bf16 / bf16 split / fp32 output with leading dimension ldo >= N (rows 16-byte aligned); only
+ * nsplit: NNAM_SPLIT_* (1 = single pass; 3 = bf16x3 fp32-accurate mode, needs a_lo, w_lo; 2 / 4 = only the activations /
+ * only the weights split).  elem: NNAM_ELEM_* of a_hi / w_hi (split passes need NNAM_ELEM_BF16).  bias may be NULL.
+ * out_kind selects bf16 / fp16 / bf16 split / fp32 output with leading dimension ldo >= N (rows 16-byte aligned); only
  * columns [0, N) are written.  A may be a column slice of a wider matrix (pointer offset + lda): that is how the
  * TDNN's valid 1 x k convolutions (chainer_networks.py:38-42) run on this kernel without an im2col copy.  */
 int nnam_linear_bias_act(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
                          long long ldw, const float* bias, void* out_hi, void* out_lo, long long ldo, int M,
-                         int N, int K, int act, int out_kind, int nsplit, void* stream);
+                         int N, int K, int act, int out_kind, int nsplit, int elem, void* stream);
 
 /* K4 -- fused ensemble mean -> RPL4 -> minus log-prior -> log-softmax head.
  * Replaces `y - logsum(y, axis=1)` (predict_folds.py:57,88; kw_utils.py:38-43), `y = y - ap` +
@@ -129,10 +145,11 @@ int nnam_gather_transform(const float* x, long long n_src, int dim, const float*
  *   p2 = c' . peep_o^T
  *   phase 1:  h' = s(gx_o + g1_o + p2) tanh(c')                              -> columns [0, H) of out
  * out_hi/out_lo are the bf16 (hi/lo) [h | c] rows of this step, (n, out_ld >= 2H).  g1 / c_prev may be NULL on the
- * first step (h = None, c = 0).  fast_tanh: 1 = tanh.approx (bf16 mode), 0 = tanhf (fp32-accurate mode).  */
+ * first step (h = None, c = 0).  fast_tanh: 1 = tanh.approx (16-bit modes), 0 = tanhf (fp32-accurate mode).
+ * elem: NNAM_ELEM_* of out_hi (out_lo, if given, is the bf16 low half and needs NNAM_ELEM_BF16).  */
 int nnam_peephole_cell(int phase, const float* gx, long long gx_ld, const float* g1, long long g1_ld, const float* p2,
                        long long p2_ld, const float* c_prev, float* c_new, void* out_hi, void* out_lo,
-                       long long out_ld, int n, int hidden, int fast_tanh, void* stream);
+                       long long out_ld, int n, int hidden, int fast_tanh, int elem, void* stream);
 
 /* K3 -- persistent recurrence kernel: one launch runs a whole layer (one or both directions) over a whole shard.
  * Replaces the per-time-step Python loop around L.LSTM / F.lstm (chainer_networks.py:44-62 via
@@ -147,6 +164,7 @@ typedef struct NnamRnnDesc {
   int streams; /* independent batches a CTA group runs concurrently (from nnam_rnn_plan) */
   int nsplit;  /* 1 = bf16 operands, 3 = bf16x3 (needs the _lo buffers) */
   int flags;   /* GRU family: bit 0 = reset gate, bits 1-2 = candidate activation (NNAM_ACT_*) */
+  int elem;    /* NNAM_ELEM_*: element type of w_hi, h_hi, xchg_hi, h0_hi and (nsplit == 1) gx; nsplit == 3 needs BF16 */
   const void* gx[2];   /* per direction: input projection + bias for every packed row, (rows, gx_ld), columns
                           gate-interleaved exactly like Chainer's upward/W rows; fp32 when nsplit == 3, bf16 when
                           nsplit == 1 (in bf16 mode it is the largest HBM stream of a layer) */
@@ -165,10 +183,11 @@ typedef struct NnamRnnDesc {
   void* h_hi;          /* layer output (rows, h_ld) bf16; direction d writes columns [d*H, (d+1)*H) */
   void* h_lo;          /* low halves (bf16x3) or NULL */
   long long h_ld;
-  void* aux_hi;        /* unused (kept for ABI stability): the r*h product travels through the exchange buffer */
-  void* aux_lo;
-  void* xchg_hi;       /* exchange buffer, (n_groups * streams * 4 * batch, H) bf16, zero-initialised scratch: every
-                          CTA of a group publishes its h slice here each step and TMA-loads the whole tile back */
+  void* xchg_hi;       /* exchange buffer, (n_groups * streams * 4 * batch, H) 16-bit, scratch: every CTA of a group
+                          publishes its h slice here each step and TMA-loads the whole tile back.  Contents on entry
+                          are irrelevant: the kernels never read a slot row they have not written in the same launch
+                          (step 0 has no h product; rows beyond the active prefix only feed their own, unused, output
+                          columns) -- tests/test_gpu_recurrent.py poisons it with NaNs to hold them to that */
   void* xchg_lo;       /* low halves (bf16x3) or NULL */
   int n_items;                 /* work items = (batch, direction) pairs, grouped by lane = (CTA group, stream);
                                   inside a lane the items are sorted by direction */
@@ -191,6 +210,8 @@ typedef struct NnamRnnDesc {
 } NnamRnnDesc;
 
 int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream);
+/* sizeof(NnamRnnDesc) as compiled into the library: bindings in other languages check their struct mirror against it. */
+int nnam_rnn_desc_size(void);
 /* CTAs per group, the number of groups the current device can run concurrently for this cell configuration, and
  * (optional, may be NULL) the measured SM cycles per recurrence step, from which the host picks the batch width, and
  * the number of streams (concurrent batches per group) the kernel instance for `batch` slots runs.

@@ -14,7 +14,10 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libnnam_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_cluster.cu", "recurrent_wide.cu", "recurrent_wide_gru.cu", "peephole.cu"]
+SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_wide.cu", "recurrent_wide_gru.cu", "peephole.cu"]
+# measured dead end kept for reference (DSMEM all-gather recurrence); NNAM_WITH_CLUSTER_EXPERIMENT=1 builds it in
+EXPERIMENTAL_SOURCES = ["experimental/recurrent_cluster.cu"]
+ABI_VERSION = 2
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -32,8 +35,13 @@ def _nvcc():
     return "nvcc"
 
 
+def _with_experiments():
+    return os.environ.get("NNAM_WITH_CLUSTER_EXPERIMENT", "0") == "1"
+
+
 def _sources():
-    return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    names = SOURCES + (EXPERIMENTAL_SOURCES if _with_experiments() else [])
+    return [os.path.join(CSRC, s) for s in names if os.path.exists(os.path.join(CSRC, s))]
 
 
 def needs_build():
@@ -54,6 +62,8 @@ def build(force=False, verbose=False):
     objdir = os.path.join(PKG_DIR, "build")
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    if _with_experiments():
+        flags.append("-DNNAM_WITH_CLUSTER_EXPERIMENT")
 
     def compile_one(src):
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
@@ -87,7 +97,7 @@ _SIGNATURES = {
     "nnam_convert_f32": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_longlong, c_int,
                                  c_void_p]),
     "nnam_linear_bias_act": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p,
-                                     c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                      c_void_p]),
     "nnam_head": (c_int, [POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_float, c_int, c_void_p, c_longlong, c_longlong, c_int, c_void_p]),
@@ -97,8 +107,9 @@ _SIGNATURES = {
     "nnam_gather_transform": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                       c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "nnam_peephole_cell": (c_int, [c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,
-                                   c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p]),
+                                   c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_void_p]),
     "nnam_rnn_seq": (c_int, [c_void_p, c_void_p]),
+    "nnam_rnn_desc_size": (c_int, []),
     "nnam_rnn_plan": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int),
                               POINTER(c_int)]),
     "nnam_rnn_solo_step_cycles": (c_int, [c_int, c_int, c_int, c_int, POINTER(c_int)]),
@@ -110,11 +121,11 @@ class RnnDesc(ctypes.Structure):
 
     _fields_ = [
         ("cell", c_int), ("hidden", c_int), ("n_dirs", c_int), ("batch", c_int), ("streams", c_int), ("nsplit", c_int),
-        ("flags", c_int),
+        ("flags", c_int), ("elem", c_int),
         ("gx", c_void_p * 2), ("gx_ld", c_longlong),
         ("w_hi", c_void_p * 2), ("w_lo", c_void_p * 2), ("w_ld", c_longlong),
         ("u_bias", c_void_p * 2),
-        ("h_hi", c_void_p), ("h_lo", c_void_p), ("h_ld", c_longlong), ("aux_hi", c_void_p), ("aux_lo", c_void_p),
+        ("h_hi", c_void_p), ("h_lo", c_void_p), ("h_ld", c_longlong),
         ("xchg_hi", c_void_p), ("xchg_lo", c_void_p),
         ("n_items", c_int), ("item_batch", c_void_p), ("item_dir", c_void_p),
         ("n_groups", c_int), ("group_item_start", c_void_p),
@@ -148,8 +159,10 @@ def lib():
             fn = getattr(handle, name)
             fn.restype = res
             fn.argtypes = args
-        if handle.nnam_abi_version() != 1:
+        if handle.nnam_abi_version() != ABI_VERSION:
             raise NnamError("libnnam_b200.so ABI version mismatch; rebuild")
+        if handle.nnam_rnn_desc_size() != ctypes.sizeof(RnnDesc):
+            raise NnamError("RnnDesc (ctypes) and NnamRnnDesc (include/nnam_b200.h) differ in size; rebuild")
         _lib = handle
     return _lib
 

@@ -88,7 +88,7 @@ int gather_transform(const float* x, long long n_src, int dim, const float* add_
                      long long ldo, int out_kind, cudaStream_t stream);
 int peephole_cell(int phase, const float* gx, long long gx_ld, const float* g1, long long g1_ld, const float* p2,
                   long long p2_ld, const float* c_prev, float* c_new, void* out_hi, void* out_lo, long long out_ld, int n,
-                  int H, int fast, cudaStream_t stream);
+                  int H, int fast, int elem, cudaStream_t stream);
 int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream);
 int rnn_solo_step_cycles(int cell, int hidden, int batch, int nsplit, int* cycles);
 int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles,
@@ -122,9 +122,9 @@ int nnam_convert_f32(const float* src, long long rows, int cols, long long lds, 
 
 int nnam_linear_bias_act(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
                          long long ldw, const float* bias, void* out_hi, void* out_lo, long long ldo, int M, int N,
-                         int K, int act, int out_kind, int nsplit, void* stream) {
+                         int K, int act, int out_kind, int nsplit, int elem, void* stream) {
   return nnam::gemm_bias_act(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, out_hi, out_lo, ldo, M, N, K, act, out_kind,
-                             nsplit, static_cast<cudaStream_t>(stream));
+                             nsplit, elem, static_cast<cudaStream_t>(stream));
 }
 
 int nnam_head(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in,
@@ -154,14 +154,16 @@ int nnam_gather_transform(const float* x, long long n_src, int dim, const float*
 
 int nnam_peephole_cell(int phase, const float* gx, long long gx_ld, const float* g1, long long g1_ld, const float* p2,
                        long long p2_ld, const float* c_prev, float* c_new, void* out_hi, void* out_lo,
-                       long long out_ld, int n, int hidden, int fast_tanh, void* stream) {
+                       long long out_ld, int n, int hidden, int fast_tanh, int elem, void* stream) {
   return nnam::peephole_cell(phase, gx, gx_ld, g1, g1_ld, p2, p2_ld, c_prev, c_new, out_hi, out_lo, out_ld, n, hidden,
-                             fast_tanh, static_cast<cudaStream_t>(stream));
+                             fast_tanh, elem, static_cast<cudaStream_t>(stream));
 }
 
 int nnam_rnn_seq(const NnamRnnDesc* desc, void* stream) {
   return nnam::rnn_seq(desc, static_cast<cudaStream_t>(stream));
 }
+
+int nnam_rnn_desc_size(void) { return static_cast<int>(sizeof(NnamRnnDesc)); }
 
 int nnam_rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* max_groups, int* step_cycles,
                   int* streams) {

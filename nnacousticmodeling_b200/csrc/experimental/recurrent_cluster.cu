@@ -2,7 +2,9 @@
 // exchanged through distributed shared memory.  Opt-in (NNAM_RNN_CLUSTER=1): measured slower than the default L2
 // exchange on B200, see profiles/r01_k3_phase_cycles.md.  Reference semantics as in recurrent.cu
 // (scripts/common/chainer_networks.py:44-62 via predict_folds.py:49-61).
-#include "recurrent_common.cuh"
+// Not part of the default build: add -DNNAM_WITH_CLUSTER_EXPERIMENT and this file (NNAM_WITH_CLUSTER_EXPERIMENT=1 in the
+// environment of nnacousticmodeling_b200._native.build) to compile it in.
+#include "../recurrent_common.cuh"
 
 namespace nnam {
 

@@ -7,12 +7,14 @@
 // recurrent cells.  A and W are bf16, K-major (row-major with K contiguous), exactly the Chainer (out, in)
 // weight layout, so no transposition is ever needed.
 //
-// Precision modes (nsplit):
-//   1  "bf16"   : one pass, A_hi . W_hi
+// Precision modes (nsplit = NNAM_SPLIT_*; elem = NNAM_ELEM_* picks bf16 or fp16 operands for the single-pass mode):
+//   1  "bf16" / "fp16" : one pass, A_hi . W_hi
 //   3  "bf16x3" : fp32-accurate.  A = A_hi + A_lo, W = W_hi + W_lo (each bf16); the kernel accumulates
 //                 A_hi.W_hi + A_hi.W_lo + A_lo.W_hi into the same fp32 TMEM accumulator (the dropped
 //                 A_lo.W_lo term is ~2^-18 relative).  Costs 3 bf16 passes = 1.5 TF32 passes but carries
 //                 16 mantissa bits instead of TF32's 10.
+//   2  A split only (A_hi.W_hi + A_lo.W_hi) and 4  W split only (A_hi.W_hi + A_hi.W_lo): two passes; per-layer
+//                 choices for the bf16 parity study (which operand's rounding flips the frame argmax).
 //
 // Structure: persistent, warp-specialised, one CTA per SM.
 //   warp 0 : TMA producer (one lane)          -- smem ring of STAGES x (A 128x64 + W bn x64) bf16, SWIZZLE_128B
@@ -46,7 +48,9 @@ struct GemmParams {
   int bn;         // tile width: a multiple of the store box width (64 bf16 / 32 fp32 columns), <= 256
   int tiles_m, tiles_n;
   int k_blocks;   // ceil(K / 64)
-  int nsplit;     // 1 or 3
+  int nsplit;     // NNAM_SPLIT_*
+  int passes;     // tensor passes over K: 1, 2 or 3
+  int f16;        // operands (and 16-bit outputs) are fp16 instead of bf16
   int act;        // NNAM_ACT_*
   const float* bias;
 };
@@ -112,14 +116,14 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
-  const int k_iters = p.k_blocks * p.nsplit;
+  const int k_iters = p.k_blocks * p.passes;
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // the dynamic shared window is 1024-byte aligned on sm_100
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
     prefetch_tmap(&tm_w_hi);
     prefetch_tmap(&tm_o_hi);
-    if (p.nsplit > 1) {
+    if (p.passes > 1) {
       prefetch_tmap(&tm_a_lo);
       prefetch_tmap(&tm_w_lo);
     }
@@ -158,9 +162,10 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / p.tiles_n;
       const int n_blk = tile % p.tiles_n;
-      for (int pass = 0; pass < p.nsplit; ++pass) {
-        const CUtensorMap* ma = (pass == 2) ? &tm_a_lo : &tm_a_hi;
-        const CUtensorMap* mw = (pass == 1) ? &tm_w_lo : &tm_w_hi;
+      for (int pass = 0; pass < p.passes; ++pass) {
+        // pass 0: hi.hi;  NNAM_SPLIT_AW: 1 = A_hi.W_lo, 2 = A_lo.W_hi;  NNAM_SPLIT_A: 1 = A_lo.W_hi;  NNAM_SPLIT_W: 1 = A_hi.W_lo
+        const CUtensorMap* ma = (pass == 2 || (pass == 1 && p.nsplit == NNAM_SPLIT_A)) ? &tm_a_lo : &tm_a_hi;
+        const CUtensorMap* mw = (pass == 1 && p.nsplit != NNAM_SPLIT_A) ? &tm_w_lo : &tm_w_hi;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
@@ -182,7 +187,7 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t idesc = make_idesc_bf16_f32(BM, static_cast<uint32_t>(p.bn));
+    const uint32_t idesc = make_idesc_e16_f32(BM, static_cast<uint32_t>(p.bn), p.f16);
     const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(smem_a));
     const uint64_t bdesc0 = make_sw128_kmajor_desc(smem_u32(smem_b));
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -275,6 +280,11 @@ __global__ void __maxnreg__(GEMM_MAX_REGS)
             for (int j = 0; j < 8; ++j)
               chunks[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                      __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else if (OUT_KIND == NNAM_OUT_F16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              chunks[j] = make_uint4(pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
           } else if (o == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -363,14 +373,14 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
   const int pair = blockIdx.x >> 1;
   const int n_pairs = gridDim.x >> 1;
   const int total_tiles = p.tiles_m * p.tiles_n;  // tiles_m counts 256-row blocks here
-  const int k_iters = p.k_blocks * p.nsplit;
+  const int k_iters = p.k_blocks * p.passes;
   const int half_bn = p.bn >> 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
     prefetch_tmap(&tm_w_hi);
     prefetch_tmap(&tm_o_hi);
-    if (p.nsplit > 1) {
+    if (p.passes > 1) {
       prefetch_tmap(&tm_a_lo);
       prefetch_tmap(&tm_w_lo);
     }
@@ -409,9 +419,10 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
       const int n_blk = tile % p.tiles_n;
       const int row_a = m_blk * (2 * BM) + static_cast<int>(rank) * BM;
       const int row_w = n_blk * p.bn + static_cast<int>(rank) * half_bn;
-      for (int pass = 0; pass < p.nsplit; ++pass) {
-        const CUtensorMap* ma = (pass == 2) ? &tm_a_lo : &tm_a_hi;
-        const CUtensorMap* mw = (pass == 1) ? &tm_w_lo : &tm_w_hi;
+      for (int pass = 0; pass < p.passes; ++pass) {
+        // pass 0: hi.hi;  NNAM_SPLIT_AW: 1 = A_hi.W_lo, 2 = A_lo.W_hi;  NNAM_SPLIT_A: 1 = A_lo.W_hi;  NNAM_SPLIT_W: 1 = A_hi.W_lo
+        const CUtensorMap* ma = (pass == 2 || (pass == 1 && p.nsplit == NNAM_SPLIT_A)) ? &tm_a_lo : &tm_a_hi;
+        const CUtensorMap* mw = (pass == 1 && p.nsplit != NNAM_SPLIT_A) ? &tm_w_lo : &tm_w_hi;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
@@ -435,7 +446,7 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t idesc = make_idesc_bf16_f32(2 * BM, static_cast<uint32_t>(p.bn));
+      const uint32_t idesc = make_idesc_e16_f32(2 * BM, static_cast<uint32_t>(p.bn), p.f16);
       const uint64_t adesc0 = make_sw128_kmajor_desc(smem_u32(smem_a));
       const uint64_t bdesc0 = make_sw128_kmajor_desc(smem_u32(smem_b));
       for (int tile = pair; tile < total_tiles; tile += n_pairs) {
@@ -523,6 +534,11 @@ __global__ void __cluster_dims__(2, 1, 1) __maxnreg__(GEMM_MAX_REGS)
             for (int j = 0; j < 8; ++j)
               chunks[j] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                      __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else if (OUT_KIND == NNAM_OUT_F16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              chunks[j] = make_uint4(pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
           } else {
             if (o == 1) {
 #pragma unroll
@@ -583,15 +599,11 @@ static int pick_bn(int n, int box_cols) {
 
 template <int OUT_KIND>
 static int launch_gemm_2sm(const CUtensorMap (&tm)[6], const GemmParams& p, int grid, cudaStream_t stream) {
-  static bool attr_set[64] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_2sm_kernel<OUT_KIND>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES);
-    if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute(2sm)");
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
+  // the attribute is per device and the call is a few hundred ns: set it on every launch rather than caching a flag
+  // that several host threads (one per GPU) would race on
+  cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_2sm_kernel<OUT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       GEMM2_SMEM_BYTES);
+  if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute(2sm)");
   gemm_bias_act_2sm_kernel<OUT_KIND><<<grid, GEMM_THREADS, GEMM2_SMEM_BYTES, stream>>>(tm[0], tm[1], tm[2], tm[3],
                                                                                         tm[4], tm[5], p);
   return check_launch("gemm_bias_act_2sm_kernel");
@@ -600,19 +612,18 @@ static int launch_gemm_2sm(const CUtensorMap (&tm)[6], const GemmParams& p, int 
 // CTA pairs pay off (+1..7 % on the K >= 1024 shapes of the BASELINE configs) once there are enough 256-row tiles to
 // keep every pair busy; NNAM_GEMM_2SM=0 forces the single-CTA kernel (A/B measurements).
 static bool use_2sm(int M, int N, int K) {
-  static int env = -1;
-  if (env < 0) {
+  // function-local statics with initialisers are initialised once, thread-safely (C++11)
+  static const int env = [] {
     const char* v = getenv("NNAM_GEMM_2SM");
-    env = (v != nullptr && v[0] == '0') ? 0 : 1;
-  }
+    return (v != nullptr && v[0] == '0') ? 0 : 1;
+  }();
   // K <= 256 is bound by the output stream in either kernel (80-86 us for a 65,536 x 2048 bf16 output); from K = 512
   // on the pair kernel wins (108.9 vs 123 us) since the accumulator hand-off between the CTAs stopped using
   // cluster-scope release / acquire (MEMBAR.ALL + ERRBAR per epilogue warp and CCTL.IVALL per tile)
-  static int min_k = -1;
-  if (min_k < 0) {
+  static const int min_k = [] {
     const char* v = getenv("NNAM_GEMM_2SM_MINK");  // tuning aid
-    min_k = v != nullptr ? atoi(v) : 384;
-  }
+    return v != nullptr ? atoi(v) : 384;
+  }();
   return env == 1 && M >= 4096 && N >= 128 && K >= min_k;
 }
 
@@ -622,17 +633,11 @@ constexpr int gemm_smem_bytes(int st, int nbox) {
 
 template <int OUT_KIND, int ST, int NBOX>
 static int launch_gemm_variant(const CUtensorMap (&tm)[6], const GemmParams& p, int grid, cudaStream_t stream) {
-  static bool attr_set[64] = {false};
   constexpr int smem = gemm_smem_bytes(ST, NBOX);
   static_assert(smem <= 227 * 1024, "GEMM shared memory over budget");
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel<OUT_KIND, ST, NBOX>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute");
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
+  cudaError_t e = cudaFuncSetAttribute(gemm_bias_act_kernel<OUT_KIND, ST, NBOX>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "gemm: cudaFuncSetAttribute");
   gemm_bias_act_kernel<OUT_KIND, ST, NBOX><<<grid, GEMM_THREADS, smem, stream>>>(tm[0], tm[1], tm[2], tm[3], tm[4],
                                                                                  tm[5], p);
   return check_launch("gemm_bias_act_kernel");
@@ -643,23 +648,28 @@ static int launch_gemm_variant(const CUtensorMap (&tm)[6], const GemmParams& p, 
 // bf16 output), so the output-bound floor is not the number of stores in flight; default off.
 template <int OUT_KIND>
 static int launch_gemm(const CUtensorMap (&tm)[6], const GemmParams& p, int grid, cudaStream_t stream) {
-  static int max_k = -1;
-  if (max_k < 0) {
+  static const int max_k = [] {
     const char* v = getenv("NNAM_GEMM_EPI_MAXK");
-    max_k = v != nullptr ? atoi(v) : 0;
-  }
-  if (p.K * p.nsplit <= max_k) return launch_gemm_variant<OUT_KIND, 3, 4>(tm, p, grid, stream);
+    return v != nullptr ? atoi(v) : 0;
+  }();
+  if (p.K * p.passes <= max_k) return launch_gemm_variant<OUT_KIND, 3, 4>(tm, p, grid, stream);
   return launch_gemm_variant<OUT_KIND, STAGES, 2>(tm, p, grid, stream);
 }
 
 int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
                   long long ldw, const float* bias, void* out_hi, void* out_lo, long long ldo, int M, int N, int K,
-                  int act, int out_kind, int nsplit, cudaStream_t stream) {
+                  int act, int out_kind, int nsplit, int elem, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(NNAM_ERR_ARG, "gemm: empty problem");
-  if (nsplit != 1 && nsplit != 3) return set_error(NNAM_ERR_ARG, "gemm: nsplit must be 1 or 3");
+  if (nsplit < NNAM_SPLIT_NONE || nsplit > NNAM_SPLIT_W)
+    return set_error(NNAM_ERR_ARG, "gemm: nsplit must be one of NNAM_SPLIT_* (1..4)");
+  if (elem != NNAM_ELEM_BF16 && elem != NNAM_ELEM_F16) return set_error(NNAM_ERR_ARG, "gemm: unknown element type %d", elem);
+  if (elem == NNAM_ELEM_F16 && nsplit != NNAM_SPLIT_NONE)
+    return set_error(NNAM_ERR_ARG, "gemm: the hi/lo split passes are defined for bf16 operands only");
+  const bool need_a_lo = nsplit == NNAM_SPLIT_A || nsplit == NNAM_SPLIT_AW;
+  const bool need_w_lo = nsplit == NNAM_SPLIT_W || nsplit == NNAM_SPLIT_AW;
   if (lda % 8 || ldw % 8) return set_error(NNAM_ERR_ARG, "gemm: lda/ldw must be multiples of 8 elements (16 B)");
   if (lda < K || ldw < K) return set_error(NNAM_ERR_ARG, "gemm: leading dimension smaller than K");
-  if (nsplit == 3 && (!a_lo || !w_lo)) return set_error(NNAM_ERR_ARG, "gemm: bf16x3 needs lo operands");
+  if ((need_a_lo && !a_lo) || (need_w_lo && !w_lo)) return set_error(NNAM_ERR_ARG, "gemm: split passes need their lo operands");
   if (out_kind == NNAM_OUT_BF16_SPLIT && !out_lo) return set_error(NNAM_ERR_ARG, "gemm: split output needs out_lo");
   if (ldo < N) return set_error(NNAM_ERR_ARG, "gemm: ldo must be >= N");
   if (out_kind == NNAM_OUT_F32 ? (ldo % 4) : (ldo % 8))
@@ -669,7 +679,7 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
        reinterpret_cast<uintptr_t>(bias)) & 15)
     return set_error(NNAM_ERR_ARG, "gemm: pointers must be 16-byte aligned");
 
-  if (out_kind != NNAM_OUT_F32 && out_kind != NNAM_OUT_BF16 && out_kind != NNAM_OUT_BF16_SPLIT)
+  if (out_kind != NNAM_OUT_F32 && out_kind != NNAM_OUT_BF16 && out_kind != NNAM_OUT_BF16_SPLIT && out_kind != NNAM_OUT_F16)
     return set_error(NNAM_ERR_ARG, "gemm: unknown out_kind %d", out_kind);
   const bool f32_out = out_kind == NNAM_OUT_F32;
   const int box_cols = f32_out ? 32 : 64;
@@ -683,6 +693,8 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
   p.tiles_n = (N + p.bn - 1) / p.bn;
   p.k_blocks = (K + BK - 1) / BK;
   p.nsplit = nsplit;
+  p.passes = nsplit == NNAM_SPLIT_AW ? 3 : (nsplit == NNAM_SPLIT_NONE ? 1 : 2);
+  p.f16 = elem == NNAM_ELEM_F16;
   p.act = act;
   p.bias = bias;
 
@@ -692,13 +704,10 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
   if ((rc = encode_tmap_bf16_2d(&tm[0], a_hi, K, M, lda, BK, BM))) return rc;
   const int w_box_rows = pair ? p.bn / 2 : p.bn;  // a CTA of a pair loads half of the W tile
   if ((rc = encode_tmap_bf16_2d(&tm[2], w_hi, K, N, ldw, BK, w_box_rows))) return rc;
-  if (nsplit == 3) {
-    if ((rc = encode_tmap_bf16_2d(&tm[1], a_lo, K, M, lda, BK, BM))) return rc;
-    if ((rc = encode_tmap_bf16_2d(&tm[3], w_lo, K, N, ldw, BK, w_box_rows))) return rc;
-  } else {
-    tm[1] = tm[0];
-    tm[3] = tm[2];
-  }
+  tm[1] = tm[0];
+  tm[3] = tm[2];
+  if (need_a_lo && (rc = encode_tmap_bf16_2d(&tm[1], a_lo, K, M, lda, BK, BM))) return rc;
+  if (need_w_lo && (rc = encode_tmap_bf16_2d(&tm[3], w_lo, K, N, ldw, BK, w_box_rows))) return rc;
   if ((rc = encode_tmap_2d(&tm[4], out_hi, f32_out, N, M, ldo, box_cols, 32))) return rc;
   if (out_kind == NNAM_OUT_BF16_SPLIT) {
     if ((rc = encode_tmap_2d(&tm[5], out_lo, false, N, M, ldo, box_cols, 32))) return rc;
@@ -713,6 +722,7 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
     switch (out_kind) {
       case NNAM_OUT_F32: return launch_gemm_2sm<NNAM_OUT_F32>(tm, p, grid2, stream);
       case NNAM_OUT_BF16: return launch_gemm_2sm<NNAM_OUT_BF16>(tm, p, grid2, stream);
+      case NNAM_OUT_F16: return launch_gemm_2sm<NNAM_OUT_F16>(tm, p, grid2, stream);
       default: return launch_gemm_2sm<NNAM_OUT_BF16_SPLIT>(tm, p, grid2, stream);
     }
   }
@@ -720,6 +730,7 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
   switch (out_kind) {
     case NNAM_OUT_F32: return launch_gemm<NNAM_OUT_F32>(tm, p, grid, stream);
     case NNAM_OUT_BF16: return launch_gemm<NNAM_OUT_BF16>(tm, p, grid, stream);
+    case NNAM_OUT_F16: return launch_gemm<NNAM_OUT_F16>(tm, p, grid, stream);
     default: return launch_gemm<NNAM_OUT_BF16_SPLIT>(tm, p, grid, stream);
   }
 }

@@ -21,6 +21,6 @@ int encode_tmap_2d(CUtensorMap* m, const void* ptr, bool f32, unsigned long long
 
 int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
                   long long ldw, const float* bias, void* out_hi, void* out_lo, long long ldo, int M, int N, int K,
-                  int act, int out_kind, int nsplit, cudaStream_t stream);
+                  int act, int out_kind, int nsplit, int elem, cudaStream_t stream);
 
 }  // namespace nnam

@@ -35,7 +35,7 @@ struct PeepParams {
   __nv_bfloat16* out_hi;  // phase 0: c' -> columns [H, 2H) of the [h | c] rows; phase 1: h' -> columns [0, H)
   __nv_bfloat16* out_lo;  // low halves (bf16x3 mode) or NULL
   long long out_ld;
-  int n, H, fast;
+  int n, H, fast, f16;
 };
 
 template <int PHASE>
@@ -63,26 +63,28 @@ __global__ void peephole_cell_kernel(const PeepParams p) {
       v = pp_sigmoid(g.w + __ldg(p.p2 + r * p.p2_ld + j), p.fast) * pp_tanh(c, p.fast);
     }
     const long long o = r * p.out_ld + (PHASE == 0 ? p.H : 0) + j;
-    const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-    p.out_hi[o] = hb;
-    if (p.out_lo != nullptr) p.out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(hb));
+    const uint16_t hb = f32_to_e16(v, p.f16);
+    reinterpret_cast<uint16_t*>(p.out_hi)[o] = hb;
+    if (p.out_lo != nullptr) p.out_lo[o] = __float2bfloat16_rn(v - e16_to_f32(hb, 0));
   }
 }
 
 int peephole_cell(int phase, const float* gx, long long gx_ld, const float* g1, long long g1_ld, const float* p2,
                   long long p2_ld, const float* c_prev, float* c_new, void* out_hi, void* out_lo, long long out_ld, int n,
-                  int H, int fast, cudaStream_t stream) {
+                  int H, int fast, int elem, cudaStream_t stream) {
   if (phase != 0 && phase != 1) return set_error(NNAM_ERR_ARG, "peephole: phase must be 0 or 1");
   if (n < 0 || H <= 0) return set_error(NNAM_ERR_ARG, "peephole: bad shape");
   if (n == 0) return NNAM_OK;
   if (!gx || !c_new || !out_hi) return set_error(NNAM_ERR_ARG, "peephole: NULL buffer");
   if (phase == 1 && !p2) return set_error(NNAM_ERR_ARG, "peephole: phase 1 needs P_o c'");
+  if (elem != NNAM_ELEM_BF16 && elem != NNAM_ELEM_F16) return set_error(NNAM_ERR_ARG, "peephole: unknown element type");
+  if (elem == NNAM_ELEM_F16 && out_lo) return set_error(NNAM_ERR_ARG, "peephole: the hi/lo split is bf16 only");
   if (gx_ld % 4 || (g1 && g1_ld % 4) || (reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(g1) & 15))
     return set_error(NNAM_ERR_ARG, "peephole: gate rows must be 16-byte aligned");
   if (gx_ld < 4LL * H || (g1 && g1_ld < 4LL * H) || out_ld < 2LL * H)
     return set_error(NNAM_ERR_ARG, "peephole: leading dimension too small");
   PeepParams p{gx, gx_ld, g1, g1_ld, p2, p2_ld, c_prev, c_new, static_cast<__nv_bfloat16*>(out_hi),
-               static_cast<__nv_bfloat16*>(out_lo), out_ld, n, H, fast};
+               static_cast<__nv_bfloat16*>(out_lo), out_ld, n, H, fast, elem == NNAM_ELEM_F16};
   const long long total = static_cast<long long>(n) * H;
   long long blocks = (total + 255) / 256;
   const long long cap = static_cast<long long>(sm_count()) * 8;

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -176,6 +177,11 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16_f32(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+// Same with the 16-bit element type chosen at run time: f16 != 0 -> A and B are IEEE fp16 (format code 0, 11-bit
+// significand), else bf16 (format code 1, 8-bit significand).  Both run at the same tensor-pipe rate (kind::f16).
+__host__ __device__ constexpr uint32_t make_idesc_e16_f32(uint32_t m, uint32_t n, int f16) {
+  return (1u << 4) | (f16 ? 0u : ((1u << 7) | (1u << 10))) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 
 // ---------------------------------------------------------------- thread-block clusters / DSMEM
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -280,5 +286,27 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// ---- 16-bit element type chosen at run time (NNAM_ELEM_BF16 = 0 / NNAM_ELEM_F16 = 1; kernel-uniform flag).
+// fp16 conversions saturate to the largest finite value instead of overflowing to inf.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_e16x2(float lo, float hi, int f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint16_t f32_to_e16(float v, int f16) {
+  return static_cast<uint16_t>(pack_e16x2(v, 0.0f, f16) & 0xffffu);
+}
+// two packed 16-bit elements -> (low element, high element)
+__device__ __forceinline__ float2 e16x2_to_float2(uint32_t bits, int f16) {
+  if (f16) return __half22float2(*reinterpret_cast<const __half2*>(&bits));
+  return make_float2(__uint_as_float(bits << 16), __uint_as_float(bits & 0xffff0000u));
+}
+__device__ __forceinline__ float e16_to_f32(uint16_t b, int f16) {
+  return f16 ? __half2float(__ushort_as_half(b)) : __uint_as_float(static_cast<uint32_t>(b) << 16);
+}
 
 }  // namespace nnam

@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
   const int unit = rank * (M_ROWS / 4) + (my_row >> 2);  // hidden unit index in [0, H)
   const int gate_col = rank * M_ROWS + my_row;           // column of gx / row of the lateral matrix
   const uint32_t tmem_lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + u_lo;
-  const uint32_t idesc = make_idesc_bf16_f32(M_ROWS, NB);
+  const int f16 = NSPLIT == 1 ? p.f16 : 0;  // the split planes of the fp32-accurate mode are always bf16
+  const uint32_t idesc = make_idesc_e16_f32(M_ROWS, NB, f16);
   const uint32_t h_hi_sa = smem_u32(h_hi_s), h_lo_sa = smem_u32(h_lo_s);
   const uint32_t c_hi_sa = smem_u32(c_hi_s), c_lo_sa = smem_u32(c_lo_s);
   const uint32_t tmem_d2 = tmem_base + static_cast<uint32_t>(S * NB);  // second accumulator of this stream (PEEP)
@@ -353,7 +354,8 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
           if (CELL == NNAM_CELL_LSTM) {
             if (p.c0 != nullptr) st_reg[m] = p.c0[o];
           } else if (CELL == NNAM_CELL_GRU && has_h0) {
-            st_reg[m] = __bfloat162float(p.h0_hi[o]) + (NSPLIT == 3 ? __bfloat162float(p.h0_lo[o]) : 0.0f);
+            st_reg[m] = e16_to_f32(reinterpret_cast<const uint16_t*>(p.h0_hi)[o], f16) +
+                        (NSPLIT == 3 ? __bfloat162float(p.h0_lo[o]) : 0.0f);
           }
         }
       }
@@ -372,16 +374,16 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
           if (NSPLIT == 3)
             dst[j] = __ldg(reinterpret_cast<const float*>(gx) + row * p.gx_ld);
           else
-            dst[j] = __bfloat162float(__ldg(reinterpret_cast<const __nv_bfloat16*>(gx) + row * p.gx_ld));
+            dst[j] = e16_to_f32(__ldg(reinterpret_cast<const uint16_t*>(gx) + row * p.gx_ld), f16);
         }
       };
       // my value for (utterance u, my unit) -> staging tile (utterance-major, UNITS bf16 per row, hi [+ lo] planes)
       auto stage_put = [&](int u, float v) {
-        const __nv_bfloat16 hb = __float2bfloat16_rn(v);
-        reinterpret_cast<__nv_bfloat16*>(stage_hi)[u * UNITS + (my_row >> 2)] = hb;
+        const uint16_t hb = f32_to_e16(v, f16);
+        reinterpret_cast<uint16_t*>(stage_hi)[u * UNITS + (my_row >> 2)] = hb;
         if (NSPLIT == 3)
           reinterpret_cast<__nv_bfloat16*>(stage_lo)[u * UNITS + (my_row >> 2)] =
-              __float2bfloat16_rn(v - __bfloat162float(hb));
+              __float2bfloat16_rn(v - e16_to_f32(hb, 0));
       };
       // staging tile -> rows of `dst` (the layer output / the r*h exchange buffer): 16-byte coalesced stores
       // (dst may be NULL: the r*h product of the GRU reset gate only travels through the exchange buffer)
@@ -696,6 +698,8 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   if (d->batch != 16 && d->batch != 32 && d->batch != 64 && d->batch != 128)
     return set_error(NNAM_ERR_ARG, "rnn: batch must be 16, 32, 64 or 128");
   if (d->nsplit != 1 && d->nsplit != 3) return set_error(NNAM_ERR_ARG, "rnn: nsplit must be 1 or 3");
+  if (d->elem != NNAM_ELEM_BF16 && d->elem != NNAM_ELEM_F16) return set_error(NNAM_ERR_ARG, "rnn: unknown element type %d", d->elem);
+  if (d->elem == NNAM_ELEM_F16 && d->nsplit != 1) return set_error(NNAM_ERR_ARG, "rnn: fp16 operands are a single-pass mode (nsplit 1)");
   if (d->n_items <= 0) return NNAM_OK;
   if (d->nsplit == 3 && (d->h_lo == nullptr)) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs h_lo");
   if (d->h_ld % 8 || d->w_ld % 8) return set_error(NNAM_ERR_ARG, "rnn: h_ld and w_ld must be multiples of 8");
@@ -778,8 +782,6 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   }
   p.h_hi = static_cast<__nv_bfloat16*>(d->h_hi);
   p.h_lo = static_cast<__nv_bfloat16*>(d->h_lo);
-  p.aux_hi = static_cast<__nv_bfloat16*>(d->aux_hi);
-  p.aux_lo = static_cast<__nv_bfloat16*>(d->aux_lo);
   p.xchg_hi = static_cast<__nv_bfloat16*>(d->xchg_hi);
   p.xchg_lo = static_cast<__nv_bfloat16*>(d->xchg_lo);
   if (d->cell == NNAM_CELL_GRU) {
@@ -801,6 +803,7 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   p.c_out = d->c_out;
   p.counters = d->counters;
   p.gru_flags = d->flags;
+  p.f16 = d->elem == NNAM_ELEM_F16;
   p.prof = static_cast<long long*>(d->debug_cycles);
   if (p.h0_hi && d->nsplit == 3 && !p.h0_lo) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs h0_lo with h0_hi");
 

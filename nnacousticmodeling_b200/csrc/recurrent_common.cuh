@@ -27,8 +27,6 @@ struct RnnParams {
   const float* u_bias[2]; // GRU family only
   __nv_bfloat16* h_hi;    // (rows, h_ld); direction d owns columns [d*H, (d+1)*H)
   __nv_bfloat16* h_lo;
-  __nv_bfloat16* aux_hi;  // GRU reset-gate variants: r*h exchange buffer, same shape as h
-  __nv_bfloat16* aux_lo;
   __nv_bfloat16* xchg_hi;  // (lanes * 4 * NB, H): per lane 4 slots of NB rows -- h parity 0/1, r*h parity 0/1
   __nv_bfloat16* xchg_lo;
   const int* item_batch;
@@ -46,6 +44,7 @@ struct RnnParams {
   float* c_out;                // optional final cell state, same shape
   unsigned int* counters;      // one per group, zero on entry
   int gru_flags;
+  int f16;                     // 16-bit element type of w / h / xchg / h0 / (nsplit 1) gx: 0 = bf16, 1 = fp16
   long long* prof;             // optional: 8 cycle accumulators per CTA (thread 0), phases of a step
 };
 
@@ -100,10 +99,17 @@ __device__ __forceinline__ uint32_t sw128_offset(int r, int c16) {
 }
 
 
-// host-side pieces shared by the two translation units
+// host-side pieces shared by the translation units
+#ifdef NNAM_WITH_CLUSTER_EXPERIMENT  // csrc/experimental/recurrent_cluster.cu (DSMEM all-gather; measured slower, not built by default)
 size_t rnn_cluster_smem_bytes(int nb, int hidden);
 int rnn_cluster_groups(int cell, int hidden, int batch, int nsplit);
 int rnn_cluster_launch(const RnnTmaps& tm, const RnnParams& p, int G, int hidden, cudaStream_t stream);
+#else
+inline int rnn_cluster_groups(int, int, int, int) { return 0; }
+inline int rnn_cluster_launch(const RnnTmaps&, const RnnParams&, int, int, cudaStream_t) {
+  return set_error(NNAM_ERR_UNSUPPORTED, "rnn: built without the cluster experiment");
+}
+#endif
 // recurrent_wide.cu: LSTM / bf16 / 128 slots per batch
 bool rnn_wide_applies(int cell, int hidden, int batch, int nsplit);
 int rnn_wide_launch(const RnnTmaps& tm, const RnnParams& p, int hidden, cudaStream_t stream);

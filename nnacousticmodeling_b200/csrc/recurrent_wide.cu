@@ -84,7 +84,8 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_mine = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * 32);
-  const uint32_t idesc = make_idesc_bf16_f32(NB, M_ROWS);  // M = utterances, N = gate rows
+  const int f16 = p.f16;
+  const uint32_t idesc = make_idesc_e16_f32(NB, M_ROWS, f16);  // M = utterances, N = gate rows
 
   const bool prof_on = p.prof != nullptr && tid == 64;  // a thread that is neither the producer nor the MMA issuer
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -230,12 +231,12 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1)
 
         // ---- gates and cell update for my 8 units (chainer F.lstm), h to the exchange slot and the layer output
         if (active) {
-          const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(gxr);
+          const uint32_t* g2 = reinterpret_cast<const uint32_t*>(gxr);
           uint32_t hp[4];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float2 ga = __bfloat1622float2(g2[2 * j]);      // (a, i) pre-activations from the input projection
-            const float2 gf = __bfloat1622float2(g2[2 * j + 1]);  // (f, o)
+            const float2 ga = e16x2_to_float2(g2[2 * j], f16);      // (a, i) pre-activations from the input projection
+            const float2 gf = e16x2_to_float2(g2[2 * j + 1], f16);  // (f, o)
             const float a = tanh_fast(acc[4 * j] + ga.x);
             const float ig = wide_sigmoid(acc[4 * j + 1] + ga.y);
             const float fg = wide_sigmoid(acc[4 * j + 2] + gf.x);
@@ -243,9 +244,9 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1)
             c_reg[j] = fmaf(a, ig, fg * c_reg[j]);
             const float h_new = og * tanh_fast(c_reg[j]);
             if (j & 1)
-              hp[j >> 1] |= static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(h_new))) << 16;
+              hp[j >> 1] |= static_cast<uint32_t>(f32_to_e16(h_new, f16)) << 16;
             else
-              hp[j >> 1] = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(h_new)));
+              hp[j >> 1] = static_cast<uint32_t>(f32_to_e16(h_new, f16));
           }
           const uint4 hv = make_uint4(hp[0], hp[1], hp[2], hp[3]);
           const long long xoff = (static_cast<long long>(group * 4 + (s & 1)) * NB + u) * H + rank * UNITS + sub * 8;
@@ -375,7 +376,8 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(stream * 128);
   const uint32_t tmem_mine = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * COLS);
-  const uint32_t idesc = make_idesc_bf16_f32(NB, M_ROWS);
+  const int f16 = p.f16;
+  const uint32_t idesc = make_idesc_e16_f32(NB, M_ROWS, f16);
 
   const bool prof_on = p.prof != nullptr && tid == 64;
   long long prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -538,8 +540,8 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             // columns [unit-major, gate-minor]: 2 words (a, i), (f, o) per unit
-            const float2 ga = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gxr[2 * half + (j >> 2)][(2 * j) & 7]));
-            const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gxr[2 * half + (j >> 2)][(2 * j + 1) & 7]));
+            const float2 ga = e16x2_to_float2(gxr[2 * half + (j >> 2)][(2 * j) & 7], f16);
+            const float2 gf = e16x2_to_float2(gxr[2 * half + (j >> 2)][(2 * j + 1) & 7], f16);
             const float a = tanh_fast(acc[4 * j] + ga.x);
             const float ig = wide_sigmoid(acc[4 * j + 1] + ga.y);
             const float fg = wide_sigmoid(acc[4 * j + 2] + gf.x);
@@ -547,7 +549,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
             float& c = c_reg[half * 8 + j];
             c = fmaf(a, ig, fg * c);
             const float h_new = og * tanh_fast(c);
-            const uint32_t hb = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(h_new)));
+            const uint32_t hb = static_cast<uint32_t>(f32_to_e16(h_new, f16));
             if (j & 1)
               hp[half * 4 + (j >> 1)] |= hb << 16;
             else

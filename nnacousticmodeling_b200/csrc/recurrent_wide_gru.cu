@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(GW_THREADS, 1)
   const uint32_t tmem_acc = tmem_base + static_cast<uint32_t>(stream * 128);
   // my lane quarter, my 16 units inside a 32-column gate block
   const uint32_t tmem_mine = tmem_acc + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(sub * 16);
-  const uint32_t idesc1 = make_idesc_bf16_f32(NB, 64);  // pass 1: [z | r] or [z | cand]
-  const uint32_t idesc2 = make_idesc_bf16_f32(NB, 32);  // pass 2: cand block on r*h
+  const int f16 = p.f16;
+  const uint32_t idesc1 = make_idesc_e16_f32(NB, 64, f16);  // pass 1: [z | r] or [z | cand]
+  const uint32_t idesc2 = make_idesc_e16_f32(NB, 32, f16);  // pass 2: cand block on r*h
   const int act_kind = (p.gru_flags >> 1) & 3;
 
   const bool prof_on = p.prof != nullptr && tid == 64;
@@ -247,8 +248,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1)
           }
         };
         auto gxv = [&](int g, int j) -> float {  // pre-activation of gate block g, my unit j, from the projection
-          const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(&gxr[g][j >> 1]);
-          return (j & 1) ? __high2float(v) : __low2float(v);
+          const float2 v = e16x2_to_float2(gxr[g][j >> 1], f16);
+          return (j & 1) ? v.y : v.x;
         };
         if (s == 0 || sw >= 2) load_gx();
         PROF_MARK(0);
@@ -283,7 +284,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1)
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
                 const float r = gw_sigmoid(__uint_as_float(r16[j]) + gxv(1, j));
-                const uint32_t v = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(r * h_reg[j])));
+                const uint32_t v = static_cast<uint32_t>(f32_to_e16(r * h_reg[j], f16));
                 if (j & 1)
                   rh[j >> 1] |= v << 16;
                 else
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1)
           for (int j = 0; j < 16; ++j) {
             const float h_new = fmaf(z[j], hb[j], (1.0f - z[j]) * h_reg[j]);
             h_reg[j] = h_new;
-            const uint32_t v = static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(h_new)));
+            const uint32_t v = static_cast<uint32_t>(f32_to_e16(h_new, f16));
             if (j & 1)
               hp[j >> 1] |= v << 16;
             else

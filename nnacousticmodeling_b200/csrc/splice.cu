@@ -17,6 +17,12 @@
 
 namespace nnam {
 
+// the "hi" plane of a 16-bit output: fp16 for NNAM_OUT_F16, bf16 for NNAM_OUT_BF16 / NNAM_OUT_BF16_SPLIT
+template <int OUT_KIND>
+__device__ __forceinline__ uint32_t pack_hi(float a, float b) {
+  return OUT_KIND == NNAM_OUT_F16 ? pack_f16x2(a, b) : pack_bf16x2(a, b);
+}
+
 constexpr int SPLICE_TILE_F = 64;
 constexpr int SPLICE_THREADS = 256;
 
@@ -216,8 +222,8 @@ __global__ void __launch_bounds__(SPLICE_THREADS) splice_transform_kernel(const 
       __nv_bfloat16* dh = out_hi + static_cast<long long>(r_first) * p.ldo + c;
       __nv_bfloat16* dl = OUT_KIND == NNAM_OUT_BF16_SPLIT ? out_lo + static_cast<long long>(r_first) * p.ldo + c : nullptr;
       auto emit = [&](const float4& v0, const float4& v1) {
-        *reinterpret_cast<uint4*>(dh) = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w),
-                                                   pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+        *reinterpret_cast<uint4*>(dh) = make_uint4(pack_hi<OUT_KIND>(v0.x, v0.y), pack_hi<OUT_KIND>(v0.z, v0.w),
+                                                   pack_hi<OUT_KIND>(v1.x, v1.y), pack_hi<OUT_KIND>(v1.z, v1.w));
         dh += row_step;
         if (OUT_KIND == NNAM_OUT_BF16_SPLIT) {
           *reinterpret_cast<uint4*>(dl) = make_uint4(
@@ -371,8 +377,8 @@ __global__ void __launch_bounds__(STREAM_THREADS) splice_stream_kernel(const Spl
                               ? static_cast<__nv_bfloat16*>(p.out_lo) + (tf0 - p.f0 + r_first) * p.ldo + c
                               : nullptr;
       auto emit = [&](const float4& v0, const float4& v1) {
-        *reinterpret_cast<uint4*>(dh) = make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w),
-                                                   pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+        *reinterpret_cast<uint4*>(dh) = make_uint4(pack_hi<OUT_KIND>(v0.x, v0.y), pack_hi<OUT_KIND>(v0.z, v0.w),
+                                                   pack_hi<OUT_KIND>(v1.x, v1.y), pack_hi<OUT_KIND>(v1.z, v1.w));
         dh += row_step;
         if (OUT_KIND == NNAM_OUT_BF16_SPLIT) {
           *reinterpret_cast<uint4*>(dl) = make_uint4(
@@ -458,10 +464,12 @@ static int launch_splice_stream(const SpliceParams& p_in, cudaStream_t stream) {
   }
   const size_t smem = splice_stream_smem(p, p.tile_f);
   if (smem > 100 * 1024) return -1;  // caller falls back to the tile-per-CTA kernel
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(splice_stream_kernel<OUT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_set = true;
+  // per-device attribute: set on every launch (cheap) rather than behind a process-wide flag, which left every
+  // device but the first without the opt-in when predict(gpu=[0, 1, ...]) runs one host thread per GPU
+  if (cudaFuncSetAttribute(splice_stream_kernel<OUT_KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    return -1;
   }
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, splice_stream_kernel<OUT_KIND>, STREAM_THREADS, smem) !=
@@ -577,9 +585,10 @@ int splice_transform(const float* x, long long x_row0, long long x_rows, long lo
       return launch_splice<NNAM_OUT_F32>(p, vec, stream);
     }
     case NNAM_OUT_BF16:
+    case NNAM_OUT_F16:
     case NNAM_OUT_BF16_SPLIT: {
       if (ldo % 8 || (reinterpret_cast<uintptr_t>(out_hi) & 15))
-        return set_error(NNAM_ERR_ARG, "splice: bf16 output needs ldo %% 8 == 0 and a 16-byte aligned buffer");
+        return set_error(NNAM_ERR_ARG, "splice: 16-bit output needs ldo %% 8 == 0 and a 16-byte aligned buffer");
       if (out_kind == NNAM_OUT_BF16_SPLIT) {
         if (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 15))
           return set_error(NNAM_ERR_ARG, "splice: split output needs an aligned out_lo");
@@ -588,6 +597,13 @@ int splice_transform(const float* x, long long x_row0, long long x_rows, long lo
           if (rc >= 0) return rc;
         }
         return launch_splice<NNAM_OUT_BF16_SPLIT>(p, aligned_in, stream);
+      }
+      if (out_kind == NNAM_OUT_F16) {
+        if (aligned_in && splice_stream_applies(p)) {
+          const int rc = launch_splice_stream<NNAM_OUT_F16>(p, stream);
+          if (rc >= 0) return rc;
+        }
+        return launch_splice<NNAM_OUT_F16>(p, aligned_in, stream);
       }
       if (aligned_in && splice_stream_applies(p)) {
         const int rc = launch_splice_stream<NNAM_OUT_BF16>(p, stream);
@@ -639,7 +655,7 @@ __global__ void gather_transform_kernel(const float* __restrict__ x, int dim, co
     } else {
       uint32_t h[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      for (int j = 0; j < 4; ++j) h[j] = pack_hi<OUT_KIND>(v[2 * j], v[2 * j + 1]);
       reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out_hi_v) + r * ldo)[c >> 3] =
           make_uint4(h[0], h[1], h[2], h[3]);
       if (OUT_KIND == NNAM_OUT_BF16_SPLIT) {
@@ -678,6 +694,10 @@ int gather_transform(const float* x, long long n_src, int dim, const float* add_
       gather_transform_kernel<NNAM_OUT_BF16><<<g, 256, 0, stream>>>(x, dim, add_shift, rescale, ivec, ivec_dim,
                                                                    row_map, n_rows, out_hi, out_lo, ldo, n_src);
       break;
+    case NNAM_OUT_F16:
+      gather_transform_kernel<NNAM_OUT_F16><<<g, 256, 0, stream>>>(x, dim, add_shift, rescale, ivec, ivec_dim,
+                                                                  row_map, n_rows, out_hi, out_lo, ldo, n_src);
+      break;
     case NNAM_OUT_BF16_SPLIT:
       if (!out_lo || (reinterpret_cast<uintptr_t>(out_lo) & 15)) return set_error(NNAM_ERR_ARG, "gather: out_lo");
       gather_transform_kernel<NNAM_OUT_BF16_SPLIT><<<g, 256, 0, stream>>>(x, dim, add_shift, rescale, ivec, ivec_dim,
@@ -691,7 +711,7 @@ int gather_transform(const float* x, long long n_src, int dim, const float* add_
 
 // ---------------------------------------------------------------------------------------------------
 // fp32 -> bf16 / bf16 split staging of weights and pre-spliced inputs (8 elements per thread).
-template <bool SPLIT>
+template <int OUT_KIND>
 __global__ void convert_f32_kernel(const float* __restrict__ src, long long rows, int cols, long long lds,
                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, long long ldd) {
   const long long vpr = ldd >> 3;
@@ -705,9 +725,9 @@ __global__ void convert_f32_kernel(const float* __restrict__ src, long long rows
     for (int j = 0; j < 8; ++j) v[j] = (c + j < cols) ? __ldg(src + r * lds + c + j) : 0.0f;
     uint32_t h[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) h[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    for (int j = 0; j < 4; ++j) h[j] = pack_hi<OUT_KIND>(v[2 * j], v[2 * j + 1]);
     reinterpret_cast<uint4*>(hi + r * ldd)[c >> 3] = make_uint4(h[0], h[1], h[2], h[3]);
-    if (SPLIT) {
+    if (OUT_KIND == NNAM_OUT_BF16_SPLIT) {
       uint32_t l[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -728,13 +748,16 @@ int convert_f32(const float* src, long long rows, int cols, long long lds, void*
   if (blocks > cap) blocks = cap;
   if (out_kind == NNAM_OUT_BF16_SPLIT) {
     if (!dst_lo || (reinterpret_cast<uintptr_t>(dst_lo) & 15)) return set_error(NNAM_ERR_ARG, "convert: dst_lo");
-    convert_f32_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+    convert_f32_kernel<NNAM_OUT_BF16_SPLIT><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
         src, rows, cols, lds, static_cast<__nv_bfloat16*>(dst_hi), static_cast<__nv_bfloat16*>(dst_lo), ldd);
   } else if (out_kind == NNAM_OUT_BF16) {
-    convert_f32_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+    convert_f32_kernel<NNAM_OUT_BF16><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+        src, rows, cols, lds, static_cast<__nv_bfloat16*>(dst_hi), nullptr, ldd);
+  } else if (out_kind == NNAM_OUT_F16) {
+    convert_f32_kernel<NNAM_OUT_F16><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
         src, rows, cols, lds, static_cast<__nv_bfloat16*>(dst_hi), nullptr, ldd);
   } else {
-    return set_error(NNAM_ERR_ARG, "convert: out_kind must be BF16 or BF16_SPLIT");
+    return set_error(NNAM_ERR_ARG, "convert: out_kind must be BF16, F16 or BF16_SPLIT");
   }
   return check_launch("convert_f32_kernel");
 }

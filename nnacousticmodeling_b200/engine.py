@@ -18,9 +18,66 @@ import torch
 
 from . import ops
 from ._native import NnamError
-from .ops import OUT_BF16, OUT_BF16_SPLIT, OUT_F32, round_up
+from .ops import (ELEM_BF16, ELEM_F16, OUT_BF16, OUT_BF16_SPLIT, OUT_F16, OUT_F32, SPLIT_A, SPLIT_AW, SPLIT_NONE,
+                  SPLIT_W, round_up)
 
 DEFAULT_CHUNK = 65536
+
+
+class Precision:
+    """Parsed ``model.precision``.
+
+    ``"fp32"``  bf16x3 error-compensated tensor-core GEMMs (<= 1e-3 of the fp32 reference), every operand as a bf16
+                hi/lo pair;
+    ``"bf16"``  single-pass bf16 operands (8-bit significand);
+    ``"fp16"``  single-pass IEEE fp16 operands (11-bit significand, saturating conversions): same tensor-pipe rate as
+                bf16 with an 8x smaller rounding error per operand -- the single-pass mode that meets north_star's
+                >= 99.5 % frame-argmax agreement on the flat logits of random-init nets (DESIGN.md section 3);
+    ``"bf16+a[:layers][+w[:layers]]"``  (MLP only) bf16 with the ACTIVATIONS (``a``) and / or WEIGHTS (``w``) of the
+                listed Linear layers carried as hi/lo pairs, i.e. one extra tensor pass each -- the per-layer parity study
+                of DESIGN.md.  Layers are numbered 0..L-1 (hidden) and L or -1 (output), separated by ',' or '/';
+                no list = every layer.
+    """
+
+    def __init__(self, spec):
+        parts = str(spec).split("+")
+        self.spec, self.base = str(spec), parts[0]
+        if self.base not in ("fp32", "bf16", "fp16"):
+            raise NnamError(f"precision must be 'fp32', 'bf16', 'fp16' or 'bf16+a[:l,..][+w[:l,..]]' (got {spec!r})")
+        self.split = self.base == "fp32"
+        self.elem = ELEM_F16 if self.base == "fp16" else ELEM_BF16
+        self.tdt = ops.E16[self.elem]
+        self.out16 = OUT_F16 if self.base == "fp16" else OUT_BF16
+        self.act_kind = OUT_BF16_SPLIT if self.split else self.out16
+        self.fast_math = not self.split  # MUFU tanh in the 16-bit modes, tanhf in the fp32-accurate mode
+        self._sel = {}
+        for part in parts[1:]:
+            which, _, arg = part.partition(":")
+            if self.base != "bf16" or which not in ("a", "w"):
+                raise NnamError(f"precision {spec!r}: per-layer splits are '+a[:layers]' / '+w[:layers]' on 'bf16'")
+            self._sel[which] = None if arg in ("", "all") else frozenset(int(t) for t in arg.replace("/", ",").split(","))
+        self.per_layer = bool(self._sel)
+
+    def _has(self, which, l, n_linear):
+        if which not in self._sel:
+            return False
+        sel = self._sel[which]
+        return sel is None or l in sel or (l - n_linear) in sel
+
+    def a_split(self, l, n_linear):
+        """Does Linear layer ``l`` (of ``n_linear``, the last one being the output layer) read split activations?"""
+        return self.split or self._has("a", l, n_linear)
+
+    def w_split(self, l, n_linear):
+        return self.split or self._has("w", l, n_linear)
+
+    def nsplit(self, l, n_linear):
+        a, w = self.a_split(l, n_linear), self.w_split(l, n_linear)
+        return SPLIT_AW if (a and w) else (SPLIT_A if a else (SPLIT_W if w else SPLIT_NONE))
+
+    def in_kind(self, l, n_linear):
+        """Output kind the PRODUCER of layer ``l``'s input must emit."""
+        return OUT_BF16_SPLIT if self.a_split(l, n_linear) else self.out16
 
 
 def _device(dev):
@@ -50,20 +107,22 @@ def _as_host_tensor(a):
 # packed parameters
 # ------------------------------------------------------------------------------------------
 class LinearDev:
-    """One Linear layer on a device: bf16 (hi[, lo]) K-major weights + fp32 bias."""
+    """One Linear layer on a device: 16-bit (hi[, bf16 lo]) K-major weights + fp32 bias."""
 
-    def __init__(self, w, b, device, split):
+    def __init__(self, w, b, device, split, elem=ELEM_BF16):
         w = np.ascontiguousarray(w, dtype=np.float32)
         self.n, self.k = w.shape
-        kind = OUT_BF16_SPLIT if split else OUT_BF16
+        kind = OUT_BF16_SPLIT if split else (OUT_F16 if elem == ELEM_F16 else OUT_BF16)
         wd = torch.from_numpy(w).to(device)
         self.w_hi, self.w_lo = ops.convert_f32(wd, kind)
         self.bias = None if b is None else torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(device)
-        self.split = split
+        self.split, self.elem = split, elem
 
-    def __call__(self, a_hi, a_lo, rows, act, out_kind, out=None):
+    def __call__(self, a_hi, a_lo, rows, act, out_kind, out=None, nsplit=None):
+        if nsplit is None:
+            nsplit = SPLIT_AW if self.split else SPLIT_NONE
         return ops.linear_bias_act(a_hi, a_lo, self.w_hi, self.w_lo, self.bias, rows, self.n, self.k, act=act,
-                                   out_kind=out_kind, nsplit=3 if self.split else 1, out=out)
+                                   out_kind=out_kind, nsplit=nsplit, out=out, elem=self.elem)
 
 
 class Workspace:
@@ -114,15 +173,22 @@ class Plan:
 
     def __init__(self, model, device):
         self.device = device
-        self.split = model.precision == "fp32"
-        self.act_kind = OUT_BF16_SPLIT if self.split else OUT_BF16
+        self.prec = prec = Precision(model.precision)
+        self.split = prec.split          # every operand is a bf16 hi/lo pair (fp32-accurate mode)
+        self.elem, self.tdt = prec.elem, prec.tdt
+        self.act_kind = prec.act_kind    # what producers of GEMM operands emit (first-layer input: see in_kind)
+        self.in_kind = prec.act_kind
         self.ws = Workspace(device)
         p = model.params
+        if prec.per_layer and model.network != "ff":
+            raise NnamError(f"precision {prec.spec!r}: per-layer splits are implemented for the MLP ('ff') only")
         with torch.cuda.device(device):
             if model.network == "ff":
-                self.layers = [LinearDev(p[f"layer_{l}/W"], p[f"layer_{l}/b"], device, self.split)
+                n_lin = model.layers + 1
+                self.in_kind = prec.in_kind(0, n_lin)
+                self.layers = [LinearDev(p[f"layer_{l}/W"], p[f"layer_{l}/b"], device, prec.w_split(l, n_lin), prec.elem)
                                for l in range(model.layers)]
-                self.out = LinearDev(p["out/W"], p["out/b"], device, self.split)
+                self.out = LinearDev(p["out/W"], p["out/b"], device, prec.w_split(model.layers, n_lin), prec.elem)
             elif model.network == "tdnn":
                 from . import tdnn_engine
                 tdnn_engine.build_plan(self, model)
@@ -132,16 +198,27 @@ class Plan:
             torch.cuda.current_stream().synchronize()
 
 
+_plan_lock = threading.Lock()
+
+
 def get_plan(model, device):
+    """Packed parameters of ``model`` on ``device`` (built on first use).  run_sharded() calls this from one host
+    thread per device on the same model: creation and the cache update happen under a lock, so no thread can drop
+    another device's freshly built plan or iterate the dict while it changes."""
     device = _device(device)
     key = (device.index, model.precision, model._version)
     plan = model._plans.get(key)
-    if plan is None:
-        if not model.params:
-            raise NnamError(f"{type(model).__name__} has no parameters: load_npz() or init_params() first")
-        plan = Plan(model, device)
-        model._plans = {k: v for k, v in model._plans.items() if k[2] == model._version}
-        model._plans[key] = plan
+    if plan is not None:
+        return plan
+    with _plan_lock:
+        plan = model._plans.get(key)
+        if plan is None:
+            if not model.params:
+                raise NnamError(f"{type(model).__name__} has no parameters: load_npz() or init_params() first")
+            plan = Plan(model, device)
+            plans = {k: v for k, v in model._plans.items() if k[2] == model._version}
+            plans[key] = plan
+            model._plans = plans
     return plan
 
 
@@ -154,15 +231,17 @@ def mlp_logits(model, plan, a_hi, a_lo, rows, tag="mlp", ws=None):
     ws = ws or plan.ws
     act = model.activation.name
     cap = a_hi.shape[0]
+    prec, n_lin = plan.prec, len(plan.layers) + 1
     for l, lin in enumerate(plan.layers):
         ld = round_up(lin.n, 16)
-        hi = ws.get(f"act.h{l % 2}.hi", cap, ld, torch.bfloat16)
-        lo = ws.get(f"act.h{l % 2}.lo", cap, ld, torch.bfloat16) if plan.split else None
-        lin(a_hi, a_lo, rows, act, plan.act_kind, out=(hi, lo))
+        kind = prec.in_kind(l + 1, n_lin)  # what the NEXT layer reads
+        hi = ws.get(f"act.h{l % 2}.hi", cap, ld, plan.tdt)
+        lo = ws.get(f"act.h{l % 2}.lo", cap, ld, torch.bfloat16) if kind == OUT_BF16_SPLIT else None
+        lin(a_hi, a_lo, rows, act, kind, out=(hi, lo), nsplit=prec.nsplit(l, n_lin))
         a_hi, a_lo = hi, lo
     ldc = round_up(plan.out.n, 16)
     logits = ws.get(f"{tag}.logits", cap, ldc, torch.float32)
-    plan.out(a_hi, a_lo, rows, "identity", OUT_F32, out=(logits, None))
+    plan.out(a_hi, a_lo, rows, "identity", OUT_F32, out=(logits, None), nsplit=prec.nsplit(n_lin - 1, n_lin))
     return logits
 
 
@@ -196,7 +275,7 @@ def call_model(model, x):
             logits = recurrent_engine.step(model, plan, xd)
         else:
             rows = xd.shape[0]
-            a_hi, a_lo = ops.convert_f32(xd.contiguous(), plan.act_kind)
+            a_hi, a_lo = ops.convert_f32(xd.contiguous(), plan.in_kind)
             logits = ff_logits(model, plan, a_hi, a_lo, rows, "call")
             logits = logits[:rows, :model.n_out].clone()
         if is_np:
@@ -323,8 +402,10 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         if have != d_in:
             raise NnamError(f"model expects {d_in} inputs per frame, the data provides {have}")
         ld_in = round_up(d_in, 8)
-        a_bufs = [(ws.get("ff.a.hi", chunk, ld_in, torch.bfloat16),
-                   ws.get("ff.a.lo", chunk, ld_in, torch.bfloat16) if plan0.split else None)]
+        if any(p.prec.spec != plan0.prec.spec for p in plans):
+            raise NnamError("ensemble members must use the same precision mode")
+        a_bufs = [(ws.get("ff.a.hi", chunk, ld_in, plan0.tdt),
+                   ws.get("ff.a.lo", chunk, ld_in, torch.bfloat16) if plan0.in_kind == OUT_BF16_SPLIT else None)]
         out_dev = None if out_on_device else [ws.get(f"ff.out{i}", chunk, n_out, torch.float32) for i in range(2)]
         # Three streams: `main` runs splice + the GEMM stack of chunk i; `aux` runs the HBM-bound head of chunk i-1 in
         # their shadow (the GEMM kernels cap their registers so that one head CTA fits next to a GEMM CTA on every SM);
@@ -343,11 +424,11 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
             if uploaded:
                 main.wait_event(uploaded[ci])
             if presliced:
-                ops.convert_f32(x_dev[c0 - lo:c1 - lo], plan0.act_kind, ldd=ld_in, out=(a_hi, a_lo))
+                ops.convert_f32(x_dev[c0 - lo:c1 - lo], plan0.in_kind, ldd=ld_in, out=(a_hi, a_lo))
             else:
                 ops.splice_transform(x_dev, n_total, splice, add, mul,
                                      None if iv_dev is None else iv_dev[c0 - iv0:c1 - iv0], f0=c0, f1=c1, x_row0=lo,
-                                     out_kind=plan0.act_kind, ldo=ld_in, out=(a_hi, a_lo))
+                                     out_kind=plan0.in_kind, ldo=ld_in, out=(a_hi, a_lo))
             if head_done[buf] is not None:
                 main.wait_event(head_done[buf])  # the head of chunk i-2 still reads these logits
             logits = [ff_logits(m, p, a_hi, a_lo, rows, f"ff{k}.{buf}", ws) for k, (m, p) in enumerate(zip(models, plans))]

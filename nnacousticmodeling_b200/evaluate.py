@@ -154,7 +154,7 @@ def evaluateModelTestTri(model, data, offsets, PIP, LMW, ap=None, GPUID=0, testO
 def main(arg_list=None):
     """scripts/common/evaluate.py:53-214 -- same flags and data flow (splice -> transform -> i-vector concat on the
     device, evaluate.py:163-171), model / NNWithRPL construction (:101-138), then evaluateModelTestTri.  Extensions:
-    ``--precision bf16|fp32`` and ``--tmp-dir`` for the .lab directory (the reference hard-codes 'lab')."""
+    ``--precision fp32|fp16|bf16`` and ``--tmp-dir`` for the .lab directory (the reference hard-codes 'lab')."""
     import argparse
 
     from . import functions as F
@@ -194,7 +194,7 @@ def main(arg_list=None):
     parser.add_argument("--fold-network-pattern", default="fold_{0}.npz")
     parser.add_argument("--master-network", default="-")
     parser.add_argument("--no-progress", action="store_true")
-    parser.add_argument("--precision", default=None, choices=["fp32", "bf16"])
+    parser.add_argument("--precision", default=None, help="fp32 | fp16 | bf16 (engine.Precision)")
     parser.add_argument("--tmp-dir", default="lab")
     args = parser.parse_args(list(map(str, arg_list)) if arg_list is not None else None)
 
@@ -225,7 +225,8 @@ def main(arg_list=None):
                 print("Loading fold {} network".format(len(folds)))
                 folds.append(new_net(f))
         rpl = None
-        if args.rpl_model != "-" and not args.no_rpl_layer:
+        # --no-rpl-layer is parsed and never used by the reference (evaluate.py:82,126-131): same here
+        if args.rpl_model != "-":
             rpl = RPL4(num_classes)
             with np.load(str(args.rpl_model)) as z:
                 rpl.load_params({k: z[k] for k in z.files})

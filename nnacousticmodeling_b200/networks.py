@@ -21,10 +21,10 @@ _default_precision = "fp32"
 
 def set_default_precision(mode):
     """'fp32' = bf16x3 error-compensated tensor-core GEMMs (<= 1e-3 of the fp32 reference);
-    'bf16' = single-pass bf16 GEMMs (throughput mode)."""
+    'fp16' / 'bf16' = single-pass 16-bit GEMMs (throughput modes; see engine.Precision for the full grammar)."""
     global _default_precision
-    if mode not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    from .engine import Precision
+    Precision(mode)  # raises NnamError on an unknown mode
     _default_precision = mode
 
 
@@ -330,10 +330,17 @@ class RPL4:
                        "lb": np.full((1, n_out), -20.0, np.float32)}
 
     def load_params(self, params):
-        for k, v in params.items():
-            k = k[len("predictor/"):] if k.startswith("predictor/") else k
-            if k in self.params:
-                self.params[k] = np.asarray(v, np.float32).reshape(1, self.n_out)
+        """Strict, like ``serializers.load_npz`` (a missing parameter is an error there too): an archive that lacks
+        W, b or lb would otherwise silently evaluate with the inert initial values."""
+        got = {(k[len("predictor/"):] if k.startswith("predictor/") else k): v for k, v in params.items()}
+        missing = [k for k in self.params if k not in got]
+        if missing:
+            raise NnamError(f"RPL4: parameter(s) {missing} missing from the archive (has {sorted(got)})")
+        for k in self.params:
+            v = np.asarray(got[k], np.float32)
+            if v.size != self.n_out:
+                raise NnamError(f"RPL4: parameter {k} has {v.size} entries, expected {self.n_out}")
+            self.params[k] = v.reshape(1, self.n_out)
 
     def namedparams(self):
         return dict(self.params)

@@ -10,7 +10,15 @@ from . import _native
 from ._native import NnamError, check
 
 ACT = {"identity": 0, "none": 0, None: 0, "relu": 1, "sigmoid": 2, "tanh": 3}
-OUT_BF16, OUT_BF16_SPLIT, OUT_F32 = 0, 1, 2
+OUT_BF16, OUT_BF16_SPLIT, OUT_F32, OUT_F16 = 0, 1, 2, 3   # NNAM_OUT_*
+ELEM_BF16, ELEM_F16 = 0, 1                                # NNAM_ELEM_*
+SPLIT_NONE, SPLIT_A, SPLIT_AW, SPLIT_W = 1, 2, 3, 4       # NNAM_SPLIT_* (operand passes of K2)
+E16 = {ELEM_BF16: torch.bfloat16, ELEM_F16: torch.float16}
+
+
+def out_dtype(out_kind):
+    """torch dtype of the (hi) output buffer of a kernel asked for ``out_kind``."""
+    return {OUT_F32: torch.float32, OUT_F16: torch.float16}.get(out_kind, torch.bfloat16)
 
 
 # launch accounting (bench.py: gpu_launches, per-kernel CUDA-event timing for the roofline block)
@@ -81,13 +89,14 @@ def splice_transform(x, n_total, splice, add_shift=None, rescale=None, ivec=None
     if ldo is None:
         ldo = cols if out_kind == OUT_F32 else round_up(cols, 8)
     n = f1 - f0
-    dt = torch.float32 if out_kind == OUT_F32 else torch.bfloat16
+    dt = out_dtype(out_kind)
     if out is None:
         hi = torch.empty((n, ldo), dtype=dt, device=x.device)
         lo = torch.empty((n, ldo), dtype=dt, device=x.device) if out_kind == OUT_BF16_SPLIT else None
     else:
         hi, lo = out
-    work = n * (dim * 4 + ivec_dim * 4 + cols * (4 if out_kind == OUT_F32 else (2 if out_kind == OUT_BF16 else 4)))
+    _req(hi, dt, "out")
+    work = n * (dim * 4 + ivec_dim * 4 + cols * (2 if out_kind in (OUT_BF16, OUT_F16) else 4))
     with _Prof("splice", work):
         check(_native.lib().nnam_splice_transform(_ptr(x), x_row0, rows, n_total, dim, splice, _ptr(add_shift),
                                               _ptr(rescale), _ptr(ivec), ivec_dim, f0, f1, _ptr(hi), _ptr(lo),
@@ -96,16 +105,17 @@ def splice_transform(x, n_total, splice, add_shift=None, rescale=None, ivec=None
 
 
 def convert_f32(src, out_kind=OUT_BF16, ldd=None, out=None):
-    """fp32 (rows, cols) -> bf16 hi (and lo) with zero padding up to ldd columns."""
+    """fp32 (rows, cols) -> 16-bit hi (bf16 or fp16; and bf16 lo) with zero padding up to ldd columns."""
     _req(src, torch.float32, "src")
     rows, cols = src.shape
     if ldd is None:
         ldd = round_up(cols, 8)
     if out is None:
-        hi = torch.empty((rows, ldd), dtype=torch.bfloat16, device=src.device)
+        hi = torch.empty((rows, ldd), dtype=out_dtype(out_kind), device=src.device)
         lo = torch.empty((rows, ldd), dtype=torch.bfloat16, device=src.device) if out_kind == OUT_BF16_SPLIT else None
     else:
         hi, lo = out
+    _req(hi, out_dtype(out_kind), "out")
     with _Prof("convert", rows * cols * 4):
         check(_native.lib().nnam_convert_f32(_ptr(src), rows, cols, src.stride(0), _ptr(hi), _ptr(lo), ldd,
                                              out_kind, _stream()))
@@ -113,23 +123,31 @@ def convert_f32(src, out_kind=OUT_BF16, ldd=None, out=None):
 
 
 def linear_bias_act(a_hi, a_lo, w_hi, w_lo, bias, M, N, K, act="identity", out_kind=OUT_BF16, nsplit=1, out=None,
-                    ldo=None):
-    """K2.  out = act(A . W^T + bias).  a_*: (>=M, lda) bf16, w_*: (>=N, ldw) bf16 (K-major)."""
-    for t, n in ((a_hi, "a_hi"), (a_lo, "a_lo"), (w_hi, "w_hi"), (w_lo, "w_lo")):
+                    ldo=None, elem=ELEM_BF16):
+    """K2.  out = act(A . W^T + bias).  a_*: (>=M, lda), w_*: (>=N, ldw) K-major; hi planes in ``elem`` (bf16 / fp16),
+    lo planes bf16.  ``nsplit``: SPLIT_* operand passes."""
+    for t, n in ((a_hi, "a_hi"), (w_hi, "w_hi")):
+        _req(t, E16[elem], n)
+    for t, n in ((a_lo, "a_lo"), (w_lo, "w_lo")):
         _req(t, torch.bfloat16, n)
     _req(bias, torch.float32, "bias")
+    if nsplit in (SPLIT_NONE, SPLIT_W):
+        a_lo = None
+    if nsplit in (SPLIT_NONE, SPLIT_A):
+        w_lo = None
     if ldo is None:
         ldo = round_up(N, 16) if out is None else out[0].stride(0)
-    dt = torch.float32 if out_kind == OUT_F32 else torch.bfloat16
+    dt = out_dtype(out_kind)
     if out is None:
         hi = torch.empty((M, ldo), dtype=dt, device=a_hi.device)
         lo = torch.empty((M, ldo), dtype=dt, device=a_hi.device) if out_kind == OUT_BF16_SPLIT else None
     else:
         hi, lo = out
+    _req(hi, dt, "out")
     with _Prof("gemm", 2.0 * M * N * K):  # ALGORITHMIC flops (one pass, unpadded), whatever nsplit is
         check(_native.lib().nnam_linear_bias_act(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(w_hi), _ptr(w_lo),
                                                  w_hi.stride(0), _ptr(bias), _ptr(hi), _ptr(lo), ldo, M, N, K,
-                                                 ACT[act], out_kind, nsplit, _stream()))
+                                                 ACT[act], out_kind, nsplit, elem, _stream()))
     return hi, lo
 
 
@@ -183,13 +201,14 @@ def gather_transform(x, row_map, add_shift=None, rescale=None, ivec=None, out_ki
     n_rows = row_map.numel()
     if ldo is None:
         ldo = round_up(dim + ivec_dim, 8)
-    dt = torch.float32 if out_kind == OUT_F32 else torch.bfloat16
+    dt = out_dtype(out_kind)
     if out is None:
         hi = torch.empty((n_rows, ldo), dtype=dt, device=x.device)
         lo = torch.empty((n_rows, ldo), dtype=dt, device=x.device) if out_kind == OUT_BF16_SPLIT else None
     else:
         hi, lo = out
-    with _Prof("splice", n_rows * ((dim + ivec_dim) * 4 + (dim + ivec_dim) * (4 if out_kind != OUT_BF16 else 2))):
+    _req(hi, dt, "out")
+    with _Prof("splice", n_rows * ((dim + ivec_dim) * 4 + (dim + ivec_dim) * (2 if out_kind in (OUT_BF16, OUT_F16) else 4))):
         check(_native.lib().nnam_gather_transform(_ptr(x), n_src, dim, _ptr(add_shift), _ptr(rescale), _ptr(ivec),
                                                   ivec_dim, _ptr(row_map), n_rows, _ptr(hi), _ptr(lo), ldo, out_kind,
                                                   _stream()))
@@ -218,10 +237,11 @@ def rnn_seq(desc, flops):
         check(_native.lib().nnam_rnn_seq(ctypes.addressof(desc), _stream()))
 
 
-def peephole_cell(phase, gx, g1, p2, c_prev, c_new, out_hi, out_lo, n, hidden, fast):
+def peephole_cell(phase, gx, g1, p2, c_prev, c_new, out_hi, out_lo, n, hidden, fast, elem=ELEM_BF16):
     """One phase of the peephole-LSTM gate arithmetic on n packed rows (see include/nnam_b200.h)."""
+    _req(out_hi, E16[elem], "out_hi")
     with _Prof("cell", n * hidden * 4 * 8):
         check(_native.lib().nnam_peephole_cell(
             phase, _ptr(gx), gx.stride(0), _ptr(g1), 0 if g1 is None else g1.stride(0), _ptr(p2),
             0 if p2 is None else p2.stride(0), _ptr(c_prev), _ptr(c_new), _ptr(out_hi), _ptr(out_lo), out_hi.stride(0),
-            n, hidden, int(bool(fast)), _stream()))
+            n, hidden, int(bool(fast)), elem, _stream()))

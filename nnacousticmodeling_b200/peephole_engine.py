@@ -36,14 +36,14 @@ def build_plan(plan, model):
     for l in range(model.layers):
         pre = f"layer_{l}/"
         L = PeepLayer()
-        L.upward = LinearDev(p[pre + "upward/W"], p[pre + "upward/b"], dev, split)
+        L.upward = LinearDev(p[pre + "upward/W"], p[pre + "upward/b"], dev, split, plan.elem)
         pmat = np.zeros((4 * h, h), np.float32)  # gate-interleaved rows [a, i, f, o] per unit
         pmat[1::4] = p[pre + "peep_i/W"]
         pmat[2::4] = p[pre + "peep_f/W"]
-        L.w1 = LinearDev(np.concatenate([p[pre + "lateral/W"], pmat], axis=1), None, dev, split)
-        L.w2 = LinearDev(p[pre + "peep_o/W"], None, dev, split)
+        L.w1 = LinearDev(np.concatenate([p[pre + "lateral/W"], pmat], axis=1), None, dev, split, plan.elem)
+        L.w2 = LinearDev(p[pre + "peep_o/W"], None, dev, split, plan.elem)
         plan.peep_layers.append(L)
-    plan.out = LinearDev(p["out/W"], p["out/b"], dev, split)
+    plan.out = LinearDev(p["out/W"], p["out/b"], dev, split, plan.elem)
 
 
 def _step(plan, layer, ws, gx_t, hc_prev, c_prev, hc_t, c_t, n):
@@ -54,12 +54,12 @@ def _step(plan, layer, ws, gx_t, hc_prev, c_prev, hc_t, c_t, n):
     if hc_prev is not None:
         g1 = ws.get("peep.g1", n, 4 * h, torch.float32)
         ops.linear_bias_act(hc_prev[0], hc_prev[1], layer.w1.w_hi, layer.w1.w_lo, None, n, 4 * h, 2 * h,
-                            out_kind=OUT_F32, nsplit=nsplit, out=(g1, None))
-    ops.peephole_cell(0, gx_t, g1, None, c_prev, c_t, hc_t[0], hc_t[1], n, h, not plan.split)
+                            out_kind=OUT_F32, nsplit=nsplit, out=(g1, None), elem=plan.elem)
+    ops.peephole_cell(0, gx_t, g1, None, c_prev, c_t, hc_t[0], hc_t[1], n, h, not plan.split, plan.elem)
     p2 = ws.get("peep.p2", n, h, torch.float32)
     ops.linear_bias_act(hc_t[0][:, h:], None if hc_t[1] is None else hc_t[1][:, h:], layer.w2.w_hi, layer.w2.w_lo, None,
-                        n, h, h, out_kind=OUT_F32, nsplit=nsplit, out=(p2, None))
-    ops.peephole_cell(1, gx_t, g1, p2, None, c_t, hc_t[0], hc_t[1], n, h, not plan.split)
+                        n, h, h, out_kind=OUT_F32, nsplit=nsplit, out=(p2, None), elem=plan.elem)
+    ops.peephole_cell(1, gx_t, g1, p2, None, c_t, hc_t[0], hc_t[1], n, h, not plan.split, plan.elem)
 
 
 def run_layers(model, plan, sched, a_hi, a_lo, rows, ws=None):
@@ -71,7 +71,7 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, ws=None):
     for l, layer in enumerate(plan.peep_layers):
         gx = ws.get("peep.gx", rows, 4 * h, torch.float32)
         layer.upward(a_hi, a_lo, rows, "identity", OUT_F32, out=(gx, None))
-        hc_hi = ws.get(f"peep.hc{l % 2}.hi", rows, 2 * h, torch.bfloat16)
+        hc_hi = ws.get(f"peep.hc{l % 2}.hi", rows, 2 * h, plan.tdt)
         hc_lo = ws.get(f"peep.hc{l % 2}.lo", rows, 2 * h, torch.bfloat16) if plan.split else None
         c = ws.get("peep.c", rows, h, torch.float32)
         for t in range(len(base) - 1):
@@ -102,7 +102,7 @@ def step(model, plan, xd):
     for l, layer in enumerate(plan.peep_layers):
         gx = plan.ws.get("peepstep.gx", B, 4 * h, torch.float32)
         layer.upward(a_hi, a_lo, B, "identity", OUT_F32, out=(gx, None))
-        hc_hi = torch.empty((B, 2 * h), dtype=torch.bfloat16, device=plan.device)
+        hc_hi = torch.empty((B, 2 * h), dtype=plan.tdt, device=plan.device)
         hc_lo = torch.empty((B, 2 * h), dtype=torch.bfloat16, device=plan.device) if plan.split else None
         c = torch.empty((B, h), dtype=torch.float32, device=plan.device)
         prev, c_prev = (None, None) if st is None else st["s"][l]

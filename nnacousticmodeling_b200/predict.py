@@ -100,7 +100,7 @@ def main(arg_list=None):
     parser.add_argument("--fold-output-pattern", default="data_{}.npy")
     parser.add_argument("--fold-network-pattern", default="fold_{}.npz")
     parser.add_argument("--no-progress", action="store_true")
-    parser.add_argument("--precision", default=None, choices=["fp32", "bf16"], help="extension: GEMM precision mode")
+    parser.add_argument("--precision", default=None, help="extension: GEMM precision mode (fp32 | fp16 | bf16, see engine.Precision)")
     args = parser.parse_args(list(map(str, arg_list)) if arg_list is not None else None)
 
     out_file = Path(args.fold_output_dir, args.fold_output_dev or args.fold_output_pattern)

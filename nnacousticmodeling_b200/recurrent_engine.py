@@ -53,7 +53,7 @@ def build_plan(plan, model):
     plan.hidden = h = model.n_units
     plan.rec_layers = []
     plan.gru_flags = 0
-    kind = OUT_BF16_SPLIT if split else OUT_BF16
+    kind = plan.act_kind  # bf16 / fp16 hi plane, or the bf16 hi/lo pair of the fp32-accurate mode
     dirs = ("fwd/", "bwd/") if model.bidirectional else ("",)
 
     def to_dev_bf16(w):
@@ -67,7 +67,7 @@ def build_plan(plan, model):
             L = RecLayer()
             up_w = np.concatenate([p[f"layer_{l}/{d}upward/W"] for d in dirs], axis=0)
             up_b = np.concatenate([p[f"layer_{l}/{d}upward/b"] for d in dirs], axis=0)
-            L.upward = LinearDev(up_w, up_b, dev, split)  # gx for both directions in one GEMM
+            L.upward = LinearDev(up_w, up_b, dev, split, plan.elem)  # gx for both directions in one GEMM
             L.lat = [to_dev_bf16(p[f"layer_{l}/{d}lateral/W"]) for d in dirs]
             L.u_bias = [None for _ in dirs]
             plan.rec_layers.append(L)
@@ -91,7 +91,7 @@ def build_plan(plan, model):
                 ub = _interleave4([p[pre + "U_z/b"][:, None], p[pre + "U_r/b"][:, None] if reset else None,
                                    p[pre + "U/b"][:, None]], h, 1)[:, 0]
                 L.u_bias.append(torch.from_numpy(np.ascontiguousarray(ub)).to(dev))
-            L.upward = LinearDev(np.concatenate(ups, axis=0), np.concatenate(upb, axis=0), dev, split)
+            L.upward = LinearDev(np.concatenate(ups, axis=0), np.concatenate(upb, axis=0), dev, split, plan.elem)
             plan.rec_layers.append(L)
     elif net == "peepholelstm":
         # chainer_networks.py:103-121.  The time-step engine (peephole_engine) always exists: it serves the stateful
@@ -115,7 +115,7 @@ def build_plan(plan, model):
             for l in range(model.layers):
                 pre = f"layer_{l}/"
                 L = RecLayer()
-                L.upward = LinearDev(p[pre + "upward/W"], p[pre + "upward/b"], dev, split)
+                L.upward = LinearDev(p[pre + "upward/W"], p[pre + "upward/b"], dev, split, plan.elem)
                 pblock = _interleave4([None, p[pre + "peep_i/W"], p[pre + "peep_f/W"]], h, h)
                 pblock[3::4] = p[pre + "peep_o/W"]
                 L.lat = [to_dev_bf16(p[pre + "lateral/W"]), to_dev_bf16(pblock)]
@@ -124,7 +124,7 @@ def build_plan(plan, model):
         return
     else:
         raise NnamError(f"network '{net}' is not implemented on the B200 path")
-    plan.out = LinearDev(p["out/W"], p["out/b"], dev, split)
+    plan.out = LinearDev(p["out/W"], p["out/b"], dev, split, plan.elem)
 
 
 def _block32(blocks, h):
@@ -159,9 +159,9 @@ def gru_wide_layers(plan, model):
             ups.append(_block32([p[key(pre, "W", g) + "/W"] for g in names], h))
             upb.append(_block32([p[key(pre, "W", g) + "/b"][:, None] for g in names], h)[:, 0] + ub)
             L.lat.append(ops.convert_f32(torch.from_numpy(_block32([p[key(pre, "U", g) + "/W"] for g in names], h)).to(dev),
-                                         OUT_BF16))
+                                         plan.prec.out16))
             L.u_bias.append(torch.from_numpy(np.ascontiguousarray(ub)).to(dev))
-        L.upward = LinearDev(np.concatenate(ups, axis=0), np.concatenate(upb, axis=0), dev, False)
+        L.upward = LinearDev(np.concatenate(ups, axis=0), np.concatenate(upb, axis=0), dev, False, plan.elem)
         L.gate_cols = len(names) * h
         layers.append(L)
     plan._gru_wide_layers = layers
@@ -511,6 +511,7 @@ def _fill_desc(plan, sched, layer, gx, h_hi, h_lo, nb, h0=None, c0=None, c_out=N
     d.cell, d.hidden, d.n_dirs, d.batch, d.nsplit = plan.cell, H, nd, nb, 3 if plan.split else 1
     d.streams = sched.streams
     d.flags = plan.gru_flags
+    d.elem = plan.elem
     for k in range(nd):
         d.gx[k] = gx.data_ptr() + gx.element_size() * k * getattr(layer, "gate_cols", 4 * H)
         d.w_hi[k] = layer.lat[k][0].data_ptr()
@@ -558,7 +559,7 @@ def _run_layers_mixed(model, plan, sched, a_hi, a_lo, rows, tag, ws):
         ranges.append((row_lo, row_lo + part.n_rows))
         row_lo += part.n_rows
     for l in range(len(plan.rec_layers)):
-        h_hi = ws.get(f"{tag}.h{l % 2}.hi", rows, nd * H, torch.bfloat16)
+        h_hi = ws.get(f"{tag}.h{l % 2}.hi", rows, nd * H, plan.tdt)
         part_layers, part_gx = [], []
         for pi, (part, nb) in enumerate(sched.parts):
             layer = (gru_wide_layers(plan, model) if (plan.cell == CELL_GRU and nb == 128) else plan.rec_layers)[l]
@@ -569,10 +570,10 @@ def _run_layers_mixed(model, plan, sched, a_hi, a_lo, rows, tag, ws):
             gate_cols = getattr(layer, "gate_cols", 4 * H)
             shared = all(((gru_wide_layers(plan, model) if (plan.cell == CELL_GRU and nb2 == 128)
                            else plan.rec_layers)[l]) is layer for _, nb2 in sched.parts)
-            gx = ws.get(f"{tag}.gx16" if shared else f"{tag}.gx16.p{pi}", rows, nd * gate_cols, torch.bfloat16)
+            gx = ws.get(f"{tag}.gx16" if shared else f"{tag}.gx16.p{pi}", rows, nd * gate_cols, plan.tdt)
             r0, r1 = (0, rows) if shared else ranges[pi]
             if r1 > r0:
-                layer.upward(a_hi[r0:r1], None, r1 - r0, "identity", OUT_BF16, out=(gx[r0:r1], None))
+                layer.upward(a_hi[r0:r1], None, r1 - r0, "identity", plan.prec.out16, out=(gx[r0:r1], None))
             part_gx.append(gx)
         ready = torch.cuda.Event()
         ready.record(main)
@@ -580,7 +581,7 @@ def _run_layers_mixed(model, plan, sched, a_hi, a_lo, rows, tag, ws):
             x_rows = part.n_lanes * 4 * nb
             name = f"{tag}.xchg{pi}.hi"
             fresh = ws.buf.get(name) is None or ws.buf[name].numel() < x_rows * H
-            xchg = (ws.get(name, x_rows, H, torch.bfloat16), None)
+            xchg = (ws.get(name, x_rows, H, plan.tdt), None)
             if fresh:
                 xchg[0].zero_()
                 ready.record(main)
@@ -613,10 +614,10 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
             gx = ws.get(f"{tag}.gx", rows, nd * 4 * H, torch.float32)
             layer.upward(a_hi, a_lo, rows, "identity", OUT_F32, out=(gx, None))
         else:
-            gx = ws.get(f"{tag}.gx16", rows, nd * gate_cols, torch.bfloat16)
-            layer.upward(a_hi, a_lo, rows, "identity", OUT_BF16, out=(gx, None))
+            gx = ws.get(f"{tag}.gx16", rows, nd * gate_cols, plan.tdt)
+            layer.upward(a_hi, a_lo, rows, "identity", plan.prec.out16, out=(gx, None))
         slot = l if want_state else l % 2  # a carried state needs every layer's h kept
-        h_hi = ws.get(f"{tag}.h{slot}.hi", rows, nd * H, torch.bfloat16)
+        h_hi = ws.get(f"{tag}.h{slot}.hi", rows, nd * H, plan.tdt)
         h_lo = ws.get(f"{tag}.h{slot}.lo", rows, nd * H, torch.bfloat16) if plan.split else None
         h0 = c0 = c_out = None
         if state_in is not None:
@@ -626,7 +627,7 @@ def run_layers(model, plan, sched, a_hi, a_lo, rows, nb, state_in=None, want_sta
         # exchange buffer: per lane 4 slots (h parity 0/1, r*h parity 0/1) of nb rows x H; zeroed once when it is created
         x_rows = sched.n_lanes * 4 * nb
         fresh = ws.buf.get(f"{tag}.xchg.hi") is None or ws.buf[f"{tag}.xchg.hi"].numel() < x_rows * H
-        xchg = (ws.get(f"{tag}.xchg.hi", x_rows, H, torch.bfloat16),
+        xchg = (ws.get(f"{tag}.xchg.hi", x_rows, H, plan.tdt),
                 ws.get(f"{tag}.xchg.lo", x_rows, H, torch.bfloat16) if plan.split else None)
         if fresh:
             xchg[0].zero_()
@@ -710,7 +711,7 @@ def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, o
 
     d_in = models[0].in_size
     ld_in = round_up(d_in, 8)
-    a_hi = ws.get("rnn.a.hi", rows, ld_in, torch.bfloat16)
+    a_hi = ws.get("rnn.a.hi", rows, ld_in, plan.tdt)
     a_lo = ws.get("rnn.a.lo", rows, ld_in, torch.bfloat16) if split else None
     ops.gather_transform(x_dev, d_src, add, mul, iv_dev, out_kind=plan.act_kind, ldo=ld_in, out=(a_hi, a_lo))
     n_out = models[0].n_out
@@ -766,7 +767,7 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         plans = [get_plan(m, device) for m in models]
         plan = plans[0]
         ws = plan.ws
-        if any(p.split != plan.split for p in plans):
+        if any(p.prec.spec != plan.prec.spec for p in plans):
             raise NnamError("forward_utterances: all ensemble members must use the same precision mode")
         stepwise = plan.cell == CELL_PEEPHOLE and not plan.peep_persistent
 

@@ -44,13 +44,13 @@ def build_plan(plan, model):
     for w in range(w1):
         for j in range(k0):
             full[w * u0:(w + 1) * u0, w + j::win] = w0[:, :, 0, j]
-    plan.tdnn_first = LinearDev(full, np.tile(p["layer_0/b"], w1), dev, split)
+    plan.tdnn_first = LinearDev(full, np.tile(p["layer_0/b"], w1), dev, split, plan.elem)
     plan.tdnn_convs = []
     for l in range(1, model.layers):
         w = p[f"layer_{l}/W"]  # (out, in, 1, k)
         w2 = np.ascontiguousarray(np.transpose(w[:, :, 0, :], (0, 2, 1))).reshape(w.shape[0], -1)  # (out, k*in)
-        plan.tdnn_convs.append(LinearDev(w2, p[f"layer_{l}/b"], dev, split))
-    plan.out = LinearDev(p["out/W"], p["out/b"], dev, split)
+        plan.tdnn_convs.append(LinearDev(w2, p[f"layer_{l}/b"], dev, split, plan.elem))
+    plan.out = LinearDev(p["out/W"], p["out/b"], dev, split, plan.elem)
 
 
 def logits(model, plan, a_hi, a_lo, rows, tag="tdnn", ws=None):
@@ -61,7 +61,7 @@ def logits(model, plan, a_hi, a_lo, rows, tag="tdnn", ws=None):
 
     def buf(l):
         ld = widths[l + 1] * units[l]
-        hi = ws.get(f"act.h{l % 2}.hi", cap, ld, torch.bfloat16)
+        hi = ws.get(f"act.h{l % 2}.hi", cap, ld, plan.tdt)
         lo = ws.get(f"act.h{l % 2}.lo", cap, ld, torch.bfloat16) if plan.split else None
         return hi, lo
 
@@ -74,7 +74,8 @@ def logits(model, plan, a_hi, a_lo, rows, tag="tdnn", ws=None):
         for w in range(widths[l + 1]):
             ops.linear_bias_act(hi[:, w * c:], None if lo is None else lo[:, w * c:], lin.w_hi, lin.w_lo, lin.bias,
                                 rows, lin.n, lin.k, act=act, out_kind=kind, nsplit=3 if plan.split else 1,
-                                out=(nhi[:, w * u:], None if nlo is None else nlo[:, w * u:]), ldo=nhi.stride(0))
+                                out=(nhi[:, w * u:], None if nlo is None else nlo[:, w * u:]), ldo=nhi.stride(0),
+                                elem=plan.elem)
         hi, lo = nhi, nlo
     out = ws.get(f"{tag}.logits", cap, round_up(plan.out.n, 16), torch.float32)
     plan.out(hi, lo, rows, "identity", OUT_F32, out=(out, None))

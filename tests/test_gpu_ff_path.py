@@ -33,13 +33,6 @@ def _agree(a, b):
     return float(np.mean(a.argmax(axis=1) == b.argmax(axis=1)))
 
 
-def _agree_near_tie(got, want, eps=1e-2):
-    """Frame counts as agreeing when the class we pick is within eps of the oracle's best class IN THE
-    ORACLE's own scores (random-init nets have nearly flat logits: top-1/top-2 gaps of ~1e-3 are common)."""
-    rows = np.arange(len(want))
-    return float(np.mean(want[rows, got.argmax(axis=1)] >= want.max(axis=1) - eps))
-
-
 @pytest.mark.parametrize("act", ["relu", "sigmoid", "tanh"])
 def test_predict_ff_cfg1_shape_fp32_mode(nn, golden_dir, act):
     """BASELINE config 1 geometry (440 -> 6x1024 -> 1909) on a small synthetic set, fp32 (bf16x3) mode."""
@@ -64,13 +57,24 @@ def test_predict_ff_cfg2_shape_both_modes(nn, golden_dir):
     want = O.log_softmax(O.mlp_forward(p, feats, 6))
     got = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv)
     assert np.abs(got - want).max() < 1e-3
-    m.precision = "bf16"
+    # 16-bit throughput mode = fp16: north_star's gate as stated (<= 5e-2 and >= 99.5 % RAW argmax agreement)
+    m.precision = "fp16"
     got16 = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv)
     assert np.abs(got16 - want).max() < 5e-2
-    # Random-init logits are almost flat (std ~0.1, 4 % of frames have a top-2 gap < 1e-3), so bf16 rounding
-    # (measured max |err| ~3e-3) flips ~1 % of raw argmaxes; every flip is a near-tie.  DESIGN.md discusses it.
-    assert _agree(got16, want) >= 0.98
-    assert _agree_near_tie(got16, want) >= 0.995
+    assert _agree(got16, want) >= 0.995
+    # Single-pass bf16 meets the max-abs tolerance but NOT the argmax gate: random-init logits are almost flat
+    # (4 % of frames have a top-2 gap < 1e-3) and bf16 rounding (max |err| ~3e-3) flips ~1.2 % of the raw argmaxes
+    # (measured table: profiles/r02_parity_table.md).  0.98 is a regression floor, not the gate.
+    m.precision = "bf16"
+    gotb = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv)
+    assert np.abs(gotb - want).max() < 5e-2
+    assert _agree(gotb, want) >= 0.98
+    # bf16 with every Linear's activations as hi/lo pairs and W-split on top == the fp32 mode's arithmetic
+    m.precision = "bf16+a+w"
+    assert np.abs(nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv) - want).max() < 1e-3
+    with pytest.raises(nn.NnamError):
+        m.precision = "int8"
+        nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv)
 
 
 def test_predict_chunking_halo_and_multi_device_are_bit_identical(nn):

@@ -180,6 +180,77 @@ def test_linear_bias_act(ops, dev, m, n, k, mode):
     assert np.abs(rec.cpu().numpy()[:, :n] - ref * (ref > 0)).max() < (2e-4 if split else 2e-2) * max(1.0, np.abs(ref).max())
 
 
+def _f16(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(torch.float16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (300, 1024, 544), (1000, 1909, 440), (4173, 1909, 1024),
+                                   (5000, 512, 544)])
+def test_linear_fp16_operands(ops, dev, m, n, k):
+    """NNAM_ELEM_F16: exact products of fp16 inputs, fp32 accumulation, fp32 / fp16 outputs (1-CTA and pair kernels)."""
+    rng = np.random.default_rng(m + n + k)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    a_hi, _ = ops.convert_f32(_t(a, dev), ops.OUT_F16)
+    w_hi, _ = ops.convert_f32(_t(w, dev), ops.OUT_F16)
+    assert a_hi.dtype == torch.float16 and np.array_equal(a_hi.float().cpu().numpy()[:, :k], _f16(a))
+    ref = _f16(a).astype(np.float64) @ _f16(w).astype(np.float64).T + b
+    got, _ = ops.linear_bias_act(a_hi, None, w_hi, None, _t(b, dev), m, n, k, act="identity", out_kind=ops.OUT_F32,
+                                 elem=ops.ELEM_F16)
+    assert np.abs(got.cpu().numpy()[:, :n] - ref).max() < 5e-5 * max(1.0, np.abs(ref).max())
+    hi, _ = ops.linear_bias_act(a_hi, None, w_hi, None, _t(b, dev), m, n, k, act="relu", out_kind=ops.OUT_F16,
+                                elem=ops.ELEM_F16)
+    assert hi.dtype == torch.float16
+    assert np.abs(hi.float().cpu().numpy()[:, :n] - ref * (ref > 0)).max() < 2e-3 * max(1.0, np.abs(ref).max())
+
+
+def test_fp16_conversions_saturate(ops, dev):
+    big = torch.tensor([[1e6, -1e6, 65504.0, 7e4, 1.0, -2.0, 0.0, 3e-8]], device=dev)
+    hi, _ = ops.convert_f32(big, ops.OUT_F16)
+    got = hi.float().cpu().numpy()[0]
+    assert np.isfinite(got).all() and got[0] == 65504.0 and got[1] == -65504.0 and got[3] == 65504.0 and got[4] == 1.0
+
+
+@pytest.mark.parametrize("nsplit", [2, 4])
+@pytest.mark.parametrize("m", [300, 4200])
+def test_linear_partial_split_passes(ops, dev, nsplit, m):
+    """NNAM_SPLIT_A (activations as hi/lo pairs) and NNAM_SPLIT_W (weights): the split operand carries 16 mantissa bits,
+    the other one stays plain bf16."""
+    n, k = 520, 544
+    rng = np.random.default_rng(nsplit + m)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    w = (rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+    a_hi, a_lo = ops.convert_f32(_t(a, dev), ops.OUT_BF16_SPLIT)
+    w_hi, w_lo = ops.convert_f32(_t(w, dev), ops.OUT_BF16_SPLIT)
+    got, _ = ops.linear_bias_act(a_hi, a_lo, w_hi, w_lo, None, m, n, k, out_kind=ops.OUT_F32, nsplit=nsplit)
+    a_eff = a if nsplit == ops.SPLIT_A else _bf16(a)
+    w_eff = w if nsplit == ops.SPLIT_W else _bf16(w)
+    ref = a_eff.astype(np.float64) @ w_eff.astype(np.float64).T
+    assert np.abs(got.cpu().numpy()[:, :n] - ref).max() < 2e-4 * max(1.0, np.abs(ref).max())
+    plain = _bf16(a).astype(np.float64) @ _bf16(w).astype(np.float64).T
+    assert np.abs(plain - ref).max() > 1e-3  # the pass really changes the result
+
+
+def test_splice_and_gather_fp16_output(ops, dev, golden_dir):
+    """K1 with NNAM_OUT_F16: the fp32 result of the bit-exact path rounded once to fp16."""
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((700, 40)).astype(np.float32)
+    iv = rng.standard_normal((700, 100)).astype(np.float32)
+    ft = O.load_kaldi_feature_transform(os.path.join(golden_dir, "final.feature_transform"))
+    want = np.concatenate((O.apply_kaldi_feature_transform(O.splicing(x, range(-5, 6)), ft), iv), axis=1)
+    hi, _ = ops.splice_transform(_t(x, dev), 700, 5, _t(ft["addShift"], dev), _t(ft["rescale"], dev), _t(iv, dev),
+                                 out_kind=ops.OUT_F16)
+    assert hi.dtype == torch.float16 and np.array_equal(hi.float().cpu().numpy()[:, :540], _f16(want))
+    ftm = O.select_transform_for_network(ft, "lstm")
+    rmap = torch.from_numpy(rng.integers(0, 700, 333).astype(np.int32)).to(dev)
+    hi, _ = ops.gather_transform(_t(x, dev), rmap, _t(ftm["addShift"], dev), _t(ftm["rescale"], dev), _t(iv, dev),
+                                 out_kind=ops.OUT_F16)
+    sel = rmap.cpu().numpy()
+    wantg = np.concatenate((O.apply_kaldi_feature_transform(x[sel], ftm), iv[sel]), axis=1)
+    assert np.array_equal(hi.float().cpu().numpy()[:, :140], _f16(wantg))
+
+
 def test_linear_activations_match_chainer_formulation(ops, dev):
     rng = np.random.default_rng(3)
     a = rng.standard_normal((256, 512)).astype(np.float32)
@@ -199,7 +270,14 @@ def test_linear_rejects_bad_arguments(ops, dev):
     with pytest.raises(NnamError):
         ops.linear_bias_act(a, None, w, None, None, 16, 16, 24, nsplit=3)  # missing lo operands
     with pytest.raises(NnamError):
-        ops.linear_bias_act(a, None, w, None, None, 16, 16, 24, nsplit=2)
+        ops.linear_bias_act(a, None, w, None, None, 16, 16, 24, nsplit=2)  # SPLIT_A without a_lo
+    with pytest.raises(NnamError):
+        ops.linear_bias_act(a, None, w, None, None, 16, 16, 24, nsplit=5)  # not a NNAM_SPLIT_* code
+    with pytest.raises(NnamError):  # the hi/lo split passes are defined for bf16 operands only
+        h = torch.zeros(16, 24, dtype=torch.float16, device=dev)
+        ops.linear_bias_act(h, a, h, a, None, 16, 16, 24, nsplit=3, elem=ops.ELEM_F16)
+    with pytest.raises(NnamError):  # element type / buffer dtype mismatch is caught on the host side
+        ops.linear_bias_act(a, None, w, None, None, 16, 16, 24, elem=ops.ELEM_F16)
     with pytest.raises(NnamError):
         a20 = torch.zeros(16, 20, dtype=torch.bfloat16, device=dev)
         ops.linear_bias_act(a20, None, w, None, None, 16, 16, 20)  # lda = 20 elements: rows not 16-byte aligned

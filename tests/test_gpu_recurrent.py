@@ -60,16 +60,21 @@ def test_predict_lstm_fp32_mode(nn, golden_dir, units, layers, lens, td):
         assert np.all(np.abs(fixed).sum(axis=1) > 0)
 
 
-def test_predict_lstm_bf16_mode(nn):
-    lens = [60, 85, 44, 70, 52, 66, 91, 38]
+def test_predict_lstm_16bit_modes(nn):
+    """fp16 = the 16-bit mode that meets north_star's gate (<= 5e-2, >= 99.5 % RAW argmax agreement); bf16 meets the
+    max-abs tolerance only (0.98 is a regression floor; see tests/test_gpu_full_size.py)."""
+    lens = [60, 85, 44, 70, 52, 66, 91, 38] * 4
     off = _offsets(lens)
     x = np.random.default_rng(1).standard_normal((off[-1], 40)).astype(np.float32)
-    m, p = _lstm(nn, 3, "lstm", 40, 512, 4, 1909, precision="bf16")
+    m, p = _lstm(nn, 3, "lstm", 40, 512, 4, 1909, precision="fp16")
     want = O.predict(O.RecurrentNet(p, "lstm", 4), x, off, "lstm", 1, 0, None)
     got = nn.predict(m, x, off, 1909, "lstm", 0, 1, 0, None, progress=False)
     assert np.abs(got - want).max() < 5e-2
-    rows = np.arange(len(want))
-    assert np.mean(want[rows, got.argmax(axis=1)] >= want.max(axis=1) - 1e-2) >= 0.995
+    assert np.mean(got.argmax(axis=1) == want.argmax(axis=1)) >= 0.995
+    m.precision = "bf16"
+    got = nn.predict(m, x, off, 1909, "lstm", 0, 1, 0, None, progress=False)
+    assert np.abs(got - want).max() < 5e-2
+    assert np.mean(got.argmax(axis=1) == want.argmax(axis=1)) >= 0.98
 
 
 def test_zoneout_lstm_is_lstm_arithmetic(nn):
@@ -158,6 +163,9 @@ def test_gru_bf16_mode_and_bidirectional(nn):
     want = O.predict(O.RecurrentNet(p, "gru", 4), x, off, "gru", 1, 0, None)
     got = nn.predict(m, x, off, 1909, "gru", 0, 1, 0, None, progress=False)
     assert np.abs(got - want).max() < 5e-2
+    m.precision = "fp16"
+    got = nn.predict(m, x, off, 1909, "gru", 0, 1, 0, None, progress=False)
+    assert np.abs(got - want).max() < 1e-2 and np.mean(got.argmax(axis=1) == want.argmax(axis=1)) >= 0.995
     mb, pb = _gru(nn, 13, "bgru", 40, 128, 2, 39, bidirectional=True)
     want = np.concatenate([O.log_softmax(O.birnn_forward_utterance(pb, "gru", 2, x[off[u]:off[u + 1]]))
                            for u in range(len(lens))])
@@ -193,9 +201,10 @@ def test_predict_peephole_lstm(nn, golden_dir, units, layers, lens, td):
     want = O.predict(O.RecurrentNet(p, "peepholelstm", layers), x, off, "peepholelstm", 1, td, ft)
     got = nn.predict(m, x, off, n_out, "peepholelstm", 0, 1, td, ft, progress=False)
     assert np.abs(got - want).max() < 1e-3
-    m.precision = "bf16"
-    got16 = nn.predict(m, x, off, n_out, "peepholelstm", 0, 1, td, ft, progress=False)
-    assert np.abs(got16 - want).max() < 5e-2
+    for prec in ("bf16", "fp16"):
+        m.precision = prec
+        got16 = nn.predict(m, x, off, n_out, "peepholelstm", 0, 1, td, ft, progress=False)
+        assert np.abs(got16 - want).max() < 5e-2
     # stateful per-step surface
     m.precision = "fp32"
     ref = O.RecurrentNet(p, "peepholelstm", layers)
@@ -229,7 +238,8 @@ def test_timedelay_longer_than_some_utterances_and_empty_input(nn, network):
 
 @pytest.mark.parametrize("network,units,n_utt", [("lstm", 512, 300), ("blstm", 128, 300), ("lstm", 192, 300),
                                                  ("lstm", 512, 2700), ("blstm", 512, 2500)])
-def test_wide_kernel_128_slots_per_batch(nn, network, units, n_utt):
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_wide_kernel_128_slots_per_batch(nn, network, units, n_utt, prec):
     """The 128-slot "wide" LSTM kernel (utterances on the MMA's M axis, h streamed through a TMA ring) against the
     oracle and against the 32-slot kernel, on more than one batch with ragged lengths."""
     from nnacousticmodeling_b200 import recurrent_engine
@@ -239,7 +249,7 @@ def test_wide_kernel_128_slots_per_batch(nn, network, units, n_utt):
     off = _offsets(lens)
     x = rng.standard_normal((off[-1], 40)).astype(np.float32)
     bid = network == "blstm"
-    m, p = _lstm(nn, 77, network, 40, units, 2, 39, precision="bf16", bidirectional=bid)
+    m, p = _lstm(nn, 77, network, 40, units, 2, 39, precision=prec, bidirectional=bid)
     wide = np.zeros((off[-1], 39), np.float32)
     recurrent_engine.forward_utterances(m, x, off, wide, 0, len(lens), timedelay=0, device=0, nb=128)
     narrow = np.zeros_like(wide)
@@ -257,7 +267,8 @@ def test_wide_kernel_128_slots_per_batch(nn, network, units, n_utt):
 
 @pytest.mark.parametrize("network,units,n_utt", [("gru", 512, 300), ("mgrurelu", 512, 300), ("mgrurelur", 128, 300),
                                                  ("bgru", 192, 300), ("gru", 512, 2700), ("mgrurelu", 256, 2600)])
-def test_wide_gru_kernel_128_slots_per_batch(nn, network, units, n_utt):
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_wide_gru_kernel_128_slots_per_batch(nn, network, units, n_utt, prec):
     """The 128-slot GRU-family kernel (gate-blocked rows, two exchanges per step with the reset gate) against the
     32-slot kernel on the whole set and against the oracle on a few utterances."""
     from nnacousticmodeling_b200 import recurrent_engine
@@ -266,7 +277,7 @@ def test_wide_gru_kernel_128_slots_per_batch(nn, network, units, n_utt):
     off = _offsets(lens)
     x = rng.standard_normal((off[-1], 40)).astype(np.float32)
     bid = network == "bgru"
-    m, p = _gru(nn, 91, network, 40, units, 2, 39, precision="bf16", bidirectional=bid)
+    m, p = _gru(nn, 91, network, 40, units, 2, 39, precision=prec, bidirectional=bid)
     wide = np.zeros((off[-1], 39), np.float32)
     recurrent_engine.forward_utterances(m, x, off, wide, 0, len(lens), timedelay=0, device=0, nb=128)
     narrow = np.zeros_like(wide)
@@ -283,7 +294,8 @@ def test_wide_gru_kernel_128_slots_per_batch(nn, network, units, n_utt):
 
 
 @pytest.mark.parametrize("network,units", [("lstm", 512), ("blstm", 512), ("gru", 512), ("bgru", 512), ("mgrurelu", 512)])
-def test_mixed_schedule_long_utterances_in_the_32_slot_kernel(nn, network, units, monkeypatch):
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_mixed_schedule_long_utterances_in_the_32_slot_kernel(nn, network, units, prec, monkeypatch):
     """MixedSchedule: the longest utterances run in the 32-slot kernel, the rest in the 128-slot kernel, as two
     concurrent launches over one packed row space; same outputs as the plain 32-slot schedule."""
     from nnacousticmodeling_b200 import recurrent_engine
@@ -294,9 +306,9 @@ def test_mixed_schedule_long_utterances_in_the_32_slot_kernel(nn, network, units
     x = rng.standard_normal((off[-1], 40)).astype(np.float32)
     bid = network in ("blstm", "bgru")
     if "lstm" in network:
-        m, p = _lstm(nn, 78, network, 40, units, 2, 39, precision="bf16", bidirectional=bid)
+        m, p = _lstm(nn, 78, network, 40, units, 2, 39, precision=prec, bidirectional=bid)
     else:
-        m, p = _gru(nn, 78, network, 40, units, 2, 39, precision="bf16", bidirectional=bid)
+        m, p = _gru(nn, 78, network, 40, units, 2, 39, precision=prec, bidirectional=bid)
     monkeypatch.setenv("NNAM_RNN_MIXED", "force")
     mixed = np.zeros((off[-1], 39), np.float32)
     recurrent_engine.forward_utterances(m, x, off, mixed, 0, len(lens), timedelay=3 if not bid else 0, device=0)

@@ -28,7 +28,7 @@ def test_library_exports_every_symbol_in_header(built_lib):
     for sym in declared:
         assert hasattr(raw, sym), f"{sym} declared in include/nnam_b200.h but not exported"
     assert declared == set(_native.EXPORTED_SYMBOLS)
-    assert built_lib.nnam_abi_version() == 1
+    assert built_lib.nnam_abi_version() == _native.ABI_VERSION
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
