@@ -324,8 +324,18 @@ def _dev_vec(a, device):
     return None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32).reshape(-1)).to(device)
 
 
+class RowSink:
+    """Consumer of finished output rows for callers that do not want the whole (N, C) matrix in host memory at once
+    (the predict_folds CLI streams them into the .npy file).  ``write(r0, r1, rows)`` is called from a helper thread,
+    once per chunk, in increasing row order for feed-forward nets; ``rows`` is a NumPy view of a pinned staging buffer
+    that is reused after the call returns."""
+
+    def write(self, r0, r1, rows):
+        raise NotImplementedError
+
+
 def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, device=0, head=None,
-                      chunk=DEFAULT_CHUNK, presliced=False):
+                      chunk=DEFAULT_CHUNK, presliced=False, sink=None):
     """Feed-forward hot loop on ONE device for frames [f0, f1) of the whole array ``x``.
 
     models    : one MLP or a list (ensemble -> logits combined in the head with head.weights)
@@ -334,7 +344,9 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
                 data to the model)
     ivectors  : optional (N, I) host array or CUDA tensor, appended after splice + transform
     out       : (N, C) float32; rows [f0, f1) are written.  Host array (pinned => async D2H overlapped
-                with the next chunk on a side stream) or CUDA tensor (results stay in HBM).
+                with the next chunk on a side stream) or CUDA tensor (results stay in HBM).  May be None when
+                ``sink`` (a RowSink) is given: every chunk is then copied into one of two pinned staging buffers and
+                handed to ``sink.write`` on a helper thread while the next chunk is computed.
     """
     if not isinstance(models, (list, tuple)):
         models = [models]
@@ -393,7 +405,9 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         prior = _dev_vec(head.prior, device)
         rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
         out_on_device = isinstance(out, torch.Tensor) and out.is_cuda
-        out_h = None if out_on_device else _as_host_tensor(out)
+        out_h = None if (out_on_device or out is None) else _as_host_tensor(out)
+        if out is None and sink is None:
+            raise NnamError("ff_forward_frames: give an output array or a RowSink")
         chunk = min(chunk, f1 - f0)
         d_in = models[0].in_size
         if any(m.in_size != d_in or m.n_out != n_out for m in models):
@@ -407,6 +421,12 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         a_bufs = [(ws.get("ff.a.hi", chunk, ld_in, plan0.tdt),
                    ws.get("ff.a.lo", chunk, ld_in, torch.bfloat16) if plan0.in_kind == OUT_BF16_SPLIT else None)]
         out_dev = None if out_on_device else [ws.get(f"ff.out{i}", chunk, n_out, torch.float32) for i in range(2)]
+        stage = writer = None
+        if sink is not None and not out_on_device:
+            stage = plan0.__dict__.get("_stage")
+            if stage is None or stage[0].shape[0] < chunk or stage[0].shape[1] != n_out:
+                stage = plan0._stage = [torch.empty((chunk, n_out), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            writer = _SinkWriter(sink, stage)
         # Three streams: `main` runs splice + the GEMM stack of chunk i; `aux` runs the HBM-bound head of chunk i-1 in
         # their shadow (the GEMM kernels cap their registers so that one head CTA fits next to a GEMM CTA on every SM);
         # `side` carries the D2H copies.  Logits and head outputs are double-buffered by chunk parity.  (Moving the
@@ -450,15 +470,65 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
             if out_on_device:
                 continue
             side.wait_event(hd)
+            if writer is not None:
+                writer.wait_free(buf)  # the sink still reads the staging buffer of chunk i-2
             with torch.cuda.stream(side):
-                out_h[c0:c1].copy_(out_dev[buf][:rows], non_blocking=True)
+                dst = stage[buf][:rows] if writer is not None else out_h[c0:c1]
+                dst.copy_(out_dev[buf][:rows], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(side)
             copied[buf] = ev
+            if writer is not None:
+                writer.submit(buf, c0, c1, ev)
         main.wait_stream(aux)  # callers that time or consume on the current stream see the whole pass
         side.synchronize()
         main.synchronize()
+        if writer is not None:
+            writer.close()
     return out
+
+
+class _SinkWriter:
+    """Helper thread that hands finished chunks (pinned staging buffers) to a RowSink in submission order."""
+
+    def __init__(self, sink, stage):
+        import queue
+        self.sink, self.stage = sink, stage
+        self.free = [threading.Event(), threading.Event()]
+        for e in self.free:
+            e.set()
+        self.q = queue.Queue()
+        self.err = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            buf, r0, r1, ev = item
+            try:
+                if self.err is None:
+                    ev.synchronize()
+                    self.sink.write(r0, r1, self.stage[buf][:r1 - r0].numpy())
+            except BaseException as e:  # noqa: BLE001  (re-raised on the caller's thread by close())
+                self.err = e
+            finally:
+                self.free[buf].set()
+
+    def wait_free(self, buf):
+        self.free[buf].wait()
+        self.free[buf].clear()
+
+    def submit(self, buf, r0, r1, ev):
+        self.q.put((buf, r0, r1, ev))
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+        if self.err is not None:
+            raise self.err
 
 
 def halo_of(presliced, splice):

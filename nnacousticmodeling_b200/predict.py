@@ -23,7 +23,7 @@ def _devices(gpu):
 
 
 def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft, progress=True, ivectors=None,
-            out=None, fix_timedelay_tail=False, head=None, presliced=False):
+            out=None, fix_timedelay_tail=False, head=None, presliced=False, sink=None):
     """predict_folds.py:27-95.  Returns (N, num_classes) float32 log-softmax outputs.
 
     Extensions: ``ivectors`` (N, I) are appended AFTER splice + transform (train.py:255-258 /
@@ -31,16 +31,27 @@ def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft,
     ``fix_timedelay_tail`` fills the last ``timedelay`` frames that the reference leaves 0 (quirk Q4);
     ``model`` may be a list of same-shaped nets whose outputs are combined on the device by ``head``
     (an ``engine.HeadSpec``: logit mean of evaluate.py:35-51, log-prob mean of predict_folds.py:199-219, RPL4,
-    prior); ``presliced`` says ``x`` is already spliced/transformed (the evaluate.py data flow).
+    prior); ``presliced`` says ``x`` is already spliced/transformed (the evaluate.py data flow); ``sink`` (an
+    ``engine.RowSink``) receives the output rows chunk by chunk instead of an array being returned (the CLI streams
+    them into the .npy file while the next chunk is computed).
+
+    The returned array is page-locked when the function allocates it: the device->host copies of the (N, C) matrix
+    -- 7.6 KB per frame, the end-to-end bottleneck -- then run asynchronously at PCIe speed under the computation.
     """
     devs = _devices(gpu)
     x = np.ascontiguousarray(x, dtype=np.float32)
     n = x.shape[0]
+    if sink is not None and len(devs) == 1 and not is_nn_recurrent(network) and n > 0:
+        engine.ff_forward_frames(model, x, ft, int(winlen) // 2, None, 0, n, ivectors=ivectors, device=devs[0],
+                                 head=head, presliced=presliced, sink=sink)
+        return None
     if out is None:
-        out = np.zeros((n, num_classes), dtype=np.float32)
+        out = engine.empty_pinned((n, num_classes)) if n > 0 else np.zeros((0, num_classes), dtype=np.float32)
     elif out.shape != (n, num_classes) or out.dtype != np.float32:
         raise NnamError("predict: out must be float32 of shape (N, num_classes)")
     if n == 0:
+        if sink is not None:
+            return None
         return out
     if is_nn_recurrent(network):
         from . import recurrent_engine
@@ -60,7 +71,33 @@ def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft,
             lambda sh, d: engine.ff_forward_frames(model, x, ft, splice, out, sh[0], sh[1], ivectors=ivectors,
                                                    device=d, head=head, presliced=presliced),
             shards, devs)
+    if sink is not None:  # recurrent nets finish utterance subsets out of row order, several devices interleave:
+        sink.write(0, n, out)  # the rows go to the sink in one piece at the end
+        return None
     return out
+
+
+class NpyFileSink(engine.RowSink):
+    """Streams rows, in order, into a ``.npy`` file that ``np.load`` reads back as the (N, C) float32 C-contiguous
+    array ``np.save`` would have written (predict_folds.py:240)."""
+
+    def __init__(self, path, n_rows, n_cols):
+        self.f = open(path, "wb")
+        np.lib.format.write_array_header_1_0(
+            self.f, {"descr": np.lib.format.dtype_to_descr(np.dtype(np.float32)), "fortran_order": False,
+                     "shape": (int(n_rows), int(n_cols))})
+        self.next_row, self.n_rows = 0, int(n_rows)
+
+    def write(self, r0, r1, rows):
+        if r0 != self.next_row:
+            raise NnamError(f"NpyFileSink: rows [{r0}, {r1}) arrived out of order (expected row {self.next_row})")
+        self.f.write(memoryview(np.ascontiguousarray(rows, dtype=np.float32)).cast("B"))
+        self.next_row = r1
+
+    def close(self):
+        self.f.close()
+        if self.next_row != self.n_rows:
+            raise NnamError(f"NpyFileSink: {self.next_row} of {self.n_rows} rows were written")
 
 
 def _activation(name):
@@ -169,9 +206,15 @@ def main(arg_list=None):
             offsets = np.load(str(Path(args.fold_data_dir, args.fold_offset_pattern.format(fold)))) if recurrent else None
             iv = (np.load(str(Path(args.fold_data_dir, args.fold_ivector_pattern.format(fold))))
                   if args.ivector_dir else None)
-            y = predict(model, x, offsets, num_classes, args.network, gpu, winlen, args.timedelay, ft,
-                        not args.no_progress, ivectors=iv)
-            np.save(str(Path(args.fold_output_dir, args.fold_output_pattern.format(fold))), y)
+            # np.save(path, y) of predict_folds.py:240, streamed: chunk i goes to the file while chunk i+1 is computed
+            sink = NpyFileSink(str(Path(args.fold_output_dir, args.fold_output_pattern.format(fold))), len(x), num_classes)
+            try:
+                predict(model, x, offsets, num_classes, args.network, gpu, winlen, args.timedelay, ft,
+                        not args.no_progress, ivectors=iv, sink=sink)
+            except BaseException:
+                sink.f.close()
+                raise
+            sink.close()
             n_folds += 1
         if n_folds == 0:
             print("Error: No fold networks found")

@@ -350,3 +350,34 @@ def test_two_phase_forward_equals_single_phase(nn, network, monkeypatch):
     if td:
         for u in (int(np.argmin(lens)), 0):
             assert np.all(two[off[u + 1] - min(td, lens[u]):off[u + 1]] == 0)
+
+
+@pytest.mark.parametrize("network,nb", [("lstm", 32), ("lstm", 128), ("gru", 32), ("gru", 128), ("blstm", 128),
+                                        ("peepholelstm", 32)])
+def test_exchange_buffer_contents_on_entry_are_irrelevant(nn, network, nb):
+    """include/nnam_b200.h: the kernels never read an exchange slot row they have not written in the same launch.  The
+    buffer is reused across layers, models and schedules without being cleared, so it is poisoned with NaNs here: any
+    read-before-write would surface as a NaN in the output."""
+    from nnacousticmodeling_b200 import engine, recurrent_engine
+    rng = np.random.default_rng(23)
+    lens = rng.integers(1, 50, size=200).tolist()
+    off = _offsets(lens)
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    bid = network == "blstm"
+    if "lstm" in network:
+        m, _ = _lstm(nn, 31, network, 40, 128, 2, 39, precision="fp16", bidirectional=bid)
+    else:
+        m, _ = _gru(nn, 31, network, 40, 128, 2, 39, precision="fp16")
+    clean = np.zeros((off[-1], 39), np.float32)
+    kw = dict(timedelay=0, device=0) if network == "peepholelstm" else dict(timedelay=0, device=0, nb=nb)
+    recurrent_engine.forward_utterances(m, x, off, clean, 0, len(lens), **kw)
+    plan = engine.get_plan(m, 0)
+    poisoned = 0
+    for name, buf in plan.ws.buf.items():
+        if "xchg" in name:
+            buf.fill_(float("nan"))
+            poisoned += 1
+    assert poisoned >= 1
+    again = np.zeros_like(clean)
+    recurrent_engine.forward_utterances(m, x, off, again, 0, len(lens), **kw)
+    assert np.isfinite(again).all() and np.array_equal(again, clean)

@@ -97,3 +97,42 @@ def test_lab_writer_matches_reference_format(golden_dir, tmp_path):
     nn.saveBin(str(tmp_path / "a.lab"), y)
     assert (tmp_path / "a.lab").read_bytes() == want
     assert np.array_equal(nn.loadBin(str(tmp_path / "a.lab")), y)
+
+
+def test_product_synth_matches_the_oracles_generator():
+    """bench.py's product arm builds its workload through the package (nnacousticmodeling_b200.synth); the tests and the
+    CPU baseline use the oracle's generator: same seed, same data."""
+    from nnacousticmodeling_b200 import synth
+    for seed, utts, iv, total in ((3, 17, 0, None), (4, 40, 12, 12345)):
+        a, b = synth.synth_set(seed, utts, 40, iv, total=total), O.synth_set(seed, utts, 40, iv, total=total)
+        for u, v in zip(a, b):
+            assert (u is None and v is None) or np.array_equal(u, v)
+    assert synth.TIMIT_TRAIN_FRAMES == 1124823
+
+
+def test_precision_grammar():
+    from nnacousticmodeling_b200.engine import Precision
+    from nnacousticmodeling_b200.ops import SPLIT_A, SPLIT_AW, SPLIT_NONE, SPLIT_W
+    p = Precision("bf16+a:0/6+w:-1")
+    assert [p.nsplit(l, 7) for l in range(7)] == [SPLIT_A, SPLIT_NONE, SPLIT_NONE, SPLIT_NONE, SPLIT_NONE, SPLIT_NONE,
+                                                  SPLIT_AW]
+    assert Precision("bf16+w").nsplit(3, 7) == SPLIT_W and Precision("fp32").nsplit(0, 7) == SPLIT_AW
+    assert Precision("fp16").nsplit(0, 7) == SPLIT_NONE and not Precision("fp16").split
+    for bad in ("int8", "fp16+a", "bf16+x"):
+        with pytest.raises(nn.NnamError):
+            Precision(bad)
+
+
+def test_npy_file_sink_writes_what_np_save_writes(tmp_path):
+    sink_cls = __import__("importlib").import_module("nnacousticmodeling_b200.predict").NpyFileSink
+    y = np.random.default_rng(0).standard_normal((1000, 39)).astype(np.float32)
+    s = sink_cls(str(tmp_path / "a.npy"), 1000, 39)
+    for r0 in range(0, 1000, 300):
+        s.write(r0, min(r0 + 300, 1000), y[r0:r0 + 300])
+    s.close()
+    np.save(str(tmp_path / "b.npy"), y)
+    assert np.array_equal(np.load(str(tmp_path / "a.npy")), y)
+    assert open(str(tmp_path / "a.npy"), "rb").read() == open(str(tmp_path / "b.npy"), "rb").read()
+    bad = sink_cls(str(tmp_path / "c.npy"), 10, 39)
+    with pytest.raises(nn.NnamError):
+        bad.write(5, 10, y[:5])
