@@ -128,6 +128,26 @@ int nnam_head_scatter(const float* const* logits_host, const float* weights_host
                       const float* prior, float prior_scale, int final_normalize, float* out, long long ld_out,
                       long long rows, int n_classes, const int* out_row_map, void* stream);
 
+/* nnam_head_scatter (out_row_map may be NULL) with the COMPACT TRANSFER FORMAT as output instead of float32 rows:
+ *   row_ref[q] = max_c y[q][c]          out16[q][c] = fp16(y[q][c] - row_ref[q])        (q = output row)
+ * out16: IEEE fp16 [rows_out, ld16] with ld16 % 8 == 0 (16-byte aligned rows), row_ref: float[rows_out].  Half the bytes
+ * of the float32 matrix cross PCIe -- the end-to-end bottleneck of the path (7,636 B per frame) -- and
+ * nnam_widen_f16_host rebuilds the reference's (N, C) float32 layout on the host.  What it costs: an entry keeps 11
+ * significant bits of its DISTANCE from the row maximum (|error| <= 2^-12 * |y - max|, i.e. <= 4e-3 at a distance of
+ * 16), so the best-scoring classes -- the ones the decoder compares -- keep float32-like resolution and the argmax is
+ * unchanged.  Used in the 16-bit precision modes (tolerance 5e-2); the fp32-accurate mode transfers float32.  */
+int nnam_head_f16(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in,
+                  int pre_normalize, const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior,
+                  float prior_scale, int final_normalize, void* out16, long long ld16, float* row_ref, long long rows,
+                  int n_classes, const int* out_row_map, void* stream);
+
+/* HOST function (no CUDA): dst_host[r][c] = float(src16_host[r][c]) + row_ref_host[r] for r < rows, c < cols, on
+ * `threads` host threads (F16C / AVX2 with non-temporal stores when the CPU has them).  All three pointers are HOST
+ * pointers; dst_host is the reference-layout float32 output (ld_dst == cols for the contiguous (N, C) array of
+ * np.save, predict_folds.py:240).  */
+int nnam_widen_f16_host(const void* src16_host, long long ld16, const float* row_ref_host, float* dst_host,
+                        long long ld_dst, long long rows, int cols, int threads);
+
 /* Row gather + feature transform (+ i-vector append) for recurrent nets: out[r] = transform(x[row_map[r]]) ++
  * ivec[row_map[r]].  Replaces the per-utterance `np.pad(..., mode="edge")` + applyKaldiFeatureTransform + padded
  * (U, Lmax+timedelay, D) batch assembly of predict_folds.py:34-43 / evaluateModelForTest.py:57-59: row_map lists,

@@ -14,7 +14,8 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libnnam_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_wide.cu", "recurrent_wide_gru.cu", "peephole.cu"]
+SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_wide.cu", "recurrent_wide_gru.cu", "peephole.cu",
+           "host_widen.cpp"]  # .cpp = host-only code, compiled with the host C++ compiler
 # measured dead end kept for reference (DSMEM all-gather recurrence); NNAM_WITH_CLUSTER_EXPERIMENT=1 builds it in
 EXPERIMENTAL_SOURCES = ["experimental/recurrent_cluster.cu"]
 ABI_VERSION = 2
@@ -66,8 +67,11 @@ def build(force=False, verbose=False):
         flags.append("-DNNAM_WITH_CLUSTER_EXPERIMENT")
 
     def compile_one(src):
-        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [_nvcc()] + flags + ["-c", "-o", obj, src]
+        obj = os.path.join(objdir, os.path.splitext(os.path.basename(src))[0] + ".o")
+        if src.endswith(".cpp"):
+            cmd = [os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", "-o", obj, src]
+        else:
+            cmd = [_nvcc()] + flags + ["-c", "-o", obj, src]
         res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
         if res.returncode != 0:
             raise NnamError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
@@ -77,7 +81,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
         objs = list(pool.map(compile_one, _sources()))
-    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs
+    cmd = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-lpthread"]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise NnamError("link failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
@@ -104,6 +108,10 @@ _SIGNATURES = {
     "nnam_head_scatter": (c_int, [POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p, c_void_p,
                                   c_void_p, c_void_p, c_float, c_int, c_void_p, c_longlong, c_longlong, c_int, c_void_p,
                                   c_void_p]),
+    "nnam_head_f16": (c_int, [POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_float, c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
+                              c_void_p]),
+    "nnam_widen_f16_host": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_int]),
     "nnam_gather_transform": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                       c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "nnam_peephole_cell": (c_int, [c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,

@@ -82,7 +82,7 @@ int convert_f32(const float* src, long long rows, int cols, long long lds, void*
 int head(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in, int pre_normalize,
          const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior, float prior_scale,
          int final_normalize, float* out, long long ld_out, long long rows, int n_classes, const int* out_row_map,
-         cudaStream_t stream);
+         void* out16, long long ld16, float* row_ref, cudaStream_t stream);
 int gather_transform(const float* x, long long n_src, int dim, const float* add_shift, const float* rescale,
                      const float* ivec, int ivec_dim, const int* row_map, long long n_rows, void* out_hi, void* out_lo,
                      long long ldo, int out_kind, cudaStream_t stream);
@@ -132,7 +132,7 @@ int nnam_head(const float* const* logits_host, const float* weights_host, int n_
               float prior_scale, int final_normalize, float* out, long long ld_out, long long rows, int n_classes,
               void* stream) {
   return nnam::head(logits_host, weights_host, n_inputs, ld_in, pre_normalize, rpl_w, rpl_b, rpl_lb, prior,
-                    prior_scale, final_normalize, out, ld_out, rows, n_classes, nullptr,
+                    prior_scale, final_normalize, out, ld_out, rows, n_classes, nullptr, nullptr, 0, nullptr,
                     static_cast<cudaStream_t>(stream));
 }
 
@@ -141,7 +141,17 @@ int nnam_head_scatter(const float* const* logits_host, const float* weights_host
                       const float* prior, float prior_scale, int final_normalize, float* out, long long ld_out,
                       long long rows, int n_classes, const int* out_row_map, void* stream) {
   return nnam::head(logits_host, weights_host, n_inputs, ld_in, pre_normalize, rpl_w, rpl_b, rpl_lb, prior,
-                    prior_scale, final_normalize, out, ld_out, rows, n_classes, out_row_map,
+                    prior_scale, final_normalize, out, ld_out, rows, n_classes, out_row_map, nullptr, 0, nullptr,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int nnam_head_f16(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in,
+                  int pre_normalize, const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior,
+                  float prior_scale, int final_normalize, void* out16, long long ld16, float* row_ref, long long rows,
+                  int n_classes, const int* out_row_map, void* stream) {
+  if (out16 == nullptr) return nnam::set_error(NNAM_ERR_ARG, "head_f16: out16 is NULL");
+  return nnam::head(logits_host, weights_host, n_inputs, ld_in, pre_normalize, rpl_w, rpl_b, rpl_lb, prior,
+                    prior_scale, final_normalize, nullptr, 0, rows, n_classes, out_row_map, out16, ld16, row_ref,
                     static_cast<cudaStream_t>(stream));
 }
 

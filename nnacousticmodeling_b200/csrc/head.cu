@@ -36,7 +36,15 @@ struct HeadParams {
   long long rows;
   int n_classes;
   const int* out_row_map;  // optional scatter: logits row r -> out row map[r] (negative: drop)
+  // compact transfer format (nnam_head_f16): out16[r][c] = fp16(y[r][c] - row_ref[r]) with row_ref[r] = max_c y[r][c];
+  // `out` is unused then.  The largest entries of a row -- the ones a decoder compares -- keep ~fp32 resolution (their
+  // offsets from the maximum are tiny), the far tail keeps 11 significant bits of its distance from the maximum.
+  uint16_t* out16;
+  long long ld16;
+  float* row_ref;
 };
+
+__device__ __forceinline__ uint32_t head_pack_f16x2(float lo, float hi) { return pack_f16x2(lo, hi); }
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -130,6 +138,21 @@ __global__ void __launch_bounds__(HEAD_THREADS, (MULTI || NV < 64) ? 1 : 2) head
         zero = true;
       }
     }
+    if (p.out16 != nullptr) {
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        if (lane + 32 * i < C) mx = fmaxf(mx, h[i]);
+      mx = zero ? 0.0f : warp_max(mx);
+      uint16_t* d16 = p.out16 + out_row * p.ld16;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) d16[c] = static_cast<uint16_t>(head_pack_f16x2(zero ? 0.0f : h[i] - mx, 0.0f) & 0xffffu);
+      }
+      if (lane == 0) p.row_ref[out_row] = zero ? 0.0f : mx - lse;
+      continue;
+    }
     float* dst = p.out + out_row * p.ld_out;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -199,8 +222,8 @@ __global__ void __launch_bounds__(HEAD_FAST_THREADS, 4) head_fast_kernel(const H
         }
       }
     }
-    float lse = 0.0f;
-    if (p.final_normalize) {
+    float lse = 0.0f, mx = 0.0f;
+    if (p.final_normalize || p.out16 != nullptr) {
       // columns past the end of the row become -inf: neutral for the max, and exp2 maps them to 0
 #pragma unroll
       for (int i = 0; i < NV4; ++i) {
@@ -211,10 +234,12 @@ __global__ void __launch_bounds__(HEAD_FAST_THREADS, 4) head_fast_kernel(const H
         if (4 * k + 2 >= C) v[i].z = -CUDART_INF_F;
         if (4 * k + 3 >= C) v[i].w = -CUDART_INF_F;
       }
-      float mx = -CUDART_INF_F;
+      mx = -CUDART_INF_F;
 #pragma unroll
       for (int i = 0; i < NV4; ++i) mx = fmaxf(fmaxf(mx, fmaxf(v[i].x, v[i].y)), fmaxf(v[i].z, v[i].w));
       mx = warp_max(mx);
+    }
+    if (p.final_normalize) {
       const float mxs = mx * LOG2E;
       float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
@@ -231,9 +256,22 @@ __global__ void __launch_bounds__(HEAD_FAST_THREADS, 4) head_fast_kernel(const H
       if (out_row < 0) {            // -2 - r: fill output row r with zeros (quirk Q4 rows the reference never writes)
         out_row = -2 - out_row;
         lse = 0.0f;
+        mx = 0.0f;
 #pragma unroll
         for (int i = 0; i < NV4; ++i) v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       }
+    }
+    if (p.out16 != nullptr) {
+      // rows of the fp16 matrix are 16-byte aligned (ld16 % 8 == 0): a lane's chunk k is one 8-byte store
+      uint2* d2 = reinterpret_cast<uint2*>(p.out16 + out_row * p.ld16);
+#pragma unroll
+      for (int i = 0; i < NV4; ++i) {
+        const int k = lane + 32 * i;
+        if (4 * k < p.ld16)  // columns in [C, ld16) are written as fp16(-inf - mx) or 0; the host never reads them
+          __stcs(d2 + k, make_uint2(head_pack_f16x2(v[i].x - mx, v[i].y - mx), head_pack_f16x2(v[i].z - mx, v[i].w - mx)));
+      }
+      if (lane == 0) p.row_ref[out_row] = mx - lse;
+      continue;
     }
     float* dst = p.out + out_row * p.ld_out;
     const int a = static_cast<int>((reinterpret_cast<uintptr_t>(dst) >> 2) & 3);  // row start modulo 16 bytes, in floats
@@ -274,11 +312,16 @@ __global__ void __launch_bounds__(HEAD_FAST_THREADS, 4) head_fast_kernel(const H
 int head(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in, int pre_normalize,
          const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior, float prior_scale,
          int final_normalize, float* out, long long ld_out, long long rows, int n_classes, const int* out_row_map,
-         cudaStream_t stream) {
+         void* out16, long long ld16, float* row_ref, cudaStream_t stream) {
   if (n_inputs < 1 || n_inputs > HEAD_MAX_INPUTS)
     return set_error(NNAM_ERR_ARG, "head: n_inputs must be in [1, %d]", HEAD_MAX_INPUTS);
   if (n_classes < 1 || n_classes > 2048) return set_error(NNAM_ERR_UNSUPPORTED, "head: n_classes must be in [1, 2048]");
-  if (ld_in < n_classes || ld_out < n_classes) return set_error(NNAM_ERR_ARG, "head: leading dimension < n_classes");
+  if (ld_in < n_classes || (out16 == nullptr && ld_out < n_classes))
+    return set_error(NNAM_ERR_ARG, "head: leading dimension < n_classes");
+  if (out16 != nullptr && (row_ref == nullptr || ld16 < n_classes || ld16 % 8 || (reinterpret_cast<uintptr_t>(out16) & 15)))
+    return set_error(NNAM_ERR_ARG, "head: the fp16 output needs row_ref, ld16 >= n_classes, ld16 %% 8 == 0 and a "
+                     "16-byte aligned buffer");
+  if (out16 == nullptr && out == nullptr) return set_error(NNAM_ERR_ARG, "head: no output buffer");
   if (rows < 0) return set_error(NNAM_ERR_ARG, "head: negative row count");
   if (rows == 0) return NNAM_OK;
   if ((rpl_w != nullptr) != (rpl_b != nullptr) || (rpl_w != nullptr) != (rpl_lb != nullptr))
@@ -303,11 +346,15 @@ int head(const float* const* logits_host, const float* weights_host, int n_input
   p.rows = rows;
   p.n_classes = n_classes;
   p.out_row_map = out_row_map;
+  p.out16 = static_cast<uint16_t*>(out16);
+  p.ld16 = ld16;
+  p.row_ref = row_ref;
   // fast path: one input, no RPL4 / per-input normalisation, 16-byte aligned input rows
   const bool fast_ok = n_inputs == 1 && !pre_normalize && rpl_w == nullptr && ld_in % 4 == 0 &&
                        (reinterpret_cast<uintptr_t>(logits_host[0]) & 15) == 0 &&
                        (prior == nullptr || (reinterpret_cast<uintptr_t>(prior) & 15) == 0) &&
-                       (reinterpret_cast<uintptr_t>(out) & 3) == 0 && n_classes + 3 <= 2048;
+                       (reinterpret_cast<uintptr_t>(out) & 3) == 0 && n_classes + 3 <= 2048 &&
+                       (out16 == nullptr || ld16 <= 2048);
   if (fast_ok) {
     const int wpb = HEAD_FAST_THREADS / 32;
     long long fb = (rows + wpb - 1) / wpb;

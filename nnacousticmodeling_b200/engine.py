@@ -335,7 +335,7 @@ class RowSink:
 
 
 def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, device=0, head=None,
-                      chunk=DEFAULT_CHUNK, presliced=False, sink=None):
+                      chunk=DEFAULT_CHUNK, presliced=False, sink=None, transfer=None, host_threads=None):
     """Feed-forward hot loop on ONE device for frames [f0, f1) of the whole array ``x``.
 
     models    : one MLP or a list (ensemble -> logits combined in the head with head.weights)
@@ -347,6 +347,10 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
                 with the next chunk on a side stream) or CUDA tensor (results stay in HBM).  May be None when
                 ``sink`` (a RowSink) is given: every chunk is then copied into one of two pinned staging buffers and
                 handed to ``sink.write`` on a helper thread while the next chunk is computed.
+    transfer  : how rows reach the host: "f32" = the float32 rows themselves; "f16" = the compact format of
+                nnam_head_f16 (fp16 offsets from the row maximum + the maximum: half the PCIe bytes, widened back to
+                float32 by ``host_threads`` host threads); None = "f16" in the 16-bit precision modes, "f32" in the
+                fp32-accurate mode (see :func:`use_compact_transfer`).
     """
     if not isinstance(models, (list, tuple)):
         models = [models]
@@ -421,12 +425,27 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         a_bufs = [(ws.get("ff.a.hi", chunk, ld_in, plan0.tdt),
                    ws.get("ff.a.lo", chunk, ld_in, torch.bfloat16) if plan0.in_kind == OUT_BF16_SPLIT else None)]
         out_dev = None if out_on_device else [ws.get(f"ff.out{i}", chunk, n_out, torch.float32) for i in range(2)]
-        stage = writer = None
-        if sink is not None and not out_on_device:
-            stage = plan0.__dict__.get("_stage")
-            if stage is None or stage[0].shape[0] < chunk or stage[0].shape[1] != n_out:
-                stage = plan0._stage = [torch.empty((chunk, n_out), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-            writer = _SinkWriter(sink, stage)
+        # Host output: "direct" = D2H straight into the caller's array; otherwise every chunk goes through one of two
+        # pinned staging buffers and a helper thread finishes it (widen the compact format and / or feed the sink)
+        compact = (not out_on_device) and use_compact_transfer(plan0, transfer)
+        writer = o16_dev = ref_dev = None
+        if (compact or sink is not None) and not out_on_device:
+            ld16 = round_up(n_out, 8)
+            key = ("f16" if compact else "f32", chunk, n_out)
+            cache = plan0.__dict__.setdefault("_stage", {})
+            if key not in cache:
+                cache.clear()
+                if compact:
+                    cache[key] = [(torch.empty((chunk, ld16), dtype=torch.float16, pin_memory=True),
+                                   torch.empty((chunk,), dtype=torch.float32, pin_memory=True)) for _ in range(2)]
+                else:
+                    cache[key] = [(torch.empty((chunk, n_out), dtype=torch.float32, pin_memory=True), None) for _ in range(2)]
+            stage = cache[key]
+            if compact:
+                o16_dev = [ws.get(f"ff.out16.{i}", chunk, ld16, torch.float16) for i in range(2)]
+                ref_dev = [ws.get(f"ff.ref.{i}", chunk, 1, torch.float32).view(-1) for i in range(2)]
+            out_np = out.numpy() if isinstance(out, torch.Tensor) else out
+            writer = _ChunkWriter(stage, compact, out_np, sink, n_out, host_threads or default_host_threads())
         # Three streams: `main` runs splice + the GEMM stack of chunk i; `aux` runs the HBM-bound head of chunk i-1 in
         # their shadow (the GEMM kernels cap their registers so that one head CTA fits next to a GEMM CTA on every SM);
         # `side` carries the D2H copies.  Logits and head outputs are double-buffered by chunk parity.  (Moving the
@@ -463,7 +482,10 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
                 else:
                     if copied[buf] is not None:
                         aux.wait_event(copied[buf])  # the side stream still reads this buffer
-                    ops.head(logits, n_out, out=out_dev[buf], **hkw)
+                    if compact:
+                        ops.head(logits, n_out, out16=(o16_dev[buf], ref_dev[buf]), **hkw)
+                    else:
+                        ops.head(logits, n_out, out=out_dev[buf], **hkw)
                 hd = torch.cuda.Event()
                 hd.record(aux)
             head_done[buf] = hd
@@ -471,10 +493,14 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
                 continue
             side.wait_event(hd)
             if writer is not None:
-                writer.wait_free(buf)  # the sink still reads the staging buffer of chunk i-2
+                writer.wait_free(buf)  # the helper thread still reads the staging buffer of chunk i-2
             with torch.cuda.stream(side):
-                dst = stage[buf][:rows] if writer is not None else out_h[c0:c1]
-                dst.copy_(out_dev[buf][:rows], non_blocking=True)
+                if compact:
+                    stage[buf][0][:rows].copy_(o16_dev[buf][:rows], non_blocking=True)
+                    stage[buf][1][:rows].copy_(ref_dev[buf][:rows], non_blocking=True)
+                else:
+                    dst = stage[buf][0][:rows] if writer is not None else out_h[c0:c1]
+                    dst.copy_(out_dev[buf][:rows], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(side)
             copied[buf] = ev
@@ -488,12 +514,36 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
     return out
 
 
-class _SinkWriter:
-    """Helper thread that hands finished chunks (pinned staging buffers) to a RowSink in submission order."""
+def use_compact_transfer(plan, transfer=None):
+    """Does a host-bound pass of ``plan`` use the compact (fp16 offsets + row maximum) transfer format?  Explicit
+    ``transfer`` ("f16" / "f32") wins, then the environment (NNAM_TRANSFER), then the precision mode: the 16-bit modes
+    (tolerance 5e-2) take it, the fp32-accurate mode (tolerance 1e-3) keeps float32 rows."""
+    mode = transfer or os.environ.get("NNAM_TRANSFER") or ("f32" if plan.split else "f16")
+    if mode not in ("f16", "f32"):
+        raise NnamError(f"transfer must be 'f16' or 'f32' (got {mode!r})")
+    return mode == "f16"
 
-    def __init__(self, sink, stage):
+
+def default_host_threads():
+    """Host threads for widening the compact format: the process's share of the CPUs it may run on (torchrun starts
+    one process per GPU), at most 16."""
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        cpus = os.cpu_count() or 1
+    share = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    return int(os.environ.get("NNAM_HOST_THREADS", max(1, min(16, cpus // share))))
+
+
+class _ChunkWriter:
+    """Helper thread that finishes chunks in submission order once their D2H copy into a pinned staging buffer has
+    completed: widens the compact format into the caller's array (or a scratch block) and / or hands the float32 rows
+    to a RowSink."""
+
+    def __init__(self, stage, compact, out, sink, n_out, threads):
         import queue
-        self.sink, self.stage = sink, stage
+        self.stage, self.compact, self.out, self.sink, self.n_out, self.threads = stage, compact, out, sink, n_out, threads
+        self.scratch = None
         self.free = [threading.Event(), threading.Event()]
         for e in self.free:
             e.set()
@@ -501,6 +551,22 @@ class _SinkWriter:
         self.err = None
         self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
+
+    def _finish(self, buf, r0, r1):
+        rows = r1 - r0
+        data, ref = self.stage[buf]
+        if not self.compact:
+            self.sink.write(r0, r1, data[:rows].numpy())
+            return
+        if self.out is not None:
+            dst = self.out[r0:r1]
+        else:
+            if self.scratch is None or self.scratch.shape[0] < rows:
+                self.scratch = np.empty((rows, self.n_out), dtype=np.float32)
+            dst = self.scratch[:rows]
+        ops.widen_f16_host(data, ref, dst, self.threads)
+        if self.sink is not None:
+            self.sink.write(r0, r1, dst)
 
     def _run(self):
         while True:
@@ -511,7 +577,7 @@ class _SinkWriter:
             try:
                 if self.err is None:
                     ev.synchronize()
-                    self.sink.write(r0, r1, self.stage[buf][:r1 - r0].numpy())
+                    self._finish(buf, r0, r1)
             except BaseException as e:  # noqa: BLE001  (re-raised on the caller's thread by close())
                 self.err = e
             finally:

@@ -152,8 +152,9 @@ def linear_bias_act(a_hi, a_lo, w_hi, w_lo, bias, M, N, K, act="identity", out_k
 
 
 def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=None, prior=None, prior_scale=1.0,
-         final_normalize=True, out=None, out_row_map=None):
-    """K4.  logits: one (rows, ld) f32 tensor or a list of them (ensemble)."""
+         final_normalize=True, out=None, out_row_map=None, out16=None):
+    """K4.  logits: one (rows, ld) f32 tensor or a list of them (ensemble).  ``out16`` = (fp16 (rows_out, ld16), f32
+    (rows_out,)) selects the compact transfer format (nnam_head_f16) instead of the float32 ``out``."""
     if isinstance(logits, torch.Tensor):
         logits = [logits]
     for t in logits:
@@ -163,7 +164,11 @@ def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=No
         raise NnamError("head: all inputs must share one leading dimension")
     if rows is None:
         rows = logits[0].shape[0]
-    if out is None:
+    if out16 is not None:
+        o16, ref = out16
+        _req(o16, torch.float16, "out16")
+        _req(ref, torch.float32, "row_ref")
+    elif out is None:
         out = torch.empty((rows, n_classes), dtype=torch.float32, device=logits[0].device)
     _req(out, torch.float32, "out")
     k = len(logits)
@@ -176,6 +181,13 @@ def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=No
             _req(t, torch.float32, "rpl")
     _req(prior, torch.float32, "prior")
     _req(out_row_map, torch.int32, "out_row_map")
+    if out16 is not None:
+        with _Prof("head", rows * n_classes * (4 * k + 2)):
+            check(_native.lib().nnam_head_f16(ptrs, wts, k, ld_in, int(bool(pre_normalize)), _ptr(rw), _ptr(rb),
+                                              _ptr(rlb), _ptr(prior), float(prior_scale), int(bool(final_normalize)),
+                                              _ptr(o16), o16.stride(0), _ptr(ref), rows, n_classes, _ptr(out_row_map),
+                                              _stream()))
+        return out16
     with _Prof("head", rows * n_classes * 4 * (k + 1)):
         if out_row_map is None:
             check(_native.lib().nnam_head(ptrs, wts, k, ld_in, int(bool(pre_normalize)), _ptr(rw), _ptr(rb),
@@ -187,6 +199,21 @@ def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=No
                                                   int(bool(final_normalize)), _ptr(out), out.stride(0), rows,
                                                   n_classes, _ptr(out_row_map), _stream()))
     return out
+
+
+def widen_f16_host(src16, row_ref, dst, threads=1):
+    """HOST op: dst[r] = float(src16[r, :C]) + row_ref[r] for the rows of the compact transfer format (see ``head``).
+    src16: (rows, ld16) fp16 host tensor / array, row_ref: (rows,) f32, dst: (rows, C) f32 C-contiguous NumPy array."""
+    rows, cols = dst.shape
+    if rows == 0:
+        return dst
+    if src16.shape[0] < rows or row_ref.shape[0] < rows or dst.strides[1] != 4:
+        raise NnamError("widen: shape mismatch")
+    sp = src16.data_ptr() if isinstance(src16, torch.Tensor) else src16.ctypes.data
+    rp = row_ref.data_ptr() if isinstance(row_ref, torch.Tensor) else row_ref.ctypes.data
+    ld16 = src16.stride(0) if isinstance(src16, torch.Tensor) else src16.strides[0] // 2
+    check(_native.lib().nnam_widen_f16_host(sp, ld16, rp, dst.ctypes.data, dst.strides[0] // 4, rows, cols, int(threads)))
+    return dst
 
 
 def gather_transform(x, row_map, add_shift=None, rescale=None, ivec=None, out_kind=OUT_BF16, ldo=None, out=None):

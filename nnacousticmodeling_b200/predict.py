@@ -23,7 +23,7 @@ def _devices(gpu):
 
 
 def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft, progress=True, ivectors=None,
-            out=None, fix_timedelay_tail=False, head=None, presliced=False, sink=None):
+            out=None, fix_timedelay_tail=False, head=None, presliced=False, sink=None, transfer=None):
     """predict_folds.py:27-95.  Returns (N, num_classes) float32 log-softmax outputs.
 
     Extensions: ``ivectors`` (N, I) are appended AFTER splice + transform (train.py:255-258 /
@@ -33,7 +33,10 @@ def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft,
     (an ``engine.HeadSpec``: logit mean of evaluate.py:35-51, log-prob mean of predict_folds.py:199-219, RPL4,
     prior); ``presliced`` says ``x`` is already spliced/transformed (the evaluate.py data flow); ``sink`` (an
     ``engine.RowSink``) receives the output rows chunk by chunk instead of an array being returned (the CLI streams
-    them into the .npy file while the next chunk is computed).
+    them into the .npy file while the next chunk is computed); ``transfer`` = "f32" | "f16" | None picks how rows cross
+    PCIe (engine.use_compact_transfer: the 16-bit precision modes send fp16 offsets from each row's maximum -- half
+    the bytes, <= 2^-12 relative to an entry's distance from the maximum -- and host threads widen them back to the
+    float32 layout; the fp32-accurate mode sends float32).
 
     The returned array is page-locked when the function allocates it: the device->host copies of the (N, C) matrix
     -- 7.6 KB per frame, the end-to-end bottleneck -- then run asynchronously at PCIe speed under the computation.
@@ -43,7 +46,7 @@ def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft,
     n = x.shape[0]
     if sink is not None and len(devs) == 1 and not is_nn_recurrent(network) and n > 0:
         engine.ff_forward_frames(model, x, ft, int(winlen) // 2, None, 0, n, ivectors=ivectors, device=devs[0],
-                                 head=head, presliced=presliced, sink=sink)
+                                 head=head, presliced=presliced, sink=sink, transfer=transfer)
         return None
     if out is None:
         out = engine.empty_pinned((n, num_classes)) if n > 0 else np.zeros((0, num_classes), dtype=np.float32)
@@ -53,6 +56,7 @@ def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft,
         if sink is not None:
             return None
         return out
+    threads = max(1, engine.default_host_threads() // len(devs))  # per device: host threads widening compact rows
     if is_nn_recurrent(network):
         from . import recurrent_engine
         if offsets is None:
@@ -62,14 +66,16 @@ def predict(model, x, offsets, num_classes, network, gpu, winlen, timedelay, ft,
         engine.run_sharded(
             lambda sh, d: recurrent_engine.forward_utterances(model, x, offsets, out, sh[0], sh[1], ft=ft,
                                                               ivectors=ivectors, timedelay=timedelay, device=d,
-                                                              fix_timedelay_tail=fix_timedelay_tail, head=head),
+                                                              fix_timedelay_tail=fix_timedelay_tail, head=head,
+                                                              transfer=transfer, host_threads=threads),
             shards, devs)
     else:
         splice = int(winlen) // 2
         shards = engine.partition_frames(n, len(devs))
         engine.run_sharded(
             lambda sh, d: engine.ff_forward_frames(model, x, ft, splice, out, sh[0], sh[1], ivectors=ivectors,
-                                                   device=d, head=head, presliced=presliced),
+                                                   device=d, head=head, presliced=presliced, transfer=transfer,
+                                                   host_threads=threads),
             shards, devs)
     if sink is not None:  # recurrent nets finish utterance subsets out of row order, several devices interleave:
         sink.write(0, n, out)  # the rows go to the sink in one piece at the end

@@ -15,7 +15,7 @@ import os
 import numpy as np
 import torch
 
-from . import ops
+from . import engine, ops
 from ._native import NnamError, RnnDesc
 from .engine import HeadSpec, LinearDev, _as_host_tensor, _dev_vec, _device, get_plan
 from .ops import OUT_BF16, OUT_BF16_SPLIT, OUT_F32, round_up
@@ -669,9 +669,10 @@ def _phase_split(lens):
 
 
 def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, out_dev, timedelay, fix_timedelay_tail,
-                   nb, device, stepwise):
+                   nb, device, stepwise, out16=None):
     """One subset of utterances (start frame relative to the shard and length of each) through the whole net:
-    packed gather -> layers -> output GEMM -> head, which scatters the rows into ``out_dev`` (all frames of the shard)."""
+    packed gather -> layers -> output GEMM -> head, which scatters the rows into ``out_dev`` (all frames of the shard)
+    or, with ``out16`` = (fp16 rows, row maxima), into the compact transfer format (ops.head)."""
     plan = plans[0]
     ws = plan.ws
     split = plan.split
@@ -734,15 +735,17 @@ def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, o
         pl.out(h_hi, h_lo, rows, "identity", OUT_F32, out=(lg, None))
         logits.append(lg)
     for u in np.nonzero(lens < timedelay)[0]:  # utterances shorter than the delay have rows no packed row maps to
-        out_dev[int(starts[u]):int(starts[u] + lens[u])].zero_()
+        for t in ((out_dev,) if out16 is None else out16):
+            t[int(starts[u]):int(starts[u] + lens[u])].zero_()
     prior = _dev_vec(head.prior, device)
     rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
     ops.head(logits, n_out, rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
-             prior_scale=head.prior_scale, final_normalize=head.final_normalize, out=out_dev, out_row_map=d_dst)
+             prior_scale=head.prior_scale, final_normalize=head.final_normalize, out=out_dev, out_row_map=d_dst,
+             out16=out16)
 
 
 def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, timedelay=0, device=0, head=None,
-                       fix_timedelay_tail=False, nb=DEFAULT_BATCH):
+                       fix_timedelay_tail=False, nb=DEFAULT_BATCH, transfer=None, host_threads=None):
     """Recurrent hot path on ONE device for utterances [u0, u1) (predict_folds.py:28-68 semantics).
 
     model: one recurrent spec or a list of them (ensemble: the logits are combined in the head, evaluate.py:35-51).
@@ -750,7 +753,9 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
     tensor, rows [offsets[u0], offsets[u1]) are written.  Output frame f of an utterance is the network output at
     step f + timedelay; like the reference, the last ``timedelay`` frames stay 0 unless fix_timedelay_tail.
     With a host ``out`` a large shard is computed in two subsets of utterances (:func:`_phase_split`) and the copy of
-    the first one to the host runs under the computation of the second.
+    the first one to the host runs under the computation of the second.  ``transfer`` / ``host_threads``: as in
+    engine.ff_forward_frames -- in the 16-bit modes the rows cross PCIe in the compact format (fp16 offsets from the row
+    maximum) into a pinned staging area and host threads widen them into ``out`` while the GPU computes the next subset.
     """
     models = list(model) if isinstance(model, (list, tuple)) else [model]
     device = _device(device)
@@ -794,18 +799,32 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
                             f"{x.shape[1] + (0 if ivectors is None else ivectors.shape[1])}")
         n_out = models[0].n_out
         on_dev = isinstance(out, torch.Tensor) and out.is_cuda
-        out_dev = out[f_lo:f_hi] if on_dev else ws.get("rnn.out", f_hi - f_lo, n_out, torch.float32)
+        n_rows = f_hi - f_lo
+        compact = (not on_dev) and engine.use_compact_transfer(plan, transfer)
+        out16 = stage = None
+        if compact:
+            ld16 = round_up(n_out, 8)
+            out16 = (ws.get("rnn.out16", n_rows, ld16, torch.float16), ws.get("rnn.ref", n_rows, 1, torch.float32).view(-1))
+            stage = plan.__dict__.get("_stage16")  # pinned staging of the shard's compact rows, grown on demand
+            if stage is None or stage[0].shape[0] < n_rows or stage[0].shape[1] != ld16:
+                stage = plan._stage16 = (torch.empty((n_rows, ld16), dtype=torch.float16, pin_memory=True),
+                                         torch.empty((n_rows,), dtype=torch.float32, pin_memory=True))
+            out_dev = None
+        else:
+            out_dev = out[f_lo:f_hi] if on_dev else ws.get("rnn.out", n_rows, n_out, torch.float32)
         phases = [np.arange(len(lens))] if (on_dev or stepwise) else _phase_split(lens)
         main = torch.cuda.current_stream()
         side = None
+        pending = []  # compact: (copy-done event, [(r0, r1), ...]) per phase, widened on the host below
         for idx in phases:
             whole = len(idx) == len(lens)
             _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts if whole else starts[idx],
-                           lens if whole else lens[idx], out_dev, timedelay, fix_timedelay_tail, nb, device, stepwise)
+                           lens if whole else lens[idx], out_dev, timedelay, fix_timedelay_tail, nb, device, stepwise,
+                           out16=out16)
             if on_dev:
                 continue
-            out_host = _as_host_tensor(out)
-            if len(phases) == 1:
+            out_host = None if compact else _as_host_tensor(out)
+            if len(phases) == 1 and not compact:
                 out_host[f_lo:f_hi].copy_(out_dev, non_blocking=True)
                 continue
             # rows of this subset, as maximal runs of neighbouring utterances, on the copy stream
@@ -816,11 +835,31 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
             done = torch.cuda.Event()
             done.record(main)
             brk = np.nonzero(np.diff(idx) != 1)[0] + 1
+            runs = []
             with torch.cuda.stream(side):
                 side.wait_event(done)
                 for run in np.split(idx, brk):
                     r0, r1 = int(starts[run[0]]), int(starts[run[-1]] + lens[run[-1]])
-                    out_host[f_lo + r0:f_lo + r1].copy_(out_dev[r0:r1], non_blocking=True)
+                    if compact:
+                        stage[0][r0:r1].copy_(out16[0][r0:r1], non_blocking=True)
+                        stage[1][r0:r1].copy_(out16[1][r0:r1], non_blocking=True)
+                        runs.append((r0, r1))
+                    else:
+                        out_host[f_lo + r0:f_lo + r1].copy_(out_dev[r0:r1], non_blocking=True)
+                if compact:
+                    copied = torch.cuda.Event()
+                    copied.record(side)
+                    pending.append((copied, runs))
+        # compact format: every launch of every phase is queued by now; widen phase k on the host while the GPU is
+        # still busy with phase k+1
+        out_np = None
+        if pending:
+            out_np = out.numpy() if isinstance(out, torch.Tensor) else out
+            threads = host_threads or engine.default_host_threads()
+        for copied, runs in pending:
+            copied.synchronize()
+            for r0, r1 in runs:
+                ops.widen_f16_host(stage[0][r0:r1], stage[1][r0:r1], out_np[f_lo + r0:f_lo + r1], threads)
         main.synchronize()
         if side is not None:
             side.synchronize()

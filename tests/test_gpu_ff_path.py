@@ -132,3 +132,30 @@ def test_npz_roundtrip_and_reload_invalidate_plan(nn, tmp_path):
     p2 = {k: v * 0.5 for k, v in p.items()}
     m2.load_params(p2)
     assert np.abs(m2(xb) - O.mlp_forward(p2, xb, 2)).max() < 1e-3
+
+
+def test_compact_transfer_matches_float32_transfer(nn, golden_dir):
+    """predict() in a 16-bit mode sends fp16 offsets from each row's maximum over PCIe (half the bytes) and widens them
+    on the host: against the float32 transfer of the same pass the argmax is unchanged, the best class is within 1e-5
+    and every entry within 2^-11 of its distance from the row maximum; shards and chunks stay bit-identical."""
+    from nnacousticmodeling_b200 import engine
+    x, off, iv = O.synth_set(21, 40, ivec_dim=100)
+    ft = nn.loadKaldiFeatureTransform(os.path.join(golden_dir, "final.feature_transform"))
+    m, _ = _mlp(nn, 16, 540, 512, 3, 1909, precision="fp16")
+    f32 = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv, transfer="f32")
+    f16 = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv)  # 16-bit mode default: compact
+    assert not np.array_equal(f32, f16)
+    dist = f32.max(axis=1, keepdims=True) - f32
+    assert np.all(np.abs(f16 - f32) <= 2.0 ** -11 * dist + 2e-5)
+    assert np.array_equal(f16.argmax(axis=1), f32.argmax(axis=1))
+    pageable = np.full((len(x), 1909), 7.0, np.float32)  # the destination need not be pinned in this format
+    assert nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv, out=pageable) is pageable
+    assert np.array_equal(pageable, f16)
+    parts = np.zeros_like(f16)
+    for f0, f1 in nn.partition_frames(len(x), 3):
+        engine.ff_forward_frames(m, x, ft, 5, parts, f0, f1, ivectors=iv, device=0, chunk=3000)
+    assert np.array_equal(parts, f16)
+    m.precision = "fp32"  # the fp32-accurate mode keeps float32 rows unless asked otherwise
+    a = nn.predict(m, x[:2000], None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv[:2000])
+    b = nn.predict(m, x[:2000], None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv[:2000], transfer="f32")
+    assert np.array_equal(a, b)

@@ -146,6 +146,42 @@ def test_head_ensembles_rpl_and_shapes(ops, dev, c, rows, ld):
     assert np.abs(got - (ys[0] + ys[1]) / 2).max() < 1e-5
 
 
+def test_head_compact_transfer_format(ops, dev):
+    """nnam_head_f16 + nnam_widen_f16_host: out = fp16(y - rowmax) + rowmax.  Entries near the row maximum keep float32-like
+    resolution (argmax unchanged), the tail keeps 11 bits of its distance from the maximum; scatter map and zero rows
+    (quirk Q4) included; single-input fast kernel and the generic ensemble kernel."""
+    rng = np.random.default_rng(11)
+    rows, c = 1500, 1909
+    ys = [(3.0 * rng.standard_normal((rows, c))).astype(np.float32) for _ in range(2)]
+    yd = []
+    for a in ys:
+        buf = torch.zeros(rows, 1920, device=dev)
+        buf[:, :c] = _t(a, dev)
+        yd.append(buf)
+    ap = (-3 + rng.standard_normal(c)).astype(np.float32)
+    rmap = rng.permutation(rows).astype(np.int32)
+    rmap[5], rmap[77] = -1, -2 - int(rmap[5])  # row 5 dropped, row 77 zero-fills the output row row 5 would have had
+    for logits, want in ((yd[0], O.head(ys[0], ap[None, :])),
+                         (yd, O.head((ys[0] + ys[1]) / np.float32(2), ap[None, :]))):
+        o16 = torch.full((rows, 1912), 9.0, dtype=torch.float16, device=dev)
+        ref = torch.full((rows,), 9.0, device=dev)
+        ops.head(logits, c, prior=_t(ap, dev), out16=(o16, ref), out_row_map=_t(rmap, dev))
+        got = np.empty((rows, c), np.float32)
+        ops.widen_f16_host(o16.cpu(), ref.cpu(), got, threads=3)
+        exp = np.zeros_like(got)
+        for r in range(rows):
+            if rmap[r] >= 0:
+                exp[rmap[r]] = want[r]
+        keep = np.ones(rows, bool)
+        keep[-2 - rmap[77]] = False
+        assert np.all(got[-2 - rmap[77]] == 0)
+        dist = exp[keep].max(axis=1, keepdims=True) - exp[keep]
+        assert np.all(np.abs(got[keep] - exp[keep]) <= 2.0 ** -11 * dist + 2e-5)
+        assert np.array_equal(got[keep].argmax(axis=1), exp[keep].argmax(axis=1))
+        top = np.take_along_axis(got[keep] - exp[keep], exp[keep].argmax(axis=1)[:, None], axis=1)
+        assert np.abs(top).max() < 1e-5  # the best class keeps float32 resolution
+
+
 # ----------------------------------------------------------------------------------------- K2
 @pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1, 16, 8), (300, 1024, 544), (1000, 1909, 440), (77, 40, 40),
                                    (2048, 2048, 2048), (513, 2048, 140), (129, 1909, 1024),
