@@ -856,10 +856,20 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         if pending:
             out_np = out.numpy() if isinstance(out, torch.Tensor) else out
             threads = host_threads or engine.default_host_threads()
-        for copied, runs in pending:
-            copied.synchronize()
-            for r0, r1 in runs:
-                ops.widen_f16_host(stage[0][r0:r1], stage[1][r0:r1], out_np[f_lo + r0:f_lo + r1], threads)
+        if pending:
+            # a phase is hundreds of short row runs (its utterances lie all over the shard): the runs, cut into pieces of
+            # <= 4096 rows, are spread over a pool of host threads (the C call releases the GIL)
+            from concurrent.futures import ThreadPoolExecutor
+
+            def widen(piece):
+                a, b = piece
+                ops.widen_f16_host(stage[0][a:b], stage[1][a:b], out_np[f_lo + a:f_lo + b], 1)
+
+            with ThreadPoolExecutor(max_workers=threads) as pool:
+                for copied, runs in pending:
+                    copied.synchronize()
+                    pieces = [(a, min(a + 4096, r1)) for r0, r1 in runs for a in range(r0, r1, 4096)]
+                    list(pool.map(widen, pieces))
         main.synchronize()
         if side is not None:
             side.synchronize()
