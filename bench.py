@@ -522,7 +522,7 @@ def run_ours(args):
             b.step_e2e()
         e2e_s = max_over_ranks(timed_host(torch, b.step_e2e, steps, barrier))
         from nnacousticmodeling_b200 import engine
-        compact = engine.use_compact_transfer(engine.get_plan(b.members[0], local))
+        compact = engine.use_compact_transfer(engine.get_plan(b.members[0], local), recurrent=b.recurrent)
         if compact:  # fp16 offsets (rows padded to 8 columns) + one float32 maximum per row
             d2h = n * ((N_CLASSES + 7) // 8 * 8 * 2 + 4)
         host_vs_dev = float((torch.from_numpy(b.out_host[:65536]).to(dev) - b.out_dev[:65536]).abs().max())

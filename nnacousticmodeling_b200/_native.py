@@ -14,7 +14,7 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libnnam_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_wide.cu", "recurrent_wide_gru.cu", "peephole.cu",
+SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_mc.cu", "recurrent_wide.cu", "recurrent_wide_gru.cu", "peephole.cu",
            "host_widen.cpp"]  # .cpp = host-only code, compiled with the host C++ compiler
 # measured dead end kept for reference (DSMEM all-gather recurrence); NNAM_WITH_CLUSTER_EXPERIMENT=1 builds it in
 EXPERIMENTAL_SOURCES = ["experimental/recurrent_cluster.cu"]

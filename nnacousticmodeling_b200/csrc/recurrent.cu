@@ -737,12 +737,16 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   const int max_groups = sm_count() / G;
   if (d->n_groups < 1 || d->n_groups > max_groups)
     return set_error(NNAM_ERR_ARG, "rnn: n_groups %d outside [1, %d]", d->n_groups, max_groups);
-  if (d->streams != cfg->s)
+  const bool mc_plan = !wide && !d->h0_hi && !d->c0 && !d->c_out && rnn_mc_groups(d->cell, H, d->batch, d->nsplit) > 0;
+  if (d->streams != (mc_plan ? 1 : cfg->s))
     return set_error(NNAM_ERR_ARG, "rnn: descriptor built for %d streams per group, this configuration runs %d "
                      "(ask nnam_rnn_plan)", d->streams, cfg->s);
   // experimental DSMEM variant: groups are independent clusters (no carried state through this path)
   const bool use_cluster = m_rows == 128 && cfg->s == 1 && !d->h0_hi && !d->c0 && !d->c_out &&
                            rnn_cluster_groups(d->cell, H, d->batch, d->nsplit) > 0;
+  // cluster + TMA-multicast exchange (recurrent_mc.cu): the low-latency kernel for 32-slot batches without carried state
+  const int mc_groups = (!wide && !d->h0_hi && !d->c0 && !d->c_out) ? rnn_mc_groups(d->cell, H, d->batch, d->nsplit) : 0;
+  const bool use_mc = mc_groups > 0 && d->streams == 1 && d->n_groups <= mc_groups;
 
   RnnTmaps tm;
   int rc;
@@ -807,6 +811,7 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   p.prof = static_cast<long long*>(d->debug_cycles);
   if (p.h0_hi && d->nsplit == 3 && !p.h0_lo) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs h0_lo with h0_hi");
 
+  if (use_mc) return rnn_mc_launch(d->cell, tm, p, G, H, stream);
   if (use_cluster) return rnn_cluster_launch(tm, p, G, H, stream);
   if (wide) {
     cudaError_t ew = cudaMemsetAsync(d->counters, 0, sizeof(unsigned int) * d->n_groups * cfg->s, stream);
@@ -863,8 +868,17 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
     if (cl < *max_groups) *max_groups = cl;
     cycles = 7000;
   }
+  int n_streams = cfg->s;
+  const int mc = rnn_mc_groups(cell, hidden, batch, nsplit);
+  if (mc > 0) {  // cluster + multicast kernel: fewer resident groups (clusters of 16 CTAs), shorter step, one stream
+    *group_ctas = 4 * hidden / 128;
+    *max_groups = mc;
+    n_streams = 1;
+    // measured, profiles/r02_k3_phase_cycles.md
+    cycles = cell == NNAM_CELL_GRU ? 8000 : 4300;
+  }
   if (step_cycles) *step_cycles = cycles;
-  if (streams) *streams = cfg->s;
+  if (streams) *streams = n_streams;
   return NNAM_OK;
 }
 

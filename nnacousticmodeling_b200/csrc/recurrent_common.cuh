@@ -110,6 +110,9 @@ inline int rnn_cluster_launch(const RnnTmaps&, const RnnParams&, int, int, cudaS
   return set_error(NNAM_ERR_UNSUPPORTED, "rnn: built without the cluster experiment");
 }
 #endif
+// recurrent_mc.cu: cluster + TMA-multicast exchange, 32 slots per batch (the critical-path kernel)
+int rnn_mc_groups(int cell, int hidden, int batch, int nsplit);
+int rnn_mc_launch(int cell, const RnnTmaps& tm, const RnnParams& p, int G, int hidden, cudaStream_t stream);
 // recurrent_wide.cu: LSTM / bf16 / 128 slots per batch
 bool rnn_wide_applies(int cell, int hidden, int batch, int nsplit);
 int rnn_wide_launch(const RnnTmaps& tm, const RnnParams& p, int hidden, cudaStream_t stream);

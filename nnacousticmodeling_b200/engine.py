@@ -514,11 +514,14 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
     return out
 
 
-def use_compact_transfer(plan, transfer=None):
+def use_compact_transfer(plan, transfer=None, recurrent=False):
     """Does a host-bound pass of ``plan`` use the compact (fp16 offsets + row maximum) transfer format?  Explicit
-    ``transfer`` ("f16" / "f32") wins, then the environment (NNAM_TRANSFER), then the precision mode: the 16-bit modes
-    (tolerance 5e-2) take it, the fp32-accurate mode (tolerance 1e-3) keeps float32 rows."""
-    mode = transfer or os.environ.get("NNAM_TRANSFER") or ("f32" if plan.split else "f16")
+    ``transfer`` ("f16" / "f32") wins, then the environment (NNAM_TRANSFER), then the path and precision mode: the
+    feed-forward path in a 16-bit mode (tolerance 5e-2) takes it -- its chunks stream, so the host widens chunk i while
+    chunk i+1 crosses PCIe (measured +22 % end to end on cfg2).  The fp32-accurate mode (tolerance 1e-3) keeps float32
+    rows, and so does the recurrent path: its rows only exist after the last layer, the widening cannot hide under
+    anything, and it measured 3-7 % slower than the plain copy (profiles/r02_transfer.md)."""
+    mode = transfer or os.environ.get("NNAM_TRANSFER") or ("f32" if (plan.split or recurrent) else "f16")
     if mode not in ("f16", "f32"):
         raise NnamError(f"transfer must be 'f16' or 'f32' (got {mode!r})")
     return mode == "f16"

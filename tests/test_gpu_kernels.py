@@ -160,6 +160,7 @@ def test_head_compact_transfer_format(ops, dev):
         yd.append(buf)
     ap = (-3 + rng.standard_normal(c)).astype(np.float32)
     rmap = rng.permutation(rows).astype(np.int32)
+    lost = int(rmap[77])  # no logits row maps to this output row any more: it keeps whatever the buffer held
     rmap[5], rmap[77] = -1, -2 - int(rmap[5])  # row 5 dropped, row 77 zero-fills the output row row 5 would have had
     for logits, want in ((yd[0], O.head(ys[0], ap[None, :])),
                          (yd, O.head((ys[0] + ys[1]) / np.float32(2), ap[None, :]))):
@@ -173,8 +174,8 @@ def test_head_compact_transfer_format(ops, dev):
             if rmap[r] >= 0:
                 exp[rmap[r]] = want[r]
         keep = np.ones(rows, bool)
-        keep[-2 - rmap[77]] = False
-        assert np.all(got[-2 - rmap[77]] == 0)
+        keep[-2 - rmap[77]] = keep[lost] = False
+        assert np.all(got[-2 - rmap[77]] == 0) and np.all(got[lost] == 18.0)  # fp16(9) + 9: untouched
         dist = exp[keep].max(axis=1, keepdims=True) - exp[keep]
         assert np.all(np.abs(got[keep] - exp[keep]) <= 2.0 ** -11 * dist + 1e-4)  # 1e-4: the head's own fp32 error
         assert np.array_equal(got[keep].argmax(axis=1), exp[keep].argmax(axis=1))
