@@ -226,6 +226,12 @@ typedef struct NnamRnnDesc {
   const float* c0;             /* optional initial cell state (n_utts, H*n_dirs) fp32 */
   float* c_out;                /* optional final cell state, same shape */
   unsigned int* counters;      /* n_groups * streams words of scratch */
+  unsigned int* started;       /* optional, DEVICE-ACCESSIBLE HOST memory (pinned): thread 0 of every CTA stores started_tag
+                                  into started[blockIdx.x] as its first action.  A host that runs two launches side by side
+                                  (recurrent_engine.MixedSchedule) polls it to know that THIS launch is resident before it
+                                  submits the other one: the multicast kernel runs as clusters of 16 CTAs, which can only
+                                  be placed while whole GPCs are still free */
+  unsigned int started_tag;
   void* debug_cycles;          /* optional: int64[8] per CTA, per-phase SM cycle totals (profiling builds/tests) */
 } NnamRnnDesc;
 

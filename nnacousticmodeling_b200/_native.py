@@ -140,7 +140,7 @@ class RnnDesc(ctypes.Structure):
         ("batch_row0", c_void_p), ("batch_steps", c_void_p), ("batch_nutt", c_void_p), ("batch_base_off", c_void_p),
         ("base", c_void_p), ("utt_len", c_void_p),
         ("h0_hi", c_void_p), ("h0_lo", c_void_p), ("c0", c_void_p), ("c_out", c_void_p),
-        ("counters", c_void_p), ("debug_cycles", c_void_p),
+        ("counters", c_void_p), ("started", c_void_p), ("started_tag", ctypes.c_uint), ("debug_cycles", c_void_p),
     ]
 
 

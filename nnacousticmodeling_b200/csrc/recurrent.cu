@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
   static_assert(NBT % 4 == 0 && NBT >= 4, "a thread owns whole lane-quad groups of 4 slots");
   const int group = blockIdx.x / p.group_ctas;
   const int rank = blockIdx.x % p.group_ctas;
+  announce_started(p);
   if (group >= p.n_groups) return;
 
   const int H = KBT > 0 ? KBT * 64 : p.hidden;
@@ -363,7 +364,12 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
 
       // input projection of my gate row for my utterance slots at step s: independent loads (slots beyond the
       // active prefix re-read its last row, so no load is predicated or dependent on another)
-      auto load_gx = [&](int s, float (&dst)[NBT]) {
+      // Raw loads: the fp32 value (fp32-accurate mode) or the 16-bit pattern (16-bit modes) of my gate row for my utterance
+      // slots at step s.  Independent loads (slots beyond the active prefix re-read its last row, so no load is predicated
+      // or dependent on another); the 16-bit -> fp32 conversion waits until the values are USED, one step later, so the
+      // (DRAM-latency) loads never stall the thread that issued them (they cost ~1.3 k cycles per step when the conversion
+      // sat right behind the load, profiles/r02_k3_phase_cycles.md).
+      auto load_gx = [&](int s, uint32_t (&dst)[NBT]) {
         const int base_s = bp[s];
         const int n_act = bp[s + 1] - base_s;
 #pragma unroll
@@ -372,10 +378,13 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
           const int uu = u < n_act ? u : n_act - 1;
           const long long row = row0 + (bwd ? bp[s_len[uu] - 1 - s] : base_s) + uu;
           if (NSPLIT == 3)
-            dst[j] = __ldg(reinterpret_cast<const float*>(gx) + row * p.gx_ld);
+            dst[j] = __float_as_uint(__ldg(reinterpret_cast<const float*>(gx) + row * p.gx_ld));
           else
-            dst[j] = e16_to_f32(__ldg(reinterpret_cast<const uint16_t*>(gx) + row * p.gx_ld), f16);
+            dst[j] = __ldg(reinterpret_cast<const uint16_t*>(gx) + row * p.gx_ld);
         }
+      };
+      auto gx_val = [&](uint32_t raw) -> float {
+        return NSPLIT == 3 ? __uint_as_float(raw) : e16_to_f32(static_cast<uint16_t>(raw), f16);
       };
       // my value for (utterance u, my unit) -> staging tile (utterance-major, UNITS bf16 per row, hi [+ lo] planes)
       auto stage_put = [&](int u, float v) {
@@ -407,13 +416,14 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
         }
       };
 
-      float gxr[NBT];
+      uint32_t gxr[NBT];
       load_gx(0, gxr);
       for (int s = 0; s < T; ++s) {
         PROF_START();
         const int n_s = bp[s + 1] - bp[s];  // active utterances (prefix of the batch), >= 1
         const bool have_h = (s > 0) || has_h0;
-        float acc[NBT], gxn[NBT];
+        float acc[NBT];
+        uint32_t gxn[NBT];
         if (have_h) {
           if (s > 0)
             group_fetch((s - 1) & 1);  // h of step s-1 sits in exchange slot (s-1) & 1
@@ -455,7 +465,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
             float x[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float v = acc[4 * m + i] + gxr[4 * m + i] + ((gate == 1 || gate == 2) ? acc2[4 * m + i] : 0.0f);
+              const float v = acc[4 * m + i] + gx_val(gxr[4 * m + i]) + ((gate == 1 || gate == 2) ? acc2[4 * m + i] : 0.0f);
               const float t = tanh_sel<FAST_TANH>(gate == 0 ? v : 0.5f * v);
               x[i] = gate == 0 ? t : (gate == 3 ? v : fmaf(t, 0.5f, 0.5f));  // the output gate stays a pre-activation
             }
@@ -497,7 +507,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
             float x[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float v = acc[4 * m + i] + gxr[4 * m + i];
+              const float v = acc[4 * m + i] + gx_val(gxr[4 * m + i]);
               const float t = tanh_sel<FAST_TANH>(gate == 0 ? v : 0.5f * v);
               x[i] = gate == 0 ? t : fmaf(t, 0.5f, 0.5f);
             }
@@ -526,7 +536,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
             float x[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              x[i] = gxr[4 * m + i] + ubs + ((two_phase && gate == 2) ? 0.0f : acc[4 * m + i]);
+              x[i] = gx_val(gxr[4 * m + i]) + ubs + ((two_phase && gate == 2) ? 0.0f : acc[4 * m + i]);
             quad_transpose(x, gate);  // x = {z_pre, r_pre, cand_pre, pad} of utterance u_lo + 4m + gate
             zp[m] = x[0];
             hp[m] = x[2];
@@ -809,6 +819,8 @@ int rnn_seq(const NnamRnnDesc* d, cudaStream_t stream) {
   p.gru_flags = d->flags;
   p.f16 = d->elem == NNAM_ELEM_F16;
   p.prof = static_cast<long long*>(d->debug_cycles);
+  p.started = d->started;
+  p.started_tag = d->started_tag;
   if (p.h0_hi && d->nsplit == 3 && !p.h0_lo) return set_error(NNAM_ERR_ARG, "rnn: bf16x3 needs h0_lo with h0_hi");
 
   if (use_mc) return rnn_mc_launch(d->cell, tm, p, G, H, stream);
@@ -875,7 +887,7 @@ int rnn_plan(int cell, int hidden, int batch, int nsplit, int* group_ctas, int* 
     *max_groups = mc;
     n_streams = 1;
     // measured, profiles/r02_k3_phase_cycles.md
-    cycles = cell == NNAM_CELL_GRU ? 8000 : 4300;
+    cycles = 4300;
   }
   if (step_cycles) *step_cycles = cycles;
   if (streams) *streams = n_streams;

@@ -46,7 +46,17 @@ struct RnnParams {
   int gru_flags;
   int f16;                     // 16-bit element type of w / h / xchg / h0 / (nsplit 1) gx: 0 = bf16, 1 = fp16
   long long* prof;             // optional: 8 cycle accumulators per CTA (thread 0), phases of a step
+  unsigned int* started;       // optional (pinned host memory): started[blockIdx.x] = started_tag when the CTA starts
+  unsigned int started_tag;
 };
+
+// "this CTA is resident": one store into device-accessible host memory (NnamRnnDesc.started)
+__device__ __forceinline__ void announce_started(const RnnParams& p) {
+  if (p.started != nullptr && threadIdx.x == 0) {
+    *reinterpret_cast<volatile unsigned int*>(p.started + blockIdx.x) = p.started_tag;
+    __threadfence_system();
+  }
+}
 
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;

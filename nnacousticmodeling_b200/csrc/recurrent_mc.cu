@@ -2,7 +2,9 @@
 // exchanged by TMA MULTICAST -- no release/acquire counter, no polling, no per-CTA pull of the whole tile.
 //
 // Reference semantics as in recurrent.cu (L.LSTM / F.lstm per Python loop iteration, scripts/common/chainer_networks.py:
-// 44-62 driven by predict_folds.py:49-61; GRU family: scripts/common/MGRU.py:67-85).
+// 44-62 driven by predict_folds.py:49-61).  LSTM family only: the GRU step with a reset gate is TWO dependent exchanges,
+// and there this exchange (one L2 write + multicast read per phase) measured slower than the counter-based one of
+// rnn_seq_kernel (8.0 k against 6.0 k cycles per step, profiles/r02_k3_phase_cycles.md), so the GRU family stays there.
 //
 // Why: a step of rnn_seq_kernel is a chain of latencies (profiles/r01_k3_phase_cycles.md): slice stores -> red.release.gpu
 // (~1.1 k cycles) -> the peers' ld.acquire poll (~1 k) -> each of the 16 CTAs pulls the WHOLE h tile back from L2 by TMA
@@ -55,8 +57,8 @@ constexpr int MC_THREADS = 512;  // 16 warps: 4 warps per TMEM lane quarter, eac
 constexpr int MC_ROWS = 128;     // gate rows per CTA (32 whole units)
 constexpr int MC_UNITS = 32;
 
-// CELL: NNAM_CELL_LSTM | NNAM_CELL_GRU.  NB: utterance slots per batch (32).  KBT: H / 64.
-template <int CELL, int NB, int KBT>
+// NB: utterance slots per batch (32).  KBT: H / 64.
+template <int NB, int KBT>
 __global__ void __launch_bounds__(MC_THREADS, 1)
     rnn_seq_mc_kernel(const __grid_constant__ RnnTmaps tmaps, const RnnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -66,17 +68,13 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
   constexpr int SLICE = NB * MC_UNITS * 2;    // bytes of one CTA's slice of the tile
   constexpr int TILE = NB * H * 2;
   constexpr int LBO = NB * 16;
-  constexpr bool GRU = CELL == NNAM_CELL_GRU;
-  // GRU: a third tile for r*h.  ONE buffer is enough there: a peer sends r*h of step s+1 only after it has every h slice
-  // of step s, and a CTA sends that after its r*h MMA of step s -- the tile's last reader -- has completed.
-  constexpr int TILES = GRU ? 3 : 2;
-  // 128 KB of weights + 96 KB of tiles leave the GRU instance no room for the prefix-sum mirror (it reads `base` through
-  // L1 instead) nor for an alignment pad (the dynamic shared window is 1024-byte aligned on sm_100; checked below)
-  constexpr int BASE_SMEM = GRU ? 0 : RNN_BASE_SMEM;
+  constexpr int TILES = 2;
+  constexpr int BASE_SMEM = RNN_BASE_SMEM;
   const int G = p.group_ctas;                 // == cluster size
   const int group = blockIdx.x / G;
   const int rank = static_cast<int>(cluster_ctarank());
   const bool active = group < p.n_groups;     // uniform over the cluster
+  announce_started(p);
 
   if ((smem_u32(smem_raw) & 1023u) != 0) __trap();  // SWIZZLE_128B weight blocks need 1024-byte alignment
   uint8_t* w_s = smem_raw;                    // KBT * W_BLOCK, SWIZZLE_128B (TMA)
@@ -116,17 +114,14 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
   cluster_wait_acquire();
 
   const int my_row = quarter * 32 + lane;
-  const int gate = my_row & 3;          // LSTM: a, i, f, o   GRU: z, r, candidate, pad
+  const int gate = my_row & 3;          // a, i, f, o
   const int ul = my_row >> 2;           // unit inside the CTA's slice
-  const int unit = rank * MC_UNITS + ul;
   const int gate_col = rank * MC_ROWS + my_row;
   const uint32_t tmem_lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + u_lo;
   const int f16 = p.f16;
   const uint32_t idesc = make_idesc_e16_f32(MC_ROWS, NB, f16);
   const uint32_t stage_off = static_cast<uint32_t>((ul >> 3) * LBO + (ul & 7) * 2);  // + u * 16
   const uint16_t mask = static_cast<uint16_t>((1u << G) - 1u);
-  const bool gru_reset = GRU && (p.gru_flags & 1) != 0;
-  const int gru_act = (p.gru_flags >> 1) & 3;
   // my private spots in the exchange buffer: [group][tile][rank] slices
   uint8_t* xg = reinterpret_cast<uint8_t*>(p.xchg_hi) + (static_cast<size_t>(group) * TILES * G + rank) * SLICE;
 
@@ -137,7 +132,6 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
 #define PROF_MARK(i) do { if (prof_on) { const long long now = clock64(); prof_acc[i] += now - prof_t; prof_t = now; } } while (0)
 
   unsigned int g = 0;            // h exchanges so far (tile / barrier parity); runs across work items
-  unsigned int g2 = 0;           // r*h exchanges so far (GRU with reset gate)
   uint32_t w_phase = 0, mma_phase = 0;
   int cur_dir = -1;
 
@@ -177,27 +171,31 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
     }
     tc_fence_before();
   };
-  // My slice is complete in `stage`: copy it to my spot of exchange tile `tile_idx` (and, if dst != nullptr, to the
-  // layer output rows), then ONE thread multicasts it from there into tile `tile_idx` of every CTA of the cluster.
+  // My slice is complete in `stage` (tile layout).  Critical path: warp 0 alone copies the 2 KB to my spot of exchange tile
+  // `tile_idx` (4 x 16 bytes per lane) and one of its lanes multicasts it from there into tile `tile_idx` of every CTA of
+  // the cluster -- no second CTA barrier.  The other warps meanwhile store the slice into the layer output rows (if any).
   auto publish = [&](int tile_idx, __nv_bfloat16* dst_hi, int n_act, int s, const int* bp, long long row0, bool bwd,
                      int h_col0) {
     __syncthreads();  // staging writes of all warps are visible
-    uint8_t* spot = xg + static_cast<size_t>(tile_idx) * G * SLICE;
-    constexpr int CHUNKS = SLICE / 16;  // NB * 4
-    for (int q = tid; q < CHUNKS; q += MC_THREADS)
-      *reinterpret_cast<uint4*>(spot + q * 16) = *reinterpret_cast<const uint4*>(stage + q * 16);
-    if (dst_hi != nullptr) {
-      for (int q = tid; q < n_act * 4; q += MC_THREADS) {
+    if (warp == 0) {
+      uint8_t* spot = xg + static_cast<size_t>(tile_idx) * G * SLICE;
+      constexpr int CHUNKS = SLICE / 16;  // NB * 4
+#pragma unroll
+      for (int q = lane; q < CHUNKS; q += 32)
+        *reinterpret_cast<uint4*>(spot + q * 16) = *reinterpret_cast<const uint4*>(stage + q * 16);
+      __syncwarp();  // orders the lanes' global stores before the elected lane's proxy fence + bulk copy
+      if (elect_one()) {
+        fence_proxy_async_all();  // generic-proxy global writes -> visible to the async proxy (the bulk copy's read)
+        bulk_load_1d_multicast(tiles + tile_idx * TILE + rank * SLICE, spot, SLICE, &bar_x[tile_idx], mask);
+      }
+      __syncwarp();
+    } else if (dst_hi != nullptr) {
+      for (int q = tid - 32; q < n_act * 4; q += MC_THREADS - 32) {
         const int u = q >> 2, j = q & 3;  // 16-byte chunk j (8 units) of utterance u's 64-byte slice
         const uint4 v = *reinterpret_cast<const uint4*>(stage + j * LBO + u * 16);
         const int t_idx = bwd ? (s_len[u] - 1 - s) : s;
         *reinterpret_cast<uint4*>(dst_hi + (row0 + bp[t_idx] + u) * p.h_ld + h_col0 + rank * MC_UNITS + j * 8) = v;
       }
-    }
-    __syncthreads();  // every thread's global stores are ordered before thread 0's proxy fence + bulk copy
-    if (tid == 0) {
-      fence_proxy_async_all();  // generic-proxy global writes -> visible to the async proxy (the bulk copy's read)
-      bulk_load_1d_multicast(tiles + tile_idx * TILE + rank * SLICE, spot, SLICE, &bar_x[tile_idx], mask);
     }
   };
 
@@ -205,7 +203,6 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
     // arm the barriers of the first exchanges
     if (tid == 0) {
       mbar_expect_tx(&bar_x[1], static_cast<uint32_t>(TILE));  // slices of h step 0 land in tile 1
-      if (GRU) mbar_expect_tx(&bar_x[2], static_cast<uint32_t>(TILE));  // first r*h exchange
     }
     for (int it = p.group_item_start[group]; it < p.group_item_start[group + 1]; ++it) {
       const int b = p.item_batch[it];
@@ -235,13 +232,14 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
         for (int i = tid; i <= T; i += MC_THREADS) s_base[i] = __ldg(base + i);
       __syncthreads();
       const int* bp = base_in_smem ? s_base : base;
-      const float ub = GRU ? __ldg(p.u_bias[d] + gate_col) : 0.0f;
 
-      float st_reg[NBT / 4];  // LSTM: cell state c; GRU: hidden state h of (utterance u_lo + 4m + gate, unit)
+      float st_reg[NBT / 4];  // cell state c of (utterance u_lo + 4m + gate, my unit)
 #pragma unroll
       for (int m = 0; m < NBT / 4; ++m) st_reg[m] = 0.0f;
 
-      auto load_gx = [&](int s, float (&dst)[NBT]) {
+      // raw 16-bit loads; the conversion waits until the values are used, one step later, so the (DRAM-latency) loads
+      // never stall the thread that issued them
+      auto load_gx = [&](int s, uint16_t (&dst)[NBT]) {
         const int base_s = bp[s];
         const int n_act = bp[s + 1] - base_s;
 #pragma unroll
@@ -249,19 +247,19 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
           const int u = u_lo + j;
           const int uu = u < n_act ? u : n_act - 1;
           const long long row = row0 + (bwd ? bp[s_len[uu] - 1 - s] : base_s) + uu;
-          dst[j] = e16_to_f32(__ldg(gx + row * p.gx_ld), f16);
+          dst[j] = __ldg(gx + row * p.gx_ld);
         }
       };
       auto stage_put = [&](int u, float v) {
         *reinterpret_cast<uint16_t*>(stage + stage_off + u * 16) = f32_to_e16(v, f16);
       };
 
-      float gxr[NBT];
+      uint16_t gxr[NBT], gxn[NBT];
       load_gx(0, gxr);
       for (int s = 0; s < T; ++s, ++g) {
         PROF_START();
         const int n_s = bp[s + 1] - bp[s];
-        float acc[NBT], gxn[NBT];
+        float acc[NBT];
         // slices of h step g-1 are in tile g & 1, announced on bar_x[g & 1]; its use before was step g-3, consumed at g-2
         const int cur = static_cast<int>(g & 1u);
         if (g > 0) {
@@ -284,9 +282,9 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
           for (int j = 0; j < NBT; ++j) acc[j] = 0.0f;
         }
         PROF_MARK(2);
-        const bool have_h = s > 0;
+        __syncthreads();  // every warp has finished reading last step's staging slice (output rows / exchange spot)
 
-        if (!GRU) {
+        {
           // ---- chainer F.lstm: c = tanh(a) s(i) + s(f) c; h = s(o) tanh(c); s(x) = tanh(x/2)/2 + 1/2
 #pragma unroll
           for (int m = 0; m < NBT / 4; ++m) {
@@ -294,7 +292,7 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
             float x[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              const float v = acc[4 * m + i] + gxr[4 * m + i];
+              const float v = acc[4 * m + i] + e16_to_f32(gxr[4 * m + i], f16);
               const float t = tanh_fast(gate == 0 ? v : 0.5f * v);
               x[i] = gate == 0 ? t : fmaf(t, 0.5f, 0.5f);
             }
@@ -310,67 +308,12 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
           PROF_MARK(3);
           publish(cur ^ 1, p.h_hi, n_s, s, bp, row0, bwd, h_col0);
           PROF_MARK(4);
-        } else {
-          // ---- GRU family (MGRU.py:67-85): U terms and their biases exist only when h does (:70-83)
-          const float ubs = have_h ? ub : 0.0f;
-          const bool two_phase = gru_reset && have_h;  // r * h must go round the cluster before the candidate matmul
-          float zp[NBT / 4], hp[NBT / 4];
-#pragma unroll
-          for (int m = 0; m < NBT / 4; ++m) {
-            zp[m] = hp[m] = 0.0f;
-            if (u_lo + 4 * m >= n_s) break;
-            float x[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = gxr[4 * m + i] + ubs + ((two_phase && gate == 2) ? 0.0f : acc[4 * m + i]);
-            quad_transpose(x, gate);  // x = {z_pre, r_pre, cand_pre, pad}
-            zp[m] = x[0];
-            hp[m] = x[2];
-            if (two_phase) {
-              const int u = u_lo + 4 * m + gate;
-              const float r = fmaf(tanh_fast(0.5f * x[1]), 0.5f, 0.5f);
-              if (u < n_s) stage_put(u, r * st_reg[m]);
-            }
-          }
-          if (two_phase) {
-            publish(2, nullptr, n_s, s, bp, row0, bwd, h_col0);
-            mma_issue(2, g2 & 1u);
-            // warp 0 has consumed this phase: thread 0 re-arms the barrier for the next r*h exchange
-            if (tid == 0) mbar_expect_tx(&bar_x[2], static_cast<uint32_t>(TILE));
-            ++g2;
-            mma_collect(acc);  // row 4j+2 now holds U (r*h)
-          }
-#pragma unroll
-          for (int m = 0; m < NBT / 4; ++m) {
-            if (u_lo + 4 * m >= n_s) break;
-            float cand = hp[m];
-            if (two_phase) {
-              float y[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) y[i] = gate == 2 ? acc[4 * m + i] : 0.0f;
-              quad_transpose(y, gate);
-              cand += y[2];
-            }
-            const int u = u_lo + 4 * m + gate;
-            const float z = fmaf(tanh_fast(0.5f * zp[m]), 0.5f, 0.5f);
-            const float hb = gru_act == NNAM_ACT_RELU ? fmaxf(cand, 0.0f)
-                             : (gru_act == NNAM_ACT_SIGMOID ? fmaf(tanh_fast(0.5f * cand), 0.5f, 0.5f)
-                                : (gru_act == NNAM_ACT_TANH ? tanh_fast(cand) : cand));
-            const float h_new = have_h ? fmaf(z, hb, (1.0f - z) * st_reg[m]) : z * hb;
-            if (u < n_s) {
-              st_reg[m] = h_new;
-              stage_put(u, h_new);
-            }
-          }
-          PROF_MARK(3);
-          publish(cur ^ 1, p.h_hi, n_s, s, bp, row0, bwd, h_col0);
-          PROF_MARK(4);
         }
 #pragma unroll
         for (int j = 0; j < NBT; ++j) gxr[j] = gxn[j];
       }
     }
-    // the slices of the last step (and the last armed r*h barrier's phase is simply never completed) must have landed
-    // before anyone leaves: peers multicast into this CTA's shared memory
+    // the slices of the last step must have landed before anyone leaves: peers multicast into this CTA's shared memory
     if (g > 0 && warp == 0) mbar_wait(&bar_x[g & 1u], ((g - 1) >> 1) & 1u);
   }
   if (prof_on) {
@@ -391,17 +334,15 @@ __global__ void __launch_bounds__(MC_THREADS, 1)
 }
 
 // ------------------------------------------------------------------------------------ host side
-static size_t mc_smem_bytes(int cell, int nb, int hidden) {
-  const bool gru = cell == NNAM_CELL_GRU;
-  const size_t tiles = gru ? 3 : 2;
-  return static_cast<size_t>(hidden / 64) * MC_ROWS * 128 + tiles * nb * hidden * 2 + static_cast<size_t>(nb) * 64 + 128 +
-         static_cast<size_t>(nb) * 4 + (gru ? 0 : (RNN_BASE_SMEM + 1) * 4) + 16;
+static size_t mc_smem_bytes(int nb, int hidden) {
+  return static_cast<size_t>(hidden / 64) * MC_ROWS * 128 + 2 * static_cast<size_t>(nb) * hidden * 2 +
+         static_cast<size_t>(nb) * 64 + 128 + static_cast<size_t>(nb) * 4 + (RNN_BASE_SMEM + 1) * 4 + 16;
 }
 
-template <int CELL, int NB, int KBT>
+template <int NB, int KBT>
 static int mc_config(int G, cudaStream_t stream, cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid) {
-  auto kern = rnn_seq_mc_kernel<CELL, NB, KBT>;
-  const size_t smem = mc_smem_bytes(CELL, NB, KBT * 64);
+  auto kern = rnn_seq_mc_kernel<NB, KBT>;
+  const size_t smem = mc_smem_bytes(NB, KBT * 64);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return set_cuda_error(e, "rnn(mc): cudaFuncSetAttribute(smem)");
   if (G > 8) {
@@ -422,45 +363,43 @@ static int mc_config(int G, cudaStream_t stream, cudaLaunchConfig_t* cfg, cudaLa
   return NNAM_OK;
 }
 
-template <int CELL, int NB, int KBT>
+template <int NB, int KBT>
 static int mc_max_groups(int G) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  if (mc_config<CELL, NB, KBT>(G, nullptr, &cfg, attr, G) != NNAM_OK) return 0;
+  if (mc_config<NB, KBT>(G, nullptr, &cfg, attr, G) != NNAM_OK) return 0;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, rnn_seq_mc_kernel<CELL, NB, KBT>, &cfg) != cudaSuccess) {
+  if (cudaOccupancyMaxActiveClusters(&n, rnn_seq_mc_kernel<NB, KBT>, &cfg) != cudaSuccess) {
     cudaGetLastError();
     return 0;
   }
   return n;
 }
 
-template <int CELL, int NB, int KBT>
+template <int NB, int KBT>
 static int mc_launch(const RnnTmaps& tm, const RnnParams& p, int G, cudaStream_t stream) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[1];
-  const int rc = mc_config<CELL, NB, KBT>(G, stream, &cfg, attr, p.n_groups * G);
+  const int rc = mc_config<NB, KBT>(G, stream, &cfg, attr, p.n_groups * G);
   if (rc) return rc;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, rnn_seq_mc_kernel<CELL, NB, KBT>, tm, p);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, rnn_seq_mc_kernel<NB, KBT>, tm, p);
   if (e != cudaSuccess) return set_cuda_error(e, "rnn(mc): cudaLaunchKernelEx");
   return NNAM_OK;
 }
 
-#define NNAM_MC_DISPATCH(FN, ...)                                                                 \
-  do {                                                                                            \
-    if (cell == NNAM_CELL_LSTM && hidden == 512) return FN<NNAM_CELL_LSTM, 32, 8>(__VA_ARGS__);    \
-    if (cell == NNAM_CELL_LSTM && hidden == 256) return FN<NNAM_CELL_LSTM, 32, 4>(__VA_ARGS__);    \
-    if (cell == NNAM_CELL_GRU && hidden == 512) return FN<NNAM_CELL_GRU, 32, 8>(__VA_ARGS__);      \
-    if (cell == NNAM_CELL_GRU && hidden == 256) return FN<NNAM_CELL_GRU, 32, 4>(__VA_ARGS__);      \
+#define NNAM_MC_DISPATCH(FN, ...)                               \
+  do {                                                          \
+    if (hidden == 512) return FN<32, 8>(__VA_ARGS__);           \
+    if (hidden == 256) return FN<32, 4>(__VA_ARGS__);           \
   } while (0)
 
-static int mc_max_groups_dispatch(int cell, int hidden, int G) {
+static int mc_max_groups_dispatch(int hidden, int G) {
   NNAM_MC_DISPATCH(mc_max_groups, G);
   return 0;
 }
 
 // Resident clusters of the multicast variant for (cell, hidden, slots, precision), 0 if it does not apply:
-// LSTM / GRU family, single-pass 16-bit operands, 32 slots, H in {256, 512} (cluster of 8 / 16 CTAs), no carried state.
+// LSTM family, single-pass 16-bit operands, 32 slots, H in {256, 512} (cluster of 8 / 16 CTAs), no carried state.
 // NNAM_RNN_MC=0 switches it off (A/B measurements).
 int rnn_mc_groups(int cell, int hidden, int batch, int nsplit) {
   static const int enabled = [] {
@@ -468,21 +407,22 @@ int rnn_mc_groups(int cell, int hidden, int batch, int nsplit) {
     return (v != nullptr && v[0] == '0') ? 0 : 1;
   }();
   if (!enabled || nsplit != 1 || batch != 32 || (hidden != 256 && hidden != 512)) return 0;
-  if (cell != NNAM_CELL_LSTM && cell != NNAM_CELL_GRU) return 0;
-  if (mc_smem_bytes(cell, batch, hidden) > 227 * 1024) return 0;
+  if (cell != NNAM_CELL_LSTM) return 0;
+  if (mc_smem_bytes(batch, hidden) > 227 * 1024) return 0;
   const int G = 4 * hidden / MC_ROWS;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
-  static int cached[64][2][2] = {};  // [device][cell][hidden == 512]; racing writers store the same value
-  int& c = cached[dev][cell == NNAM_CELL_GRU ? 1 : 0][hidden == 512 ? 1 : 0];
+  static int cached[64][2] = {};  // [device][hidden == 512]; racing writers store the same value
+  int& c = cached[dev][hidden == 512 ? 1 : 0];
   if (c == 0) {
-    const int n = mc_max_groups_dispatch(cell, hidden, G);
+    const int n = mc_max_groups_dispatch(hidden, G);
     c = n > 0 ? n : -1;
   }
   return c > 0 ? c : 0;
 }
 
 int rnn_mc_launch(int cell, const RnnTmaps& tm, const RnnParams& p, int G, int hidden, cudaStream_t stream) {
+  if (cell != NNAM_CELL_LSTM) return set_error(NNAM_ERR_UNSUPPORTED, "rnn(mc): LSTM family only");
   NNAM_MC_DISPATCH(mc_launch, tm, p, G, stream);
   return set_error(NNAM_ERR_UNSUPPORTED, "rnn(mc): no instance for this configuration");
 }

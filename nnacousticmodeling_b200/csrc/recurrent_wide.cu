@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(WIDE_THREADS, 1)
   constexpr int NB = WIDE_NB;
   const int group = blockIdx.x / p.group_ctas;
   const int rank = blockIdx.x % p.group_ctas;
+  announce_started(p);
   if (group >= p.n_groups) return;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -312,6 +313,7 @@ __global__ void __launch_bounds__(S * WPS * 32, 1)
   constexpr int NB = WIDE_NB;
   const int group = blockIdx.x / p.group_ctas;
   const int rank = blockIdx.x % p.group_ctas;
+  announce_started(p);
   if (group >= p.n_groups) return;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1)
   constexpr bool RESET = NG == 3;
   const int group = blockIdx.x / p.group_ctas;
   const int rank = blockIdx.x % p.group_ctas;
+  announce_started(p);
   if (group >= p.n_groups) return;
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
