@@ -576,7 +576,7 @@ def run_ours(args):
                               "argmax_agreement_raw": float(np.mean(got[keep].argmax(axis=1) == y_cpu[keep].argmax(axis=1))),
                               "gate": "north_star: <= 5e-2 and >= 0.995 (16-bit modes), <= 1e-3 (fp32 mode)"}
             if args.cpu_python_prepare and not b.recurrent:
-                r2, dt2, s2, _, _ = cpu_reference_rate(args.workload, min(args.cpu_sample, 65536), params, b.x, b.offsets,
+                r2, dt2, s2, _, _ = cpu_reference_rate(args.workload, min(args.cpu_sample, 32768), params, b.x, b.offsets,
                                                        b.iv, with_python_prepare=True)
                 line["cpu_baseline"]["with_reference_python_splice"] = {"value": r2, "sample": s2, "seconds": dt2}
         if not args.no_cli:
@@ -584,7 +584,7 @@ def run_ours(args):
                 line["cli"] = cli_wall_clock(b, args.precision)
             except Exception as e:  # noqa: BLE001
                 line["cli"] = {"error": repr(e)}
-        extras = [e for e in args.extra.split(",") if e and e != args.workload]
+        extras = [e for e in args.extra.split(",") if e in WORKLOADS and e != args.workload]
         del b
         torch.cuda.empty_cache()
         line["extra"] = []
@@ -691,8 +691,9 @@ def main():
                     help="fp16 | bf16 | fp32 (bf16x3) | bf16+a[:layers][+w[:layers]] -- see engine.Precision")
     ap.add_argument("--cpu-sample", type=int, default=None,
                     help="frames of the workload timed on the CPU (default: ~10-30 s of host work)")
-    ap.add_argument("--cpu-python-prepare", action="store_true",
-                    help="also time the CPU baseline with the reference's per-frame Python splice loop (BASELINE.md 3)")
+    ap.add_argument("--no-cpu-python-prepare", dest="cpu_python_prepare", action="store_false",
+                    help="skip the second CPU figure: the baseline with the reference's per-frame Python splice loop "
+                         "(kw_nn_utils.py:26-36; BASELINE.md section 3 asks for both)")
     ap.add_argument("--cpu-threads-all", action="store_true", help="force every host core for BLAS (reference arm default)")
     ap.add_argument("--extra", default="cfg3,cfg4", help="other workloads reported as short extra records at N = 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -399,3 +399,35 @@ def test_recurrent_compact_transfer(nn):
     assert np.all(np.abs(f16 - f32) <= 2.0 ** -11 * dist + 2e-5)
     live = np.abs(f32).sum(axis=1) > 0
     assert np.array_equal(f16[live].argmax(axis=1), f32[live].argmax(axis=1))
+
+
+@pytest.mark.parametrize("network,nb", [("lstm", 32), ("lstm", 64), ("lstm", 128), ("blstm", None), ("gru", 32),
+                                        ("gru", 128), ("bgru", None), ("peepholelstm", None)])
+def test_repeated_runs_are_bit_identical(nn, network, nb, monkeypatch):
+    """Race proxy (compute-sanitizer is closed on this GPU pool, profiles/r02_sanitizer.md): every K3 kernel family --
+    counter-based exchange, cluster + multicast exchange, 128-slot two-stream kernels, the mixed two-launch schedule
+    (nb=None lets the cost model pick it; forced here) -- must give bit-identical outputs on repeated runs of the same
+    ragged workload.  A missing barrier / fence in the cross-CTA exchange shows up as run-to-run differences."""
+    from nnacousticmodeling_b200 import recurrent_engine
+    rng = np.random.default_rng(97)
+    lens = np.concatenate([rng.integers(120, 160, size=40), rng.integers(1, 60, size=500)])
+    rng.shuffle(lens)
+    off = _offsets(lens.tolist())
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    bid = network in ("blstm", "bgru")
+    if "lstm" in network:
+        m, _ = _lstm(nn, 55, network, 40, 512 if network != "peepholelstm" else 128, 2, 39, precision="fp16",
+                     bidirectional=bid)
+    else:
+        m, _ = _gru(nn, 55, network, 40, 512, 2, 39, precision="fp16", bidirectional=bid)
+    if nb is None and network != "peepholelstm":
+        monkeypatch.setenv("NNAM_RNN_MIXED", "force")
+    kw = {} if nb is None else {"nb": nb}
+    outs = []
+    for _ in range(6):
+        o = np.zeros((off[-1], 39), np.float32)
+        recurrent_engine.forward_utterances(m, x, off, o, 0, len(lens), timedelay=0, device=0, **kw)
+        outs.append(o)
+    assert np.isfinite(outs[0]).all()
+    for o in outs[1:]:
+        assert np.array_equal(o, outs[0])
