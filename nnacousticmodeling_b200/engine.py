@@ -427,7 +427,8 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         out_dev = None if out_on_device else [ws.get(f"ff.out{i}", chunk, n_out, torch.float32) for i in range(2)]
         # Host output: "direct" = D2H straight into the caller's array; otherwise every chunk goes through one of two
         # pinned staging buffers and a helper thread finishes it (widen the compact format and / or feed the sink)
-        compact = (not out_on_device) and use_compact_transfer(plan0, transfer)
+        host_threads = host_threads or default_host_threads()
+        compact = (not out_on_device) and use_compact_transfer(plan0, transfer, host_threads=host_threads)
         writer = o16_dev = ref_dev = None
         if (compact or sink is not None) and not out_on_device:
             ld16 = round_up(n_out, 8)
@@ -445,7 +446,7 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
                 o16_dev = [ws.get(f"ff.out16.{i}", chunk, ld16, torch.float16) for i in range(2)]
                 ref_dev = [ws.get(f"ff.ref.{i}", chunk, 1, torch.float32).view(-1) for i in range(2)]
             out_np = out.numpy() if isinstance(out, torch.Tensor) else out
-            writer = _ChunkWriter(stage, compact, out_np, sink, n_out, host_threads or default_host_threads())
+            writer = _ChunkWriter(stage, compact, out_np, sink, n_out, host_threads)
         # Three streams: `main` runs splice + the GEMM stack of chunk i; `aux` runs the HBM-bound head of chunk i-1 in
         # their shadow (the GEMM kernels cap their registers so that one head CTA fits next to a GEMM CTA on every SM);
         # `side` carries the D2H copies.  Logits and head outputs are double-buffered by chunk parity.  (Moving the
@@ -514,14 +515,22 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
     return out
 
 
-def use_compact_transfer(plan, transfer=None, recurrent=False):
+MIN_WIDEN_THREADS = 12  # host threads a process needs before the compact transfer beats the plain float32 copy
+
+
+def use_compact_transfer(plan, transfer=None, recurrent=False, host_threads=None):
     """Does a host-bound pass of ``plan`` use the compact (fp16 offsets + row maximum) transfer format?  Explicit
     ``transfer`` ("f16" / "f32") wins, then the environment (NNAM_TRANSFER), then the path and precision mode: the
     feed-forward path in a 16-bit mode (tolerance 5e-2) takes it -- its chunks stream, so the host widens chunk i while
     chunk i+1 crosses PCIe (measured +22 % end to end on cfg2).  The fp32-accurate mode (tolerance 1e-3) keeps float32
     rows, and so does the recurrent path: its rows only exist after the last layer, the widening cannot hide under
-    anything, and it measured 3-7 % slower than the plain copy (profiles/r02_transfer.md)."""
-    mode = transfer or os.environ.get("NNAM_TRANSFER") or ("f32" if (plan.split or recurrent) else "f16")
+    anything, and it measured 3-7 % slower than the plain copy.  The widening needs host cores: with 16 threads it
+    sustains 64 GB/s of float32 and wins; with the 4 threads a rank gets when 8 processes share a 32-core box it is the
+    bottleneck (10.4 M against 11.9 M frames/s on 8 GPUs, where plain copies already run at 98 % of the box's 92.6 GB/s
+    D2H ceiling), so it is only chosen when the process has at least MIN_WIDEN_THREADS (profiles/r02_transfer.md)."""
+    threads = host_threads or default_host_threads()
+    auto = "f32" if (plan.split or recurrent or threads < MIN_WIDEN_THREADS) else "f16"
+    mode = transfer or os.environ.get("NNAM_TRANSFER") or auto
     if mode not in ("f16", "f32"):
         raise NnamError(f"transfer must be 'f16' or 'f32' (got {mode!r})")
     return mode == "f16"

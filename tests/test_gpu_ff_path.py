@@ -143,17 +143,21 @@ def test_compact_transfer_matches_float32_transfer(nn, golden_dir):
     ft = nn.loadKaldiFeatureTransform(os.path.join(golden_dir, "final.feature_transform"))
     m, _ = _mlp(nn, 16, 540, 512, 3, 1909, precision="fp16")
     f32 = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv, transfer="f32")
-    f16 = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv)  # 16-bit mode default: compact
+    f16 = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv, transfer="f16")
     assert not np.array_equal(f32, f16)
+    plan = engine.get_plan(m, 0)  # the default: compact in a 16-bit mode when the process has cores to widen with
+    assert engine.use_compact_transfer(plan, host_threads=16) and not engine.use_compact_transfer(plan, host_threads=4)
+    assert not engine.use_compact_transfer(plan, host_threads=16, recurrent=True)
     dist = f32.max(axis=1, keepdims=True) - f32
     assert np.all(np.abs(f16 - f32) <= 2.0 ** -11 * dist + 2e-5)
     assert np.array_equal(f16.argmax(axis=1), f32.argmax(axis=1))
     pageable = np.full((len(x), 1909), 7.0, np.float32)  # the destination need not be pinned in this format
-    assert nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv, out=pageable) is pageable
+    assert nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv, out=pageable,
+                      transfer="f16") is pageable
     assert np.array_equal(pageable, f16)
     parts = np.zeros_like(f16)
     for f0, f1 in nn.partition_frames(len(x), 3):
-        engine.ff_forward_frames(m, x, ft, 5, parts, f0, f1, ivectors=iv, device=0, chunk=3000)
+        engine.ff_forward_frames(m, x, ft, 5, parts, f0, f1, ivectors=iv, device=0, chunk=3000, transfer="f16")
     assert np.array_equal(parts, f16)
     m.precision = "fp32"  # the fp32-accurate mode keeps float32 rows unless asked otherwise
     a = nn.predict(m, x[:2000], None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv[:2000])
