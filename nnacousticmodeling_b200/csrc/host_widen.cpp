@@ -10,6 +10,10 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -79,6 +83,81 @@ __attribute__((target("avx2,f16c"))) void widen_rows_f16c(const uint16_t* src, l
 }
 #endif
 
+// Persistent worker pool: a widening call covers ~30 MB (a piece small enough to still sit in the last-level cache when
+// it is read back, see engine._ChunkWriter), i.e. ~0.5 ms of work on 16 threads -- creating the threads per call would
+// cost as much again.  One job at a time (calls from several Python threads are serialised by the job mutex).
+class Pool {
+ public:
+  static Pool& get() {
+    static Pool p;
+    return p;
+  }
+  // run fn(part) for part in [0, parts) on up to `threads` threads (the caller is one of them)
+  void run(int parts, int threads, const std::function<void(int)>& fn) {
+    std::lock_guard<std::mutex> job_lock(job_mu_);
+    grow(threads - 1);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      fn_ = &fn;
+      parts_ = parts;
+      next_.store(0);
+      pending_ = parts;
+      helpers_ = threads - 1;
+      ++epoch_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> lk(mu_);
+    done_cv_.wait(lk, [&] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  Pool() = default;
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  void grow(int n) {
+    while (static_cast<int>(workers_.size()) < n) {
+      const int id = static_cast<int>(workers_.size());
+      workers_.emplace_back([this, id] {
+        unsigned long long seen = 0;
+        for (;;) {
+          {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return stop_ || (epoch_ != seen && id < helpers_); });
+            if (stop_) return;
+            seen = epoch_;
+          }
+          work();
+        }
+      });
+    }
+  }
+  void work() {
+    for (;;) {
+      const int part = next_.fetch_add(1);
+      if (part >= parts_) break;
+      (*fn_)(part);
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--pending_ == 0) done_cv_.notify_all();
+    }
+  }
+  std::mutex job_mu_, mu_;
+  std::condition_variable cv_, done_cv_;
+  std::vector<std::thread> workers_;
+  const std::function<void(int)>* fn_ = nullptr;
+  std::atomic<int> next_{0};
+  int parts_ = 0, pending_ = 0, helpers_ = 0;
+  unsigned long long epoch_ = 0;
+  bool stop_ = false;
+};
+
 }  // namespace
 
 extern "C" int nnam_widen_f16_host(const void* src16_host, long long ld16, const float* row_ref_host, float* dst_host,
@@ -95,15 +174,14 @@ extern "C" int nnam_widen_f16_host(const void* src16_host, long long ld16, const
 #endif
     widen_rows_scalar(src, ld16, row_ref_host, dst_host, ld_dst, r0, r1, cols);
   };
-  long long t = threads < 1 ? 1 : threads;
-  if (t > rows / 256 + 1) t = rows / 256 + 1;  // not worth a thread for a few rows
+  long long t = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
+  if (t > rows / 64 + 1) t = rows / 64 + 1;  // not worth a thread for a few rows
   if (t == 1) {
     run(0, rows);
     return NNAM_OK;
   }
-  std::vector<std::thread> pool;
-  pool.reserve(static_cast<size_t>(t));
-  for (long long i = 0; i < t; ++i) pool.emplace_back(run, rows * i / t, rows * (i + 1) / t);
-  for (auto& th : pool) th.join();
+  // twice as many parts as threads: a thread that was descheduled does not hold the call up for a whole share
+  const int parts = static_cast<int>(2 * t);
+  Pool::get().run(parts, static_cast<int>(t), [&](int part) { run(rows * part / parts, rows * (part + 1) / parts); });
   return NNAM_OK;
 }

@@ -425,26 +425,40 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         a_bufs = [(ws.get("ff.a.hi", chunk, ld_in, plan0.tdt),
                    ws.get("ff.a.lo", chunk, ld_in, torch.bfloat16) if plan0.in_kind == OUT_BF16_SPLIT else None)]
         out_dev = None if out_on_device else [ws.get(f"ff.out{i}", chunk, n_out, torch.float32) for i in range(2)]
-        # Host output: "direct" = D2H straight into the caller's array; otherwise every chunk goes through one of two
-        # pinned staging buffers and a helper thread finishes it (widen the compact format and / or feed the sink)
+        # Host output.  "direct" = D2H straight into the caller's array; otherwise a chunk goes through one of two pinned
+        # staging buffers and a helper thread finishes it (widen the compact format and / or feed the sink).  With the
+        # compact format and a PINNED destination the chunks are MIXED: PCIe and the widening threads are two servers,
+        # compact chunks load both (half the PCIe bytes + host work), float32 chunks only PCIe, so a fraction x of the
+        # chunks goes compact such that both finish together (see _TransferStats).
         host_threads = host_threads or default_host_threads()
-        compact = (not out_on_device) and use_compact_transfer(plan0, transfer, host_threads=host_threads)
-        writer = o16_dev = ref_dev = None
+        mixable = (not out_on_device) and sink is None and out_h is not None and out_h.is_pinned()
+        compact = (not out_on_device) and use_compact_transfer(plan0, transfer, host_threads=host_threads, mixable=mixable)
+        writer = o16_dev = ref_dev = stats = None
+        frac_compact = 1.0
         if (compact or sink is not None) and not out_on_device:
             ld16 = round_up(n_out, 8)
-            key = ("f16" if compact else "f32", chunk, n_out)
+            # Compact chunks cross PCIe in PIECES of a few thousand rows through a small ring of pinned buffers (4 x 16 MB
+            # for 1909 classes): the widening threads then read a piece while it is still in the last-level cache (the
+            # DMA wrote it there or it was just brought in), instead of streaming a 250 MB chunk back from DRAM -- the
+            # widening is bound by the host's memory system, and this takes a third of its traffic away.
+            piece = max(256, min(chunk, int(os.environ.get("NNAM_PIECE_ROWS", "4096")))) if compact else chunk
+            slots = max(2, int(os.environ.get("NNAM_PIECE_SLOTS", "4")))
+            key = ("f16" if compact else "f32", piece, n_out, slots)
             cache = plan0.__dict__.setdefault("_stage", {})
             if key not in cache:
                 cache.clear()
                 if compact:
-                    cache[key] = [(torch.empty((chunk, ld16), dtype=torch.float16, pin_memory=True),
-                                   torch.empty((chunk,), dtype=torch.float32, pin_memory=True)) for _ in range(2)]
+                    cache[key] = [(torch.empty((piece, ld16), dtype=torch.float16, pin_memory=True),
+                                   torch.empty((piece,), dtype=torch.float32, pin_memory=True)) for _ in range(slots)]
                 else:
                     cache[key] = [(torch.empty((chunk, n_out), dtype=torch.float32, pin_memory=True), None) for _ in range(2)]
             stage = cache[key]
             if compact:
                 o16_dev = [ws.get(f"ff.out16.{i}", chunk, ld16, torch.float16) for i in range(2)]
                 ref_dev = [ws.get(f"ff.ref.{i}", chunk, 1, torch.float32).view(-1) for i in range(2)]
+                if mixable and (transfer or os.environ.get("NNAM_TRANSFER")) is None:
+                    stats = plan0.__dict__.setdefault("_xfer_stats", _TransferStats(host_threads))
+                    frac_compact = stats.compact_fraction()
             out_np = out.numpy() if isinstance(out, torch.Tensor) else out
             writer = _ChunkWriter(stage, compact, out_np, sink, n_out, host_threads)
         # Three streams: `main` runs splice + the GEMM stack of chunk i; `aux` runs the HBM-bound head of chunk i-1 in
@@ -455,8 +469,53 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         aux = plan0.__dict__.setdefault("_aux_stream", torch.cuda.Stream(device=device))
         aux.wait_stream(main)
         a_hi, a_lo = a_bufs[0]
-        copied = [None, None]      # D2H of the chunk that last used out_dev[buf]
+        copied_f, copied_c = [None, None], [None, None]  # D2H of the chunk that last used out_dev[i] / o16_dev[i]
+        n_f = n_c = 0
+        copies = []                # (start, end, bytes) of every D2H copy, for the transfer statistics
         head_done = [None, None]   # head of the chunk that last used the logits buffers of this parity
+        pending = None
+        ring = [0]
+
+        def drain(as_compact, via_writer, ob, c0, c1, hd):
+            """Queue the device->host copies of a finished chunk (rows [c0, c1)) and hand them to the helper thread."""
+            rows = c1 - c0
+            side.wait_event(hd)
+            ev = None
+            if as_compact:
+                for p0 in range(0, rows, piece):
+                    p1 = min(p0 + piece, rows)
+                    slot = ring[0] % len(stage)
+                    ring[0] += 1
+                    writer.wait_free(slot)  # the helper thread still widens the piece that used this slot
+                    with torch.cuda.stream(side):
+                        t0 = torch.cuda.Event(enable_timing=True) if stats is not None else None
+                        if t0 is not None:
+                            t0.record(side)
+                        stage[slot][0][:p1 - p0].copy_(o16_dev[ob][p0:p1], non_blocking=True)
+                        stage[slot][1][:p1 - p0].copy_(ref_dev[ob][p0:p1], non_blocking=True)
+                        ev = torch.cuda.Event(enable_timing=stats is not None)
+                        ev.record(side)
+                        if stats is not None:
+                            copies.append((t0, ev, (p1 - p0) * (o16_dev[ob].stride(0) * 2 + 4)))
+                    writer.submit(slot, c0 + p0, c0 + p1, ev)
+                copied_c[ob] = ev
+                return
+            if via_writer:
+                writer.wait_free(ob)  # the helper thread still reads the staging buffer of the chunk two before
+            with torch.cuda.stream(side):
+                t0 = torch.cuda.Event(enable_timing=True) if stats is not None else None
+                if t0 is not None:
+                    t0.record(side)
+                dst = stage[ob][0][:rows] if via_writer else out_h[c0:c1]
+                dst.copy_(out_dev[ob][:rows], non_blocking=True)
+                ev = torch.cuda.Event(enable_timing=stats is not None)
+                ev.record(side)
+                if stats is not None:
+                    copies.append((t0, ev, rows * n_out * 4))
+            copied_f[ob] = ev
+            if via_writer:
+                writer.submit(ob, c0, c1, ev)
+
         for ci, c0 in enumerate(range(f0, f1, chunk)):
             c1 = min(c0 + chunk, f1)
             rows = c1 - c0
@@ -476,49 +535,78 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
             gemm_done.record(main)
             hkw = dict(rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
                        prior_scale=head.prior_scale, final_normalize=head.final_normalize)
+            # this chunk's transfer format (error diffusion of the compact fraction over the chunk index)
+            as_compact = compact and int((ci + 1) * frac_compact + 1e-9) > int(ci * frac_compact + 1e-9)
+            via_writer = writer is not None and (as_compact or not compact)
+            if as_compact:
+                ob, n_c = n_c % 2, n_c + 1   # ring position among the compact chunks / the staging buffers
+            else:
+                ob, n_f = n_f % 2, n_f + 1   # ring position among the float32 chunks
+            last = copied_c if as_compact else copied_f
             aux.wait_event(gemm_done)
             with torch.cuda.stream(aux):
                 if out_on_device:
                     ops.head(logits, n_out, out=out[c0:c1], **hkw)
                 else:
-                    if copied[buf] is not None:
-                        aux.wait_event(copied[buf])  # the side stream still reads this buffer
-                    if compact:
-                        ops.head(logits, n_out, out16=(o16_dev[buf], ref_dev[buf]), **hkw)
+                    if last[ob] is not None:
+                        aux.wait_event(last[ob])  # the side stream still reads this buffer
+                    if as_compact:
+                        ops.head(logits, n_out, out16=(o16_dev[ob], ref_dev[ob]), **hkw)
                     else:
-                        ops.head(logits, n_out, out=out_dev[buf], **hkw)
+                        ops.head(logits, n_out, out=out_dev[ob], **hkw)
                 hd = torch.cuda.Event()
                 hd.record(aux)
             head_done[buf] = hd
             if out_on_device:
                 continue
-            side.wait_event(hd)
-            if writer is not None:
-                writer.wait_free(buf)  # the helper thread still reads the staging buffer of chunk i-2
-            with torch.cuda.stream(side):
-                if compact:
-                    stage[buf][0][:rows].copy_(o16_dev[buf][:rows], non_blocking=True)
-                    stage[buf][1][:rows].copy_(ref_dev[buf][:rows], non_blocking=True)
-                else:
-                    dst = stage[buf][0][:rows] if writer is not None else out_h[c0:c1]
-                    dst.copy_(out_dev[buf][:rows], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(side)
-            copied[buf] = ev
-            if writer is not None:
-                writer.submit(buf, c0, c1, ev)
+            # the copies of chunk i are queued one iteration later, after chunk i+1's kernels: queueing them may block on
+            # the helper thread (ring slots), and the GPU should have its next chunk by then
+            if pending is not None:
+                drain(*pending)
+            pending = (as_compact, via_writer, ob, c0, c1, hd)
+        if pending is not None:
+            drain(*pending)
         main.wait_stream(aux)  # callers that time or consume on the current stream see the whole pass
         side.synchronize()
         main.synchronize()
         if writer is not None:
             writer.close()
+        if stats is not None:
+            stats.update(copies, writer)
     return out
+
+
+class _TransferStats:
+    """What the two servers of the host-bound output path sustain in THIS process, measured on the passes so far: PCIe
+    (bytes / duration of the D2H copies, CUDA events) and the widening threads (float32 bytes written / time spent
+    in nnam_widen_f16_host).  A compact chunk costs 3,828 B/frame of PCIe plus 7,636 B/frame of widening, a float32
+    chunk 7,636 B/frame of PCIe; both servers finish together when the compact fraction is
+        x = 1 / (P / W + 0.5)      (P, W in bytes/s; x >= 1 means: everything compact)
+    e.g. P = 57, W = 70 GB/s (one GPU, 16 threads) -> x = 0.76; under contention (8 ranks sharing the host's 92 GB/s of
+    ingest and 32 cores) both P and W shrink and x follows.  Before the first measurement: P = 55 GB/s, W = 4.4 GB/s per
+    thread (what one GPU on this pod shows)."""
+
+    def __init__(self, threads):
+        self.pcie, self.widen, self.last_d2h_bytes = 55e9, 4.4e9 * threads, None
+
+    def compact_fraction(self):
+        x = 1.0 / (self.pcie / max(self.widen, 1e6) + 0.5)
+        return 1.0 if x > 0.97 else max(x, 0.0)
+
+    def update(self, copies, writer):
+        ms = sum(a.elapsed_time(b) for a, b, _ in copies)
+        nbytes = sum(n for _, _, n in copies)
+        self.last_d2h_bytes = nbytes
+        if ms > 1.0 and nbytes > (64 << 20):  # passes too small to measure keep the previous estimate
+            self.pcie = 0.5 * self.pcie + 0.5 * nbytes / (ms * 1e-3)
+        if writer is not None and writer.widen_s > 1e-3 and writer.widen_bytes > (64 << 20):
+            self.widen = 0.5 * self.widen + 0.5 * writer.widen_bytes / writer.widen_s
 
 
 MIN_WIDEN_THREADS = 12  # host threads a process needs before the compact transfer beats the plain float32 copy
 
 
-def use_compact_transfer(plan, transfer=None, recurrent=False, host_threads=None):
+def use_compact_transfer(plan, transfer=None, recurrent=False, host_threads=None, mixable=False):
     """Does a host-bound pass of ``plan`` use the compact (fp16 offsets + row maximum) transfer format?  Explicit
     ``transfer`` ("f16" / "f32") wins, then the environment (NNAM_TRANSFER), then the path and precision mode: the
     feed-forward path in a 16-bit mode (tolerance 5e-2) takes it -- its chunks stream, so the host widens chunk i while
@@ -527,9 +615,11 @@ def use_compact_transfer(plan, transfer=None, recurrent=False, host_threads=None
     anything, and it measured 3-7 % slower than the plain copy.  The widening needs host cores: with 16 threads it
     sustains 64 GB/s of float32 and wins; with the 4 threads a rank gets when 8 processes share a 32-core box it is the
     bottleneck (10.4 M against 11.9 M frames/s on 8 GPUs, where plain copies already run at 98 % of the box's 92.6 GB/s
-    D2H ceiling), so it is only chosen when the process has at least MIN_WIDEN_THREADS (profiles/r02_transfer.md)."""
+    D2H ceiling), so ALL-compact is only chosen when the process has at least MIN_WIDEN_THREADS.  With a pinned
+    destination (``mixable``) the feed-forward path instead sends a measured FRACTION of the chunks compact and the rest as
+    float32 rows, which helps with any number of threads (_TransferStats; profiles/r02_transfer.md)."""
     threads = host_threads or default_host_threads()
-    auto = "f32" if (plan.split or recurrent or threads < MIN_WIDEN_THREADS) else "f16"
+    auto = "f32" if (plan.split or recurrent or (threads < MIN_WIDEN_THREADS and not mixable)) else "f16"
     mode = transfer or os.environ.get("NNAM_TRANSFER") or auto
     if mode not in ("f16", "f32"):
         raise NnamError(f"transfer must be 'f16' or 'f32' (got {mode!r})")
@@ -556,7 +646,8 @@ class _ChunkWriter:
         import queue
         self.stage, self.compact, self.out, self.sink, self.n_out, self.threads = stage, compact, out, sink, n_out, threads
         self.scratch = None
-        self.free = [threading.Event(), threading.Event()]
+        self.widen_s, self.widen_bytes = 0.0, 0
+        self.free = [threading.Event() for _ in stage]
         for e in self.free:
             e.set()
         self.q = queue.Queue()
@@ -576,7 +667,11 @@ class _ChunkWriter:
             if self.scratch is None or self.scratch.shape[0] < rows:
                 self.scratch = np.empty((rows, self.n_out), dtype=np.float32)
             dst = self.scratch[:rows]
+        import time
+        t0 = time.perf_counter()
         ops.widen_f16_host(data, ref, dst, self.threads)
+        self.widen_s += time.perf_counter() - t0
+        self.widen_bytes += dst.size * 4
         if self.sink is not None:
             self.sink.write(r0, r1, dst)
 
