@@ -14,14 +14,21 @@ Pinning status
   own NumPy helpers import and run; ``oracle/make_golden.py`` ran them and committed their
   outputs under ``tests/golden/``; ``tests/test_oracle_golden.py`` checks this module
   against those vectors bit for bit.
-* network cells (Linear, LSTM, GRU/MGRU, peephole, TDNN, RPL4): PARITY UNPINNED by the
-  reference.  The arithmetic lives in Chainer 3.5 (``README.md:92``), which is neither
-  vendored nor installable here, and the reference ships no tests, golden outputs or
-  trained models.  The cells follow ``scripts/common/chainer_networks.py``,
-  ``scripts/common/MGRU.py:67-85`` (in-repo, authoritative for the GRU family),
-  ``scripts/common/RPL.py:68-74`` and the published Chainer v3.5 link definitions; the LSTM
-  and no-reset MGRU algebra is additionally cross-checked against ``torch.nn.LSTMCell`` /
-  a hand-derived fp64 evaluation in ``tests/test_oracle_cells.py``.
+* network cells, predict(), NNWithRPL, RPL4, evaluateModelTestTri: PINNED (round 2) to
+  outputs of the reference's OWN code.  ``oracle/make_golden_nets.py`` runs the unmodified
+  ``chainer_networks.py`` / ``MGRU.py`` / ``RPL.py`` / ``predict_folds.py`` / ``evaluate.py``
+  / ``evaluateModelForTest.py`` / ``master_script.py`` on a NumPy-only stand-in for the
+  few Chainer 3.5 classes they touch (``tests/chainer_shim``; Chainer itself is neither
+  vendored nor installable here) and commits inputs + outputs under ``tests/golden/nets/``;
+  ``tests/test_reference_goldens.py`` checks this module against them (< 2e-5) for all nine
+  ``get_nn`` kinds, fold / dev mode and every folds / master / rpl combination.  What
+  remains a restatement of Chainer v3.5 inside the stand-in (a few lines each, upstream
+  path cited there): Linear, F.lstm / L.LSTM, StatefulGRU, StatefulPeepholeLSTM,
+  StatefulZoneoutLSTM, Convolution2D and the elementwise functions; the LSTM and no-reset
+  MGRU algebra is additionally cross-checked against ``torch.nn.LSTMCell`` and an fp64
+  evaluation in ``tests/test_oracle_cells.py``.
+* bidirectional stacks (SURVEY A9): PARITY UNPINNED -- the reference has no such class;
+  the definition is this module's (``birnn_forward_utterance``).
 """
 from __future__ import annotations
 
