@@ -141,12 +141,13 @@ int nnam_head_f16(const float* const* logits_host, const float* weights_host, in
                   float prior_scale, int final_normalize, void* out16, long long ld16, float* row_ref, long long rows,
                   int n_classes, const int* out_row_map, void* stream);
 
-/* HOST function (no CUDA): dst_host[r][c] = float(src16_host[r][c]) + row_ref_host[r] for r < rows, c < cols, on
- * `threads` host threads (F16C / AVX2 with non-temporal stores when the CPU has them).  All three pointers are HOST
- * pointers; dst_host is the reference-layout float32 output (ld_dst == cols for the contiguous (N, C) array of
- * np.save, predict_folds.py:240).  */
+/* HOST function (no CUDA): dst_host[q][c] = float(src16_host[r][c]) + row_ref_host[r] for r < rows, c < cols, with
+ * q = r, or q = dst_rows_host[r] when that map is given (the recurrent path ships a subset of utterances as one
+ * contiguous block and scatters its rows to their frame positions here), on `threads` host threads (persistent pool;
+ * F16C / AVX2 with non-temporal stores when the CPU has them).  All pointers are HOST pointers; dst_host is the
+ * reference-layout float32 output (ld_dst == cols for the contiguous (N, C) array of np.save, predict_folds.py:240).  */
 int nnam_widen_f16_host(const void* src16_host, long long ld16, const float* row_ref_host, float* dst_host,
-                        long long ld_dst, long long rows, int cols, int threads);
+                        long long ld_dst, const long long* dst_rows_host, long long rows, int cols, int threads);
 
 /* Row gather + feature transform (+ i-vector append) for recurrent nets: out[r] = transform(x[row_map[r]]) ++
  * ivec[row_map[r]].  Replaces the per-utterance `np.pad(..., mode="edge")` + applyKaldiFeatureTransform + padded

@@ -111,7 +111,8 @@ _SIGNATURES = {
     "nnam_head_f16": (c_int, [POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_float, c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
                               c_void_p]),
-    "nnam_widen_f16_host": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_longlong, c_int, c_int]),
+    "nnam_widen_f16_host": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
+                                    c_int]),
     "nnam_gather_transform": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                       c_longlong, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "nnam_peephole_cell": (c_int, [c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p,

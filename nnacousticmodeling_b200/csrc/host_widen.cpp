@@ -49,11 +49,11 @@ inline float half_to_float(uint16_t h) {
   return f;
 }
 
-void widen_rows_scalar(const uint16_t* src, long long ld16, const float* ref, float* dst, long long ld_dst, long long r0,
-                       long long r1, int cols) {
+void widen_rows_scalar(const uint16_t* src, long long ld16, const float* ref, float* dst, long long ld_dst,
+                       const long long* dst_rows, long long r0, long long r1, int cols) {
   for (long long r = r0; r < r1; ++r) {
     const uint16_t* s = src + r * ld16;
-    float* d = dst + r * ld_dst;
+    float* d = dst + (dst_rows ? dst_rows[r] : r) * ld_dst;
     const float a = ref[r];
     for (int c = 0; c < cols; ++c) d[c] = half_to_float(s[c]) + a;
   }
@@ -61,10 +61,11 @@ void widen_rows_scalar(const uint16_t* src, long long ld16, const float* ref, fl
 
 #if defined(__x86_64__)
 __attribute__((target("avx2,f16c"))) void widen_rows_f16c(const uint16_t* src, long long ld16, const float* ref, float* dst,
-                                                         long long ld_dst, long long r0, long long r1, int cols) {
+                                                         long long ld_dst, const long long* dst_rows, long long r0,
+                                                         long long r1, int cols) {
   for (long long r = r0; r < r1; ++r) {
     const uint16_t* s = src + r * ld16;
-    float* d = dst + r * ld_dst;
+    float* d = dst + (dst_rows ? dst_rows[r] : r) * ld_dst;
     const float a = ref[r];
     const __m256 va = _mm256_set1_ps(a);
     int c = 0;
@@ -161,18 +162,19 @@ class Pool {
 }  // namespace
 
 extern "C" int nnam_widen_f16_host(const void* src16_host, long long ld16, const float* row_ref_host, float* dst_host,
-                                   long long ld_dst, long long rows, int cols, int threads) {
+                                   long long ld_dst, const long long* dst_rows_host, long long rows, int cols,
+                                   int threads) {
   if (rows < 0 || cols <= 0 || ld16 < cols || ld_dst < cols || !src16_host || !row_ref_host || !dst_host) return NNAM_ERR_ARG;
   if (rows == 0) return NNAM_OK;
   const uint16_t* src = static_cast<const uint16_t*>(src16_host);
   auto run = [&](long long r0, long long r1) {
 #if defined(__x86_64__)
     if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("f16c")) {
-      widen_rows_f16c(src, ld16, row_ref_host, dst_host, ld_dst, r0, r1, cols);
+      widen_rows_f16c(src, ld16, row_ref_host, dst_host, ld_dst, dst_rows_host, r0, r1, cols);
       return;
     }
 #endif
-    widen_rows_scalar(src, ld16, row_ref_host, dst_host, ld_dst, r0, r1, cols);
+    widen_rows_scalar(src, ld16, row_ref_host, dst_host, ld_dst, dst_rows_host, r0, r1, cols);
   };
   long long t = threads < 1 ? 1 : (threads > 64 ? 64 : threads);
   if (t > rows / 64 + 1) t = rows / 64 + 1;  // not worth a thread for a few rows

@@ -656,8 +656,15 @@ class _ChunkWriter:
         self.thread.start()
 
     def _finish(self, buf, r0, r1):
-        rows = r1 - r0
         data, ref = self.stage[buf]
+        if isinstance(r1, np.ndarray):  # scattered piece: r1 holds the destination row of every source row
+            import time
+            t0 = time.perf_counter()
+            ops.widen_f16_host(data, ref, self.out, self.threads, dst_rows=r1)
+            self.widen_s += time.perf_counter() - t0
+            self.widen_bytes += len(r1) * self.n_out * 4
+            return
+        rows = r1 - r0
         if not self.compact:
             self.sink.write(r0, r1, data[:rows].numpy())
             return

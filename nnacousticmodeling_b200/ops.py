@@ -201,18 +201,26 @@ def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=No
     return out
 
 
-def widen_f16_host(src16, row_ref, dst, threads=1):
+def widen_f16_host(src16, row_ref, dst, threads=1, dst_rows=None):
     """HOST op: dst[r] = float(src16[r, :C]) + row_ref[r] for the rows of the compact transfer format (see ``head``).
-    src16: (rows, ld16) fp16 host tensor / array, row_ref: (rows,) f32, dst: (rows, C) f32 C-contiguous NumPy array."""
-    rows, cols = dst.shape
+    src16: (rows, ld16) fp16 host tensor / array, row_ref: (rows,) f32, dst: (rows, C) f32 C-contiguous NumPy array --
+    or, with ``dst_rows`` (int64 array of ``len(dst_rows)`` destination row indices), the WHOLE output array, of which
+    row dst_rows[r] receives source row r."""
+    import numpy as np
+    rows, cols = (len(dst_rows) if dst_rows is not None else dst.shape[0]), dst.shape[1]
     if rows == 0:
         return dst
+    if dst_rows is not None:
+        dst_rows = np.ascontiguousarray(dst_rows, dtype=np.int64)
+        if dst_rows.min() < 0 or dst_rows.max() >= dst.shape[0]:
+            raise NnamError("widen: destination row outside the output array")
     if src16.shape[0] < rows or row_ref.shape[0] < rows or dst.strides[1] != 4:
         raise NnamError("widen: shape mismatch")
     sp = src16.data_ptr() if isinstance(src16, torch.Tensor) else src16.ctypes.data
     rp = row_ref.data_ptr() if isinstance(row_ref, torch.Tensor) else row_ref.ctypes.data
     ld16 = src16.stride(0) if isinstance(src16, torch.Tensor) else src16.strides[0] // 2
-    check(_native.lib().nnam_widen_f16_host(sp, ld16, rp, dst.ctypes.data, dst.strides[0] // 4, rows, cols, int(threads)))
+    check(_native.lib().nnam_widen_f16_host(sp, ld16, rp, dst.ctypes.data, dst.strides[0] // 4,
+                                            None if dst_rows is None else dst_rows.ctypes.data, rows, cols, int(threads)))
     return dst
 
 

@@ -710,10 +710,14 @@ def _phase_split(lens):
 
 
 def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, out_dev, timedelay, fix_timedelay_tail,
-                   nb, device, stepwise, out16=None):
+                   nb, device, stepwise, out16=None, out_starts=None):
     """One subset of utterances (start frame relative to the shard and length of each) through the whole net:
     packed gather -> layers -> output GEMM -> head, which scatters the rows into ``out_dev`` (all frames of the shard)
-    or, with ``out16`` = (fp16 rows, row maxima), into the compact transfer format (ops.head)."""
+    or, with ``out16`` = (fp16 rows, row maxima), into the compact transfer format (ops.head).  ``out_starts``: first
+    OUTPUT row of every utterance when that differs from its first input frame (the compact format packs the rows of a
+    subset one after the other)."""
+    if out_starts is None:
+        out_starts = starts
     plan = plans[0]
     ws = plan.ws
     split = plan.split
@@ -730,14 +734,15 @@ def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, o
     # packed row -> source frame (edge-padded by `timedelay`) and -> destination frame (or -1); like the schedule
     # these maps depend only on where the utterances lie, and are cached with it
     maps = plan.__dict__.setdefault("_map_cache", {})
-    mkey = (starts.tobytes(), lens.tobytes(), timedelay, bool(fix_timedelay_tail), nb)
+    mkey = (starts.tobytes(), lens.tobytes(), timedelay, bool(fix_timedelay_tail), nb,
+            None if out_starts is starts else out_starts.tobytes())
     if mkey not in maps:
         utt = sched.order[sched.row_sorted_utt]  # utterance index inside the subset
         step = sched.row_step
         l_row = lens[utt]
         start = starts[utt]
         src = start + np.minimum(step, l_row - 1)
-        dst = start + step - timedelay
+        dst = out_starts[utt] + step - timedelay
         keep = step >= timedelay
         dst = np.where(keep, dst, -1)
         if not fix_timedelay_tail:
@@ -777,7 +782,7 @@ def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, o
         logits.append(lg)
     for u in np.nonzero(lens < timedelay)[0]:  # utterances shorter than the delay have rows no packed row maps to
         for t in ((out_dev,) if out16 is None else out16):
-            t[int(starts[u]):int(starts[u] + lens[u])].zero_()
+            t[int(out_starts[u]):int(out_starts[u] + lens[u])].zero_()
     prior = _dev_vec(head.prior, device)
     rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
     ops.head(logits, n_out, rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
@@ -842,75 +847,85 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         on_dev = isinstance(out, torch.Tensor) and out.is_cuda
         n_rows = f_hi - f_lo
         compact = (not on_dev) and engine.use_compact_transfer(plan, transfer, recurrent=True)
-        out16 = stage = None
+        out16 = None
         if compact:
             ld16 = round_up(n_out, 8)
             out16 = (ws.get("rnn.out16", n_rows, ld16, torch.float16), ws.get("rnn.ref", n_rows, 1, torch.float32).view(-1))
-            stage = plan.__dict__.get("_stage16")  # pinned staging of the shard's compact rows, grown on demand
-            if stage is None or stage[0].shape[0] < n_rows or stage[0].shape[1] != ld16:
-                stage = plan._stage16 = (torch.empty((n_rows, ld16), dtype=torch.float16, pin_memory=True),
-                                         torch.empty((n_rows,), dtype=torch.float32, pin_memory=True))
             out_dev = None
         else:
             out_dev = out[f_lo:f_hi] if on_dev else ws.get("rnn.out", n_rows, n_out, torch.float32)
         phases = [np.arange(len(lens))] if (on_dev or stepwise) else _phase_split(lens)
         main = torch.cuda.current_stream()
         side = None
-        pending = []  # compact: (copy-done event, [(r0, r1), ...]) per phase, widened on the host below
+        queued = []  # compact: (phase-done event, first packed output row, destination rows) per phase
+        packed = 0
         for idx in phases:
             whole = len(idx) == len(lens)
-            _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts if whole else starts[idx],
-                           lens if whole else lens[idx], out_dev, timedelay, fix_timedelay_tail, nb, device, stepwise,
-                           out16=out16)
+            p_starts, p_lens = (starts, lens) if whole else (starts[idx], lens[idx])
+            # compact format: the rows of this subset are packed one utterance after the other, so that they cross PCIe
+            # as ONE contiguous block (a subset's utterances lie all over the shard); the host scatters them back
+            o_starts = None
+            if compact:
+                o_starts = packed + np.concatenate([[0], np.cumsum(p_lens[:-1])]).astype(np.int64)
+            _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, p_starts, p_lens, out_dev, timedelay,
+                           fix_timedelay_tail, nb, device, stepwise, out16=out16, out_starts=o_starts)
             if on_dev:
                 continue
             out_host = None if compact else _as_host_tensor(out)
             if len(phases) == 1 and not compact:
                 out_host[f_lo:f_hi].copy_(out_dev, non_blocking=True)
                 continue
-            # rows of this subset, as maximal runs of neighbouring utterances, on the copy stream
             if side is None:
                 side = plan.__dict__.get("_d2h_stream")
                 if side is None:
                     side = plan._d2h_stream = torch.cuda.Stream()
             done = torch.cuda.Event()
             done.record(main)
+            if compact:
+                n_p = int(p_lens.sum())
+                dst_rows = f_lo + np.repeat(p_starts - np.concatenate([[0], np.cumsum(p_lens[:-1])]), p_lens) + np.arange(n_p)
+                queued.append((done, packed, dst_rows.astype(np.int64)))
+                packed += n_p
+                continue
+            # rows of this subset, as maximal runs of neighbouring utterances, on the copy stream
             brk = np.nonzero(np.diff(idx) != 1)[0] + 1
-            runs = []
             with torch.cuda.stream(side):
                 side.wait_event(done)
                 for run in np.split(idx, brk):
                     r0, r1 = int(starts[run[0]]), int(starts[run[-1]] + lens[run[-1]])
-                    if compact:
-                        stage[0][r0:r1].copy_(out16[0][r0:r1], non_blocking=True)
-                        stage[1][r0:r1].copy_(out16[1][r0:r1], non_blocking=True)
-                        runs.append((r0, r1))
-                    else:
-                        out_host[f_lo + r0:f_lo + r1].copy_(out_dev[r0:r1], non_blocking=True)
-                if compact:
-                    copied = torch.cuda.Event()
-                    copied.record(side)
-                    pending.append((copied, runs))
-        # compact format: every launch of every phase is queued by now; widen phase k on the host while the GPU is
-        # still busy with phase k+1
-        out_np = None
-        if pending:
-            out_np = out.numpy() if isinstance(out, torch.Tensor) else out
+                    out_host[f_lo + r0:f_lo + r1].copy_(out_dev[r0:r1], non_blocking=True)
+        if queued:
+            # Every kernel of every phase is queued by now, so this thread may block on the ring: the packed rows cross
+            # PCIe in pieces of a few thousand rows through a small ring of pinned buffers and a helper thread widens
+            # each piece into its frame positions of ``out`` while the piece is still in the last-level cache
+            # (engine._ChunkWriter, as in the feed-forward path); phase k drains while the GPU computes phase k+1.
             threads = host_threads or engine.default_host_threads()
-        if pending:
-            # a phase is hundreds of short row runs (its utterances lie all over the shard): the runs, cut into pieces of
-            # <= 4096 rows, are spread over a pool of host threads (the C call releases the GIL)
-            from concurrent.futures import ThreadPoolExecutor
-
-            def widen(piece):
-                a, b = piece
-                ops.widen_f16_host(stage[0][a:b], stage[1][a:b], out_np[f_lo + a:f_lo + b], 1)
-
-            with ThreadPoolExecutor(max_workers=threads) as pool:
-                for copied, runs in pending:
-                    copied.synchronize()
-                    pieces = [(a, min(a + 4096, r1)) for r0, r1 in runs for a in range(r0, r1, 4096)]
-                    list(pool.map(widen, pieces))
+            piece = max(256, int(os.environ.get("NNAM_PIECE_ROWS", "4096")))
+            slots = max(2, int(os.environ.get("NNAM_PIECE_SLOTS", "4")))
+            key = ("f16", piece, n_out, slots)
+            cache = plan.__dict__.setdefault("_stage", {})
+            if key not in cache:
+                cache.clear()
+                cache[key] = [(torch.empty((piece, ld16), dtype=torch.float16, pin_memory=True),
+                               torch.empty((piece,), dtype=torch.float32, pin_memory=True)) for _ in range(slots)]
+            stage = cache[key]
+            out_np = out.numpy() if isinstance(out, torch.Tensor) else out
+            writer = engine._ChunkWriter(stage, True, out_np, None, n_out, threads)
+            k = 0
+            for done, p0, dst_rows in queued:
+                side.wait_event(done)
+                for a0 in range(0, len(dst_rows), piece):
+                    a1 = min(a0 + piece, len(dst_rows))
+                    slot = k % slots
+                    k += 1
+                    writer.wait_free(slot)
+                    with torch.cuda.stream(side):
+                        stage[slot][0][:a1 - a0].copy_(out16[0][p0 + a0:p0 + a1], non_blocking=True)
+                        stage[slot][1][:a1 - a0].copy_(out16[1][p0 + a0:p0 + a1], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                    writer.submit(slot, 0, dst_rows[a0:a1], ev)
+            writer.close()
         main.synchronize()
         if side is not None:
             side.synchronize()
