@@ -121,7 +121,7 @@ def make_models(w, precision, device):
 
 
 def make_params(w, seed=4321):
-    """Oracle-side random-init parameters (scripts/gpu_parity_table.py, the reference arm; NOT the product arm)."""
+    """Oracle-side random-init parameters (tests/tools/gpu_parity_table.py, the reference arm; NOT the product arm)."""
     from oracle import nnam_oracle as O
     rng = np.random.default_rng(seed)
     if w["network"] == "ff":

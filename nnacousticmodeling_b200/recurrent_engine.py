@@ -389,9 +389,9 @@ class Schedule:
 
 class MixedSchedule:
     """Two schedules over one packed row space, run as two concurrent cooperative launches on disjoint SM sets: the
-    longest utterances in the low-latency 32-slot kernel (one batch per CTA group; they are the critical path of a
-    layer: 785 steps x 6.5 k cycles against 10 k in the 128-slot kernel), everything else in the 128-slot
-    two-stream kernel on the remaining groups.  Exposes the attributes forward_utterances() reads from a Schedule."""
+    longest utterances in the low-latency 32-slot kernel (they are the critical path of a layer: 785 steps x 4.3 k
+    cycles against 10 k in the 128-slot kernel; the groups holding shorter batches work through up to three of them one
+    after the other), everything else in the 128-slot two-stream kernel on the remaining groups.  Exposes the attributes forward_utterances() reads from a Schedule."""
 
     def __init__(self, steps, k_long, groups_long, nb_long, streams_long, nb_bulk, groups_bulk, streams_bulk,
                  ratio_bulk, n_dirs, device):
@@ -444,19 +444,26 @@ def _mixed_candidate(plan, steps, s_sorted, nsplit, best_cost):
             continue
         # both kernels use 16-CTA groups on disjoint SMs: g_a groups (clusters, for the multicast kernel, of which at
         # most max_a are resident) leave max_b - g_a groups for the bulk part
-        for g_a in ((int(forced),) if forced else (1, 2, 3, 4)):
+        forced_b = os.environ.get("NNAM_RNN_MIXED_BATCHES")  # tuning aid
+        for g_a in ((int(forced),) if forced else (1, 2, 3, 4, 5, 6)):
             if max_b - g_a < 1 or g_a > max_a:
                 break
-            # one batch per group; a bidirectional net needs a group per direction of a batch to keep the two passes
-            # over its longest utterance side by side
-            k = nb_a * max(1, g_a // plan.n_dirs)
-            if len(steps) - k < 128:
-                continue
-            _, _, crit_a = assign_lanes(s_sorted[:k:nb_a], plan.n_dirs, g_a, streams_a)
-            _, _, crit_b = assign_lanes(s_sorted[k::128], plan.n_dirs, max_b - g_a, streams_b, ratio)
-            cost = max(crit_a * cyc_a, crit_b * cyc_b)
-            if best is None or cost < best[0]:
-                best = (cost, k, g_a, nb_a, streams_a, max_b - g_a, streams_b, ratio)
+            # At least one batch per group (a bidirectional net needs a group per direction of a batch to keep the two
+            # passes over its longest utterance side by side); up to three, worked through one after the other: the
+            # groups that hold the 2nd, 3rd ... longest batch have time left while the first walks the longest
+            # utterance, and every batch they take shortens the bulk part's own longest lane.
+            b_min = max(1, g_a // plan.n_dirs)
+            for n_bat in ((int(forced_b),) if forced_b else range(b_min, 3 * b_min + 1)):
+                k = nb_a * n_bat
+                if len(steps) - k < 128:
+                    break
+                _, _, crit_a = assign_lanes(s_sorted[:k:nb_a], plan.n_dirs, g_a, streams_a)
+                _, _, crit_b = assign_lanes(s_sorted[k::128], plan.n_dirs, max_b - g_a, streams_b, ratio)
+                cost = max(crit_a * cyc_a, crit_b * cyc_b)
+                if best is None or cost < best[0]:
+                    best = (cost, k, g_a, nb_a, streams_a, max_b - g_a, streams_b, ratio)
+                if crit_a * cyc_a > crit_b * cyc_b and not forced_b:
+                    break  # the long part is already the longer one: more batches only make it longer
     if best is None or (best[0] > 0.95 * best_cost and os.environ.get("NNAM_RNN_MIXED") != "force"):
         return None
     return best

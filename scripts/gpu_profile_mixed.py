@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Timing of the two concurrent recurrence launches of a MixedSchedule (cfg3 geometry).
-usage: gpu_profile_mixed.py [n_utt] [long groups: 0 = plain schedule, -1 = cost model, 1-4] [lstm|gru|blstm|bgru]"""
+usage: gpu_profile_mixed.py [n_utt] [long groups: 0 = plain schedule, -1 = cost model, 1-6] [lstm|gru|blstm|bgru] [long batches]"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -14,13 +14,14 @@ elif g_a < 0:
 else:
     os.environ["NNAM_RNN_MIXED"] = "force"
     os.environ["NNAM_RNN_MIXED_GROUPS"] = str(g_a)
+    if len(sys.argv) > 4:
+        os.environ["NNAM_RNN_MIXED_BATCHES"] = sys.argv[4]
 import nnacousticmodeling_b200 as nn
 from nnacousticmodeling_b200 import recurrent_engine as R, ops
-from oracle import nnam_oracle as O
-x, off, _ = O.synth_set(1234, n_utt)
+from nnacousticmodeling_b200 import synth
+x, off, _ = synth.synth_set(1234, n_utt)
 bid = net in ("blstm", "bgru")
-p = O.init_recurrent(np.random.default_rng(1), {"blstm": "lstm", "bgru": "gru"}.get(net, net), 40, 512, 4, 1909, bidirectional=bid)
-m = nn.get_nn(net, 4, [512], 1909, nn.F.relu, [5]); m.load_params(p); m.precision = "bf16"
+m = nn.get_nn(net, 4, [512], 1909, nn.F.relu, [5]); m.init_params(40, np.random.default_rng(1)); m.precision = os.environ.get("PREC", "fp16")
 td = 0 if bid else 5
 dev = torch.device("cuda:0")
 xd = torch.from_numpy(x).to(dev); out = torch.empty((len(x), 1909), device=dev)

@@ -6,15 +6,14 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import nnacousticmodeling_b200 as nn
 from nnacousticmodeling_b200 import recurrent_engine as R
-from oracle import nnam_oracle as O
+from nnacousticmodeling_b200 import synth
 
 nb = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 prec = sys.argv[2] if len(sys.argv) > 2 else "bf16"
 net = sys.argv[3] if len(sys.argv) > 3 else "lstm"
 n_utt = int(sys.argv[4]) if len(sys.argv) > 4 else 1344
-x, off, _ = O.synth_set(1234, n_utt)
-p = O.init_recurrent(np.random.default_rng(1), net, 40, 512, 4, 1909)
-m = nn.get_nn(net, 4, [512], 1909, nn.F.relu, [5]); m.load_params(p); m.precision = prec
+x, off, _ = synth.synth_set(1234, n_utt)
+m = nn.get_nn(net, 4, [512], 1909, nn.F.relu, [5]); m.init_params(40, np.random.default_rng(1)); m.precision = prec
 dev = torch.device("cuda:0")
 xd = torch.from_numpy(x).to(dev); out = torch.empty((len(x), 1909), device=dev)
 for _ in range(2):

@@ -7,7 +7,7 @@ seconds).  north_star's gates, asserted here exactly as stated -- RAW frame-argm
   fp32 mode  (bf16x3 GEMMs)        max |err| <= 1e-3
   16-bit throughput mode           max |err| <= 5e-2  AND  argmax agreement >= 99.5 %
 
-Which 16-bit mode meets the second gate was MEASURED (scripts/gpu_parity_table.py, profiles/r02_parity_table.md): the
+Which 16-bit mode meets the second gate was MEASURED (tests/tools/gpu_parity_table.py, profiles/r02_parity_table.md): the
 logits of random-init nets are almost flat (top-1/top-2 gaps of 1e-3 are common), single-pass bf16 (8-bit
 significand) flips 1.1-1.4 % of the argmaxes -- 0.6-0.9 % even with bf16-exact weights on both sides -- and does NOT
 meet it; single-pass fp16 (11-bit significand, same tensor-pipe rate) agrees on 99.8-99.9 % and does.  So "fp16" is

@@ -11,7 +11,7 @@ large random sample of frames / utterances with the fp32 oracle:
 Weight variants: "plain" = fp32 LeCun-normal weights as drawn; "e16" = the same weights pre-rounded to the mode's 16-bit
 element type ON BOTH SIDES (SURVEY 8d "bf16-exact weights" variant: identical weights, the oracle stays fp32 arithmetic).
 
-  python scripts/gpu_parity_table.py --workloads cfg2,cfg3 --modes bf16,fp16 --out gpurun_out/parity.jsonl
+  python tests/tools/gpu_parity_table.py --workloads cfg2,cfg3 --modes bf16,fp16 --out gpurun_out/parity.jsonl
 """
 import argparse
 import json
@@ -21,7 +21,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 from oracle import nnam_oracle as O  # noqa: E402  (the checker)

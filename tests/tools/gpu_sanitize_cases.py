@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Small instances of every kernel family for compute-sanitizer (racecheck / synccheck / memcheck / initcheck):
 
-  compute-sanitizer --tool racecheck python scripts/gpu_sanitize_cases.py [case ...]
+  compute-sanitizer --tool racecheck python tests/tools/gpu_sanitize_cases.py [case ...]
 
 Cases: k1 (splice stream + tile kernels, gather, convert), k2 (1-CTA and cta_group::2 GEMM, every output kind / pass
 mode), k3_64 (32/64-slot LSTM, GRU, peephole), k3_128 (128-slot LSTM / GRU, two streams per group), k3_mixed (two
@@ -12,7 +12,7 @@ import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
