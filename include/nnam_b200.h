@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define NNAM_ABI_VERSION 2
+#define NNAM_ABI_VERSION 3
 
 /* error codes */
 #define NNAM_OK 0
@@ -140,6 +140,19 @@ int nnam_head_f16(const float* const* logits_host, const float* weights_host, in
                   int pre_normalize, const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior,
                   float prior_scale, int final_normalize, void* out16, long long ld16, float* row_ref, long long rows,
                   int n_classes, const int* out_row_map, void* stream);
+
+/* K2 + K4 fused for ONE net without RPL: out = log_softmax(A . W^T + bias - prior_scale * prior), i.e. the output
+ * L.Linear (chainer_networks.py:21-22, 61-62, ...) followed by `y - logsum(y, axis=1)` (predict_folds.py:57,88) or by
+ * `y = y - ap; y - logsum(y)` (evaluateModelForTest.py:75-77,110-112), without the float32 logits ever going to HBM:
+ * the CTAs holding the 256-column tiles of a 128-row block form a thread-block cluster and exchange the rows' running
+ * max / sum-exp through distributed shared memory (N <= 2048 classes).  Operands as nnam_linear_bias_act.  Exactly one
+ * of `out` (float32 rows, leading dimension ld_out >= N, any 4-byte aligned pitch -- the (frames, N) array itself) and
+ * `out16` + `row_ref` (the compact transfer format of nnam_head_f16; ld16 % 8 == 0) is given.  out_row_map as in
+ * nnam_head_scatter (NULL: row r -> row r; -1: drop; -2 - q: zero-fill row q).  bias / prior may be NULL.  */
+int nnam_linear_logsoftmax(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
+                           long long ldw, const float* bias, const float* prior, float prior_scale, float* out,
+                           long long ld_out, void* out16, long long ld16, float* row_ref, const int* out_row_map,
+                           int M, int N, int K, int nsplit, int elem, void* stream);
 
 /* HOST function (no CUDA): dst_host[q][c] = float(src16_host[r][c]) + row_ref_host[r] for r < rows, c < cols, with
  * q = r, or q = dst_rows_host[r] when that map is given (the recurrent path ships a subset of utterances as one

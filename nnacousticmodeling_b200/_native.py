@@ -14,11 +14,11 @@ from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p, POINTER
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libnnam_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_mc.cu", "recurrent_wide.cu", "recurrent_wide_gru.cu", "peephole.cu",
+SOURCES = ["api.cu", "gemm.cu", "gemm_head.cu", "splice.cu", "head.cu", "recurrent.cu", "recurrent_mc.cu", "recurrent_wide.cu", "recurrent_wide_gru.cu", "peephole.cu",
            "host_widen.cpp"]  # .cpp = host-only code, compiled with the host C++ compiler
 # measured dead end kept for reference (DSMEM all-gather recurrence); NNAM_WITH_CLUSTER_EXPERIMENT=1 builds it in
 EXPERIMENTAL_SOURCES = ["experimental/recurrent_cluster.cu"]
-ABI_VERSION = 2
+ABI_VERSION = 3
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
@@ -111,6 +111,9 @@ _SIGNATURES = {
     "nnam_head_f16": (c_int, [POINTER(c_void_p), POINTER(c_float), c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_float, c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_int, c_void_p,
                               c_void_p]),
+    "nnam_linear_logsoftmax": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p,
+                                       c_float, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_int,
+                                       c_int, c_int, c_int, c_int, c_void_p]),
     "nnam_widen_f16_host": (c_int, [c_void_p, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_longlong, c_int,
                                     c_int]),
     "nnam_gather_transform": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

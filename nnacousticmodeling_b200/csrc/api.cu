@@ -127,6 +127,14 @@ int nnam_linear_bias_act(const void* a_hi, const void* a_lo, long long lda, cons
                              nsplit, elem, static_cast<cudaStream_t>(stream));
 }
 
+int nnam_linear_logsoftmax(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
+                           long long ldw, const float* bias, const float* prior, float prior_scale, float* out,
+                           long long ld_out, void* out16, long long ld16, float* row_ref, const int* out_row_map,
+                           int M, int N, int K, int nsplit, int elem, void* stream) {
+  return nnam::linear_logsoftmax(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, prior, prior_scale, out, ld_out, out16, ld16,
+                                 row_ref, out_row_map, M, N, K, nsplit, elem, static_cast<cudaStream_t>(stream));
+}
+
 int nnam_head(const float* const* logits_host, const float* weights_host, int n_inputs, long long ld_in,
               int pre_normalize, const float* rpl_w, const float* rpl_b, const float* rpl_lb, const float* prior,
               float prior_scale, int final_normalize, float* out, long long ld_out, long long rows, int n_classes,

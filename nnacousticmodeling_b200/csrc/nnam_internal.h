@@ -23,4 +23,9 @@ int gemm_bias_act(const void* a_hi, const void* a_lo, long long lda, const void*
                   long long ldw, const float* bias, void* out_hi, void* out_lo, long long ldo, int M, int N, int K,
                   int act, int out_kind, int nsplit, int elem, cudaStream_t stream);
 
+int linear_logsoftmax(const void* a_hi, const void* a_lo, long long lda, const void* w_hi, const void* w_lo,
+                      long long ldw, const float* bias, const float* prior, float prior_scale, float* out,
+                      long long ld_out, void* out16, long long ld16, float* row_ref, const int* out_row_map, int M,
+                      int N, int K, int nsplit, int elem, cudaStream_t stream);
+
 }  // namespace nnam

@@ -125,6 +125,32 @@ class LinearDev:
                                    out_kind=out_kind, nsplit=nsplit, out=out, elem=self.elem)
 
 
+    def logsoftmax(self, a_hi, a_lo, rows, prior=None, prior_scale=1.0, nsplit=None, out=None, out16=None,
+                   out_row_map=None):
+        """This layer as the output layer of a single net, fused with the head (ops.linear_logsoftmax)."""
+        if nsplit is None:
+            nsplit = SPLIT_AW if self.split else SPLIT_NONE
+        return ops.linear_logsoftmax(a_hi, a_lo, self.w_hi, self.w_lo, self.bias, rows, self.n, self.k, prior=prior,
+                                     prior_scale=prior_scale, nsplit=nsplit, elem=self.elem, out=out, out16=out16,
+                                     out_row_map=out_row_map)
+
+
+def fused_head_ok(models, head):
+    """Opt-in (NNAM_FUSED_HEAD=1; =force also takes class counts below 512): run the output layer and the head as ONE
+    kernel (ops.linear_logsoftmax) when the head is plain -- a single net, no RPL, weight 1, final log-softmax, at most
+    2048 classes.  Off by default: measured SLOWER than the unfused pair for float32 rows (671 vs 294 us per 65,536 x
+    1909 x 512 chunk; the fused epilogue runs on four lone warps at IPC 0.2, profiles/r02_fused_head.md)."""
+    env = os.environ.get("NNAM_FUSED_HEAD", "0")
+    if env not in ("1", "force") or len(models) != 1 or head.rpl is not None or head.pre_normalize or not head.final_normalize:
+        return False
+    if head.weights is not None and [float(w) for w in head.weights] != [1.0]:
+        return False
+    n = models[0].n_out
+    if models[0].network == "tdnn" or n > ops.FUSED_HEAD_MAX_CLASSES:
+        return False
+    return env == "force" or n >= 512
+
+
 class Workspace:
     """Grow-only named device buffers (the kernels never allocate).
 
@@ -225,9 +251,8 @@ def get_plan(model, device):
 # ------------------------------------------------------------------------------------------
 # MLP stack on already-staged bf16 inputs
 # ------------------------------------------------------------------------------------------
-def mlp_logits(model, plan, a_hi, a_lo, rows, tag="mlp", ws=None):
-    """Run the Linear stack; returns fp32 logits (rows, roundup(C, 16)) in workspace memory (``ws``: the
-    workspace to use -- ensemble members share the first member's activation buffers)."""
+def mlp_hidden(model, plan, a_hi, a_lo, rows, ws=None):
+    """Run the hidden Linear stack; returns the operands (hi, lo) of the output layer."""
     ws = ws or plan.ws
     act = model.activation.name
     cap = a_hi.shape[0]
@@ -239,9 +264,19 @@ def mlp_logits(model, plan, a_hi, a_lo, rows, tag="mlp", ws=None):
         lo = ws.get(f"act.h{l % 2}.lo", cap, ld, torch.bfloat16) if kind == OUT_BF16_SPLIT else None
         lin(a_hi, a_lo, rows, act, kind, out=(hi, lo), nsplit=prec.nsplit(l, n_lin))
         a_hi, a_lo = hi, lo
+    return a_hi, a_lo
+
+
+def mlp_logits(model, plan, a_hi, a_lo, rows, tag="mlp", ws=None):
+    """Run the Linear stack; returns fp32 logits (rows, roundup(C, 16)) in workspace memory (``ws``: the
+    workspace to use -- ensemble members share the first member's activation buffers)."""
+    ws = ws or plan.ws
+    cap = a_hi.shape[0]
+    n_lin = len(plan.layers) + 1
+    a_hi, a_lo = mlp_hidden(model, plan, a_hi, a_lo, rows, ws)
     ldc = round_up(plan.out.n, 16)
     logits = ws.get(f"{tag}.logits", cap, ldc, torch.float32)
-    plan.out(a_hi, a_lo, rows, "identity", OUT_F32, out=(logits, None), nsplit=prec.nsplit(n_lin - 1, n_lin))
+    plan.out(a_hi, a_lo, rows, "identity", OUT_F32, out=(logits, None), nsplit=plan.prec.nsplit(n_lin - 1, n_lin))
     return logits
 
 
@@ -408,6 +443,8 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
             add, mul = _dev_vec(ft["addShift"], device), _dev_vec(ft["rescale"], device)
         prior = _dev_vec(head.prior, device)
         rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
+        fused = fused_head_ok(models, head)
+        n_lin = len(getattr(plan0, "layers", ())) + 1
         out_on_device = isinstance(out, torch.Tensor) and out.is_cuda
         out_h = None if (out_on_device or out is None) else _as_host_tensor(out)
         if out is None and sink is None:
@@ -528,13 +565,6 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
                 ops.splice_transform(x_dev, n_total, splice, add, mul,
                                      None if iv_dev is None else iv_dev[c0 - iv0:c1 - iv0], f0=c0, f1=c1, x_row0=lo,
                                      out_kind=plan0.in_kind, ldo=ld_in, out=(a_hi, a_lo))
-            if head_done[buf] is not None:
-                main.wait_event(head_done[buf])  # the head of chunk i-2 still reads these logits
-            logits = [ff_logits(m, p, a_hi, a_lo, rows, f"ff{k}.{buf}", ws) for k, (m, p) in enumerate(zip(models, plans))]
-            gemm_done = torch.cuda.Event()
-            gemm_done.record(main)
-            hkw = dict(rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
-                       prior_scale=head.prior_scale, final_normalize=head.final_normalize)
             # this chunk's transfer format (error diffusion of the compact fraction over the chunk index)
             as_compact = compact and int((ci + 1) * frac_compact + 1e-9) > int(ci * frac_compact + 1e-9)
             via_writer = writer is not None and (as_compact or not compact)
@@ -543,19 +573,42 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
             else:
                 ob, n_f = n_f % 2, n_f + 1   # ring position among the float32 chunks
             last = copied_c if as_compact else copied_f
-            aux.wait_event(gemm_done)
-            with torch.cuda.stream(aux):
+            if fused:
+                # output layer + head as ONE kernel on the main stream (no logits buffer, nothing for `aux` to do)
+                h_hi, h_lo = mlp_hidden(models[0], plan0, a_hi, a_lo, rows, ws)
+                okw = dict(prior=prior, prior_scale=head.prior_scale, nsplit=plan0.prec.nsplit(n_lin - 1, n_lin))
                 if out_on_device:
-                    ops.head(logits, n_out, out=out[c0:c1], **hkw)
+                    plan0.out.logsoftmax(h_hi, h_lo, rows, out=out[c0:c1], **okw)
                 else:
                     if last[ob] is not None:
-                        aux.wait_event(last[ob])  # the side stream still reads this buffer
+                        main.wait_event(last[ob])  # the side stream still reads this buffer
                     if as_compact:
-                        ops.head(logits, n_out, out16=(o16_dev[ob], ref_dev[ob]), **hkw)
+                        plan0.out.logsoftmax(h_hi, h_lo, rows, out16=(o16_dev[ob], ref_dev[ob]), **okw)
                     else:
-                        ops.head(logits, n_out, out=out_dev[ob], **hkw)
+                        plan0.out.logsoftmax(h_hi, h_lo, rows, out=out_dev[ob], **okw)
                 hd = torch.cuda.Event()
-                hd.record(aux)
+                hd.record(main)
+            else:
+                if head_done[buf] is not None:
+                    main.wait_event(head_done[buf])  # the head of chunk i-2 still reads these logits
+                logits = [ff_logits(m, p, a_hi, a_lo, rows, f"ff{k}.{buf}", ws) for k, (m, p) in enumerate(zip(models, plans))]
+                gemm_done = torch.cuda.Event()
+                gemm_done.record(main)
+                hkw = dict(rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
+                           prior_scale=head.prior_scale, final_normalize=head.final_normalize)
+                aux.wait_event(gemm_done)
+                with torch.cuda.stream(aux):
+                    if out_on_device:
+                        ops.head(logits, n_out, out=out[c0:c1], **hkw)
+                    else:
+                        if last[ob] is not None:
+                            aux.wait_event(last[ob])  # the side stream still reads this buffer
+                        if as_compact:
+                            ops.head(logits, n_out, out16=(o16_dev[ob], ref_dev[ob]), **hkw)
+                        else:
+                            ops.head(logits, n_out, out=out_dev[ob], **hkw)
+                    hd = torch.cuda.Event()
+                    hd.record(aux)
             head_done[buf] = hd
             if out_on_device:
                 continue

@@ -151,6 +151,44 @@ def linear_bias_act(a_hi, a_lo, w_hi, w_lo, bias, M, N, K, act="identity", out_k
     return hi, lo
 
 
+FUSED_HEAD_MAX_CLASSES = 2048  # eight 256-column tiles: one thread-block cluster spans a row
+
+
+def linear_logsoftmax(a_hi, a_lo, w_hi, w_lo, bias, M, N, K, prior=None, prior_scale=1.0, nsplit=1, elem=ELEM_BF16,
+                      out=None, out16=None, out_row_map=None):
+    """K2 + K4 fused for one net without RPL: log_softmax(A . W^T + bias - prior_scale * prior) straight from the
+    accumulators (the float32 logits never go to HBM).  ``out``: float32 (rows_out, >= N) tensor, or ``out16`` = (fp16
+    (rows_out, ld16), f32 (rows_out,)) for the compact transfer format; ``out_row_map`` as in :func:`head`."""
+    for t, n in ((a_hi, "a_hi"), (w_hi, "w_hi")):
+        _req(t, E16[elem], n)
+    for t, n in ((a_lo, "a_lo"), (w_lo, "w_lo")):
+        _req(t, torch.bfloat16, n)
+    _req(bias, torch.float32, "bias")
+    _req(prior, torch.float32, "prior")
+    _req(out_row_map, torch.int32, "out_row_map")
+    if nsplit in (SPLIT_NONE, SPLIT_W):
+        a_lo = None
+    if nsplit in (SPLIT_NONE, SPLIT_A):
+        w_lo = None
+    o16 = ref = None
+    if out16 is not None:
+        o16, ref = out16
+        _req(o16, torch.float16, "out16")
+        _req(ref, torch.float32, "row_ref")
+        out = None
+    else:
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.float32, device=a_hi.device)
+        _req(out, torch.float32, "out")
+    with _Prof("gemm", 2.0 * M * N * K):
+        check(_native.lib().nnam_linear_logsoftmax(_ptr(a_hi), _ptr(a_lo), a_hi.stride(0), _ptr(w_hi), _ptr(w_lo),
+                                                   w_hi.stride(0), _ptr(bias), _ptr(prior), float(prior_scale), _ptr(out),
+                                                   0 if out is None else out.stride(0), _ptr(o16),
+                                                   0 if o16 is None else o16.stride(0), _ptr(ref), _ptr(out_row_map),
+                                                   M, N, K, nsplit, elem, _stream()))
+    return out16 if out16 is not None else out
+
+
 def head(logits, n_classes, rows=None, weights=None, pre_normalize=False, rpl=None, prior=None, prior_scale=1.0,
          final_normalize=True, out=None, out_row_map=None, out16=None):
     """K4.  logits: one (rows, ld) f32 tensor or a list of them (ensemble).  ``out16`` = (fp16 (rows_out, ld16), f32

@@ -17,7 +17,7 @@ import torch
 
 from . import engine, ops
 from ._native import NnamError, RnnDesc
-from .engine import HeadSpec, LinearDev, _as_host_tensor, _dev_vec, _device, get_plan
+from .engine import HeadSpec, LinearDev, _as_host_tensor, _dev_vec, _device, fused_head_ok, get_plan
 from .ops import OUT_BF16, OUT_BF16_SPLIT, OUT_F32, round_up
 
 CELL_LSTM, CELL_GRU, CELL_PEEPHOLE = 0, 1, 2
@@ -770,6 +770,7 @@ def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, o
     ops.gather_transform(x_dev, d_src, add, mul, iv_dev, out_kind=plan.act_kind, ldo=ld_in, out=(a_hi, a_lo))
     n_out = models[0].n_out
     logits = []
+    fused = fused_head_ok(models, head)
     for k, (m, pl) in enumerate(zip(models, plans)):
         if m.in_size != d_in or m.n_out != n_out:
             raise NnamError("forward_utterances: ensemble members must share input and output sizes")
@@ -784,6 +785,8 @@ def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, o
             if key not in scheds:  # same utterances and batch width => same packed row order, other grouping
                 scheds[key], _ = pick_schedule(pl, lens + timedelay, device, nb)
             h_hi, h_lo, _ = run_layers(m, pl, scheds[key], a_hi, a_lo, rows, nb, ws=ws)
+        if fused:
+            break  # one member: its output layer runs fused with the head below
         lg = ws.get(f"rnn.logits{k}", rows, round_up(n_out, 16), torch.float32)
         pl.out(h_hi, h_lo, rows, "identity", OUT_F32, out=(lg, None))
         logits.append(lg)
@@ -792,6 +795,10 @@ def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, o
             t[int(out_starts[u]):int(out_starts[u] + lens[u])].zero_()
     prior = _dev_vec(head.prior, device)
     rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
+    if fused:
+        plans[0].out.logsoftmax(h_hi, h_lo, rows, prior=prior, prior_scale=head.prior_scale, out_row_map=d_dst,
+                                out=None if out16 is not None else out_dev, out16=out16)
+        return
     ops.head(logits, n_out, rows=rows, weights=head.weights, pre_normalize=head.pre_normalize, rpl=rpl, prior=prior,
              prior_scale=head.prior_scale, final_normalize=head.final_normalize, out=out_dev, out_row_map=d_dst,
              out16=out16)

@@ -184,6 +184,66 @@ def test_head_compact_transfer_format(ops, dev):
 
 
 # ----------------------------------------------------------------------------------------- K2
+@pytest.mark.parametrize("m,n,k,elem,nsplit", [(1000, 1909, 512, "f16", 1), (4173, 1909, 1024, "f16", 1), (300, 39, 136, "bf16", 1),
+                                                (777, 600, 72, "bf16", 1), (129, 2048, 2048, "f16", 1), (1500, 1909, 440, "bf16", 3),
+                                                (20000, 1909, 512, "f16", 1)])
+def test_linear_logsoftmax_fused(ops, dev, m, n, k, elem, nsplit):
+    """nnam_linear_logsoftmax (output layer + head in one kernel, row statistics exchanged across a thread-block cluster)
+    against the unfused pair nnam_linear_bias_act -> nnam_head / nnam_head_f16 on the same operands, and against the
+    float64 result: plain rows, scatter map with dropped and zero-filled rows, prior, compact format."""
+    rng = np.random.default_rng(m + n + k)
+    a = rng.standard_normal((m, k)).astype(np.float32)
+    w = (3.0 * rng.standard_normal((n, k)) / np.sqrt(k)).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    ap = (-3 + rng.standard_normal(n)).astype(np.float32)
+    e = ops.ELEM_F16 if elem == "f16" else ops.ELEM_BF16
+    kind = ops.OUT_BF16_SPLIT if nsplit == 3 else (ops.OUT_F16 if elem == "f16" else ops.OUT_BF16)
+    a_hi, a_lo = ops.convert_f32(_t(a, dev), kind)
+    w_hi, w_lo = ops.convert_f32(_t(w, dev), kind)
+    bd, apd = _t(b, dev), _t(ap, dev)
+    logits, _ = ops.linear_bias_act(a_hi, a_lo, w_hi, w_lo, bd, m, n, k, out_kind=ops.OUT_F32, nsplit=nsplit, elem=e)
+    for prior, scale in ((None, 1.0), (apd, 0.7)):
+        want = ops.head(logits, n, rows=m, prior=prior, prior_scale=scale).cpu().numpy()
+        got = ops.linear_logsoftmax(a_hi, a_lo, w_hi, w_lo, bd, m, n, k, prior=prior, prior_scale=scale, nsplit=nsplit,
+                                    elem=e).cpu().numpy()
+        assert got.shape == (m, n)
+        assert np.abs(got - want).max() < 2e-5
+        assert np.abs(np.exp(got.astype(np.float64)).sum(axis=1) - 1).max() < 1e-4
+    if elem == "f16" and nsplit == 1:  # float64 check on the fp16-rounded operands
+        z = a_hi.float().cpu().numpy().astype(np.float64)[:m, :k] @ w_hi.float().cpu().numpy().astype(np.float64)[:n, :k].T + b
+        z -= z.max(axis=1, keepdims=True)
+        ref = z - np.log(np.exp(z).sum(axis=1, keepdims=True))
+        got = ops.linear_logsoftmax(a_hi, a_lo, w_hi, w_lo, bd, m, n, k, elem=e).cpu().numpy()
+        assert np.abs(got - ref).max() < 1e-4  # fp32 accumulation over K <= 2048 + approximate exp2
+    # scatter map: a permutation with one dropped row and one zero-filled row
+    rmap = rng.permutation(m).astype(np.int32)
+    lost = int(rmap[min(77, m - 1)])
+    rmap[5], rmap[min(77, m - 1)] = -1, -2 - int(rmap[5])
+    zrow = -2 - int(rmap[min(77, m - 1)])
+    rm = _t(rmap, dev)
+    want = torch.full((m, n), 7.0, device=dev)
+    ops.head(logits, n, rows=m, prior=apd, out=want, out_row_map=rm)
+    got = torch.full((m, n), 7.0, device=dev)
+    ops.linear_logsoftmax(a_hi, a_lo, w_hi, w_lo, bd, m, n, k, prior=apd, nsplit=nsplit, elem=e, out=got, out_row_map=rm)
+    want, got = want.cpu().numpy(), got.cpu().numpy()
+    assert np.all(got[zrow] == 0) and np.all(got[lost] == 7.0)
+    assert np.abs(got - want).max() < 2e-5
+    # compact transfer format
+    ld16 = (n + 7) // 8 * 8
+    o16w = torch.full((m, ld16), 9.0, dtype=torch.float16, device=dev)
+    refw = torch.full((m,), 9.0, device=dev)
+    ops.head(logits, n, rows=m, prior=apd, out16=(o16w, refw), out_row_map=rm)
+    o16 = torch.full((m, ld16), 9.0, dtype=torch.float16, device=dev)
+    ref = torch.full((m,), 9.0, device=dev)
+    ops.linear_logsoftmax(a_hi, a_lo, w_hi, w_lo, bd, m, n, k, prior=apd, nsplit=nsplit, elem=e, out16=(o16, ref),
+                          out_row_map=rm)
+    assert np.abs(ref.cpu().numpy() - refw.cpu().numpy()).max() < 2e-5
+    d = (o16.float() - o16w.float()).abs().cpu().numpy()[:, :n]
+    scale_ = np.maximum(o16w.float().abs().cpu().numpy()[:, :n], 1.0)
+    assert (d <= 2.0 ** -10 * scale_ + 2e-5).all()  # one fp16 ulp: the two paths round v - max from slightly different v
+    assert np.all(o16.cpu().numpy()[:, n:] == 9.0)  # padding columns untouched
+
+
 @pytest.mark.parametrize("m,n,k", [(128, 256, 64), (1, 16, 8), (300, 1024, 544), (1000, 1909, 440), (77, 40, 40),
                                    (2048, 2048, 2048), (513, 2048, 140), (129, 1909, 1024),
                                    # M >= 4096 runs the CTA-pair (cta_group::2) kernel: ragged M, ragged N, short K
