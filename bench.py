@@ -429,7 +429,8 @@ def roofline_block(kern, peaks, wname, steps):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(f"{wname}:{dom}")
     if dom in ("gemm", "rnn"):
-        roof = {"bound": "tensor", "kernel": "gemm_bias_act_kernel + gemm_bias_act_2sm_kernel" if dom == "gemm" else "rnn_seq_kernel",
+        roof = {"bound": "tensor", "kernel": ("gemm_bias_act_2sm_kernel + gemm_bias_act_kernel + gemm_logsoftmax_kernel (output layer fused with the head)"
+                           if dom == "gemm" else "rnn_seq_kernel"),
                 "achieved": kern[dom]["tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": kern[dom]["tflops"] / peaks["tf_sustained"], "traffic": traffic,
                 "peak_source": f"{peaks['src']} 16-bit dense sustained (kernel timed inside a long step); burst peak "

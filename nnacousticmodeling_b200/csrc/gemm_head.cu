@@ -9,10 +9,10 @@
 // because the row-wise log-sum-exp spans eight 256-column GEMM tiles.  Here the CTAs that hold the column tiles of one
 // 128-row block form a THREAD-BLOCK CLUSTER (one CTA per tile, <= 8):
 //
-//   pass 1   each epilogue thread owns one row of its CTA's accumulator tile (a TMEM lane): running max m and
-//            s = sum exp(v - m) over the tile's valid columns
+//   pass 1   eight epilogue warps, two per TMEM lane quarter: a thread owns one row (a TMEM lane) of one 128-column half
+//            of its CTA's accumulator tile: running max m and s = sum exp(v - m) over the half's valid columns
 //   exchange (m, s) of every row goes into the shared memory of ALL CTAs of the cluster with st.async, which completes
-//            transaction bytes on the receiving CTA's mbarrier -- 8 partials per row, no fences
+//            transaction bytes on the receiving CTA's mbarrier -- 16 partials per row, no fences
 //   pass 2   lse = M + log(sum_r s_r exp(m_r - M)); the accumulator is read from TMEM a second time, v - lse goes through
 //            a swizzled shared-memory box and leaves as 128-byte row segments (the (N, 1909) float32 rows are only
 //            4-byte aligned, so no TMA store), through the optional row map of the recurrent path
@@ -32,14 +32,16 @@ constexpr int BM = 128;
 constexpr int BN = 256;
 constexpr int BK = 64;
 constexpr int UK = 16;
-constexpr int ST = 4;
+constexpr int ST = 3;
+constexpr int HALF = 128;                   // columns of a tile one epilogue warp handles
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KiB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KiB
-constexpr int THREADS = 256;
+constexpr int THREADS = 384;                // 4 control warps + 8 epilogue warps
 constexpr int BOX_BYTES = 32 * 128;         // one epilogue warp's staging box: 32 rows x 128 B
 constexpr int MAX_CLUSTER = 8;
-constexpr int XCHG_BYTES = 2 * MAX_CLUSTER * BM * 8;  // [accumulator parity][source rank][row] (m, s)
-constexpr int SMEM_BYTES = ST * (A_STAGE_BYTES + B_STAGE_BYTES) + 4 * BOX_BYTES + BN * 4 + XCHG_BYTES + 256;
+constexpr int XCHG_BYTES = 2 * 2 * MAX_CLUSTER * BM * 8;  // [accumulator parity][source rank, half][row] (m, s)
+constexpr int ROWPTR_BYTES = 8 * 32 * 8;               // per epilogue warp: output address of each of its 32 rows
+constexpr int SMEM_BYTES = ST * (A_STAGE_BYTES + B_STAGE_BYTES) + 8 * BOX_BYTES + BN * 4 + XCHG_BYTES + ROWPTR_BYTES + 256;
 static_assert(SMEM_BYTES <= 227 * 1024, "fused output kernel: shared memory over budget");
 constexpr int TMEM_COLS = 512;
 constexpr float NEG_BIG = -3.0e38f;  // finite stand-in for -inf as the running maximum's start value
@@ -75,7 +77,7 @@ __device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, f
                "f"(a), "f"(b), "r"(cluster_bar)
                : "memory");
 }
-__device__ __forceinline__ void named_bar_sync_epi() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // running (max, sum exp) over one 32-column chunk held as raw accumulator bits + the staged bias slice
 __device__ __forceinline__ void online_chunk(const uint32_t (&r)[32], const float* bias_s, float& m, float& s) {
@@ -102,7 +104,7 @@ __device__ __forceinline__ void online_chunk(const uint32_t (&r)[32], const floa
 }
 
 template <bool COMPACT>
-__global__ void __maxnreg__(184)
+__global__ void __maxnreg__(168)
     gemm_logsoftmax_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                            const __grid_constant__ CUtensorMap tm_w_hi, const __grid_constant__ CUtensorMap tm_w_lo,
                            const Params p) {
@@ -110,9 +112,10 @@ __global__ void __maxnreg__(184)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + ST * A_STAGE_BYTES;
   uint8_t* smem_epi = smem_b + ST * B_STAGE_BYTES;
-  float* bias_s = reinterpret_cast<float*>(smem_epi + 4 * BOX_BYTES);
+  float* bias_s = reinterpret_cast<float*>(smem_epi + 8 * BOX_BYTES);
   float2* xchg = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bias_s) + BN * 4);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + XCHG_BYTES);
+  unsigned long long* rowptr_s = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(xchg) + XCHG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rowptr_s) + ROWPTR_BYTES);
   uint64_t* empty_bar = full_bar + ST;
   uint64_t* tfull_bar = empty_bar + ST;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -144,7 +147,7 @@ __global__ void __maxnreg__(184)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);                         // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
       mbar_init(&x_bar[a], 1);  // one arrive.expect_tx per block; the peers' st.async stores complete the bytes
     }
     fence_mbar_init();
@@ -222,13 +225,17 @@ __global__ void __maxnreg__(184)
       if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
-    // -------------------------------------------------------------- epilogue
+    // -------------------------------------------------------------- epilogue: 8 warps, two per TMEM lane quarter
     const int q = warp & 3;               // TMEM lane quarter of this warp
+    const int hf = (warp - 4) >> 2;       // which 128-column half of the tile this warp handles
     const int trow = q * 32 + lane;       // row of the 128-row block = TMEM lane this thread owns
-    uint8_t* box = smem_epi + q * BOX_BYTES;
+    const int h0 = hf * HALF;             // first column (within the tile) of this warp's half
+    uint8_t* box = smem_epi + (warp - 4) * BOX_BYTES;
+    unsigned long long* rowptr = rowptr_s + (warp - 4) * 32;  // this warp's copy of its rows' output addresses
     // the CTA's column tile never changes: stage bias - prior_scale * prior once; columns >= N get -inf, so they drop
     // out of max / sum-exp without predicates (their accumulators are 0: the TMA zero-fills W rows >= N)
-    for (int c = q * 32 + lane; c < BN; c += 128) {
+    {
+      const int c = threadIdx.x - 128;  // 256 epilogue threads, 256 columns
       const int gc = n0 + c;
       float b = -CUDART_INF_F;
       if (gc < p.N) {
@@ -238,8 +245,9 @@ __global__ void __maxnreg__(184)
       bias_s[c] = b;
     }
     named_bar_sync_epi();
-    const int valid = min(BN, p.N - n0);
-    const int nch = (valid + 31) >> 5;  // 32-column chunks with at least one valid column (warp-uniform, >= 1)
+    const int valid = max(0, min(HALF, p.N - n0 - h0));  // valid columns of this warp's half (0 for a ragged last tile)
+    const int nch = (valid + 31) >> 5;                   // 32-column chunks with at least one valid column
+    const float* bias_h = bias_s + h0;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t x_phase = 0;  // bit a: phase of x_bar[a]
@@ -254,35 +262,46 @@ __global__ void __maxnreg__(184)
           zero = true;
         }
       }
+      // address of this row's first element of the warp's half, staged for the store loops (0: row not written)
+      {
+        unsigned long long a = 0;
+        if (orow >= 0)
+          a = COMPACT ? reinterpret_cast<unsigned long long>(p.out16 + orow * p.ld16 + n0 + h0)
+                      : reinterpret_cast<unsigned long long>(p.out + orow * p.ld_out + n0 + h0);
+        rowptr[lane] = a;
+      }
+      __syncwarp();
+      const uint32_t vmask = __ballot_sync(0xffffffffu, orow >= 0);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN);
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + h0);
 
-      // ---- pass 1: running max / sum-exp over this tile's columns; the load of chunk c+1 is in flight while chunk c
+      // ---- pass 1: running max / sum-exp over this half's columns; the load of chunk c+1 is in flight while chunk c
       // is reduced
       float m = NEG_BIG, s = 0.0f;
-      {
+      if (nch > 0) {
         uint32_t ra[32], rb[32];
         tmem_ld32(taddr, ra);
         tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < BN / 32; c += 2) {
+        for (int c = 0; c < HALF / 32; c += 2) {
           if (c < nch) {
             if (c + 1 < nch) tmem_ld32(taddr + 32 * (c + 1), rb);
-            online_chunk(ra, bias_s + 32 * c, m, s);
+            online_chunk(ra, bias_h + 32 * c, m, s);
             tmem_ld_wait();
             if (c + 2 < nch) tmem_ld32(taddr + 32 * (c + 2), ra);
-            if (c + 1 < nch) online_chunk(rb, bias_s + 32 * (c + 1), m, s);
+            if (c + 1 < nch) online_chunk(rb, bias_h + 32 * (c + 1), m, s);
             tmem_ld_wait();
           }
         }
       }
 
-      // ---- exchange the row partials with every CTA of the cluster (this one included)
+      // ---- exchange the row partials with every CTA of the cluster (this one included): 2 * cl partials per row
       {
-        // this CTA's barrier expects (m, s) of 128 rows from each of the `cl` CTAs in the current phase
-        if (q == 0 && lane == 0) mbar_expect_tx(&x_bar[acc], static_cast<uint32_t>(cl * BM * 8));
-        const uint32_t slot = smem_u32(xchg + (acc * MAX_CLUSTER + rank) * BM + trow);
+        // this CTA's barrier expects (m, s) of 128 rows from both halves of each of the `cl` CTAs in the current phase
+        if (warp == 4 && lane == 0) mbar_expect_tx(&x_bar[acc], static_cast<uint32_t>(cl * 2 * BM * 8));
+        const uint32_t slot = smem_u32(xchg + (acc * 2 * MAX_CLUSTER + rank * 2 + hf) * BM + trow);
         const uint32_t bar = smem_u32(&x_bar[acc]);
         for (int r = 0; r < cl; ++r)
           st_async_f32x2(mapa_shared(slot, static_cast<uint32_t>(r)), m, s, mapa_shared(bar, static_cast<uint32_t>(r)));
@@ -290,16 +309,16 @@ __global__ void __maxnreg__(184)
         x_phase ^= 1u << acc;
       }
       float mx = NEG_BIG;
-      for (int r = 0; r < cl; ++r) mx = fmaxf(mx, xchg[(acc * MAX_CLUSTER + r) * BM + trow].x);
+      for (int r = 0; r < 2 * cl; ++r) mx = fmaxf(mx, xchg[(acc * 2 * MAX_CLUSTER + r) * BM + trow].x);
       float sum = 0.0f;
-      for (int r = 0; r < cl; ++r) {
-        const float2 t = xchg[(acc * MAX_CLUSTER + r) * BM + trow];
+      for (int r = 0; r < 2 * cl; ++r) {
+        const float2 t = xchg[(acc * 2 * MAX_CLUSTER + r) * BM + trow];
         sum = fmaf(t.y, ex2_approx((t.x - mx) * LOG2E), sum);
       }
       const float log_sum = logf(sum);
       // float32 rows: v - (mx + log_sum).  compact: fp16(v - mx) and row_ref = max_c y = -log_sum.
       const float sub = COMPACT ? mx : mx + log_sum;
-      if (COMPACT && rank == 0 && orow >= 0) p.row_ref[orow] = zero ? 0.0f : -log_sum;
+      if (COMPACT && rank == 0 && hf == 0 && orow >= 0) p.row_ref[orow] = zero ? 0.0f : -log_sum;
 
       // ---- pass 2: second read of the accumulator, normalise, stage, store row segments
       constexpr int CH2 = COMPACT ? 64 : 32;  // columns per staged box (128 B per row)
@@ -311,14 +330,14 @@ __global__ void __maxnreg__(184)
           for (int j0 = 0; j0 < CH2 / 32; ++j0) tmem_ld32(taddr + c0 + 32 * j0, r[j0]);
           tmem_ld_wait();
           float v[CH2];
-          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_h + c0);
 #pragma unroll
           for (int j = 0; j < CH2 / 4; ++j) {
             const float4 b = b4[j];
-            v[4 * j] = zero ? 0.0f : __uint_as_float(r[(4 * j) >> 5][(4 * j) & 31]) + b.x - sub;
-            v[4 * j + 1] = zero ? 0.0f : __uint_as_float(r[(4 * j + 1) >> 5][(4 * j + 1) & 31]) + b.y - sub;
-            v[4 * j + 2] = zero ? 0.0f : __uint_as_float(r[(4 * j + 2) >> 5][(4 * j + 2) & 31]) + b.z - sub;
-            v[4 * j + 3] = zero ? 0.0f : __uint_as_float(r[(4 * j + 3) >> 5][(4 * j + 3) & 31]) + b.w - sub;
+            v[4 * j] = zero ? 0.0f : __uint_as_float(r[(4 * j) >> 5][(4 * j) & 31]) + (b.x - sub);
+            v[4 * j + 1] = zero ? 0.0f : __uint_as_float(r[(4 * j + 1) >> 5][(4 * j + 1) & 31]) + (b.y - sub);
+            v[4 * j + 2] = zero ? 0.0f : __uint_as_float(r[(4 * j + 2) >> 5][(4 * j + 2) & 31]) + (b.z - sub);
+            v[4 * j + 3] = zero ? 0.0f : __uint_as_float(r[(4 * j + 3) >> 5][(4 * j + 3) & 31]) + (b.w - sub);
           }
           if (COMPACT) {
 #pragma unroll
@@ -342,31 +361,33 @@ __global__ void __maxnreg__(184)
         if (COMPACT) {
           // rows of out16 are 16-byte aligned (ld16 % 8 == 0): 8 lanes write one 128-byte row segment, 4 rows at a time
           const int sub_row = lane >> 3, ch = lane & 7;
-          const int col = n0 + c0 + ch * 8;  // first of this lane's 8 columns
+          const int cw = c0 + ch * 8;          // first of this lane's 8 columns, within the half
+          const int left = valid - cw;         // valid columns from there on
 #pragma unroll
           for (int rr = 0; rr < 32; rr += 4) {
             const int r_ = rr + sub_row;
-            const long long dst = __shfl_sync(0xffffffffu, orow, r_);
-            if (dst >= 0 && col < p.N) {
+            const unsigned long long base = rowptr[r_];
+            if (base != 0 && left > 0) {
               const uint4 val = *reinterpret_cast<const uint4*>(box + r_ * 128 + ((ch ^ (r_ & 7)) << 4));
-              uint16_t* d = p.out16 + dst * p.ld16 + col;
-              if (col + 8 <= p.N) {
+              uint16_t* d = reinterpret_cast<uint16_t*>(base) + cw;
+              if (left >= 8) {
                 *reinterpret_cast<uint4*>(d) = val;
               } else {
                 const uint32_t w[4] = {val.x, val.y, val.z, val.w};
-                for (int e = 0; e < p.N - col; ++e) d[e] = static_cast<uint16_t>((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
+                for (int e = 0; e < left; ++e) d[e] = static_cast<uint16_t>((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
               }
             }
           }
         } else {
           // (N, C) float32 rows are only 4-byte aligned: a warp writes one 128-byte row segment per instruction
-          const int col = n0 + c0 + lane;
-#pragma unroll 8
+          const bool col_ok = c0 + lane < valid;
+          const unsigned long long lane_off = static_cast<unsigned long long>(c0 + lane) * 4ull;
+#pragma unroll
           for (int rr = 0; rr < 32; ++rr) {
-            const long long dst = __shfl_sync(0xffffffffu, orow, rr);
-            if (dst >= 0 && col < p.N) {
+            if ((vmask >> rr) & 1u) {  // warp-uniform
+              const unsigned long long base = rowptr[rr];  // broadcast
               const float val = *reinterpret_cast<const float*>(box + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
-              p.out[dst * p.ld_out + col] = val;
+              if (col_ok) *reinterpret_cast<float*>(base + lane_off) = val;
             }
           }
         }

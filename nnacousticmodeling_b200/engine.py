@@ -135,20 +135,25 @@ class LinearDev:
                                      out_row_map=out_row_map)
 
 
-def fused_head_ok(models, head):
-    """Opt-in (NNAM_FUSED_HEAD=1; =force also takes class counts below 512): run the output layer and the head as ONE
-    kernel (ops.linear_logsoftmax) when the head is plain -- a single net, no RPL, weight 1, final log-softmax, at most
-    2048 classes.  Off by default: measured SLOWER than the unfused pair for float32 rows (671 vs 294 us per 65,536 x
-    1909 x 512 chunk; the fused epilogue runs on four lone warps at IPC 0.2, profiles/r02_fused_head.md)."""
-    env = os.environ.get("NNAM_FUSED_HEAD", "0")
-    if env not in ("1", "force") or len(models) != 1 or head.rpl is not None or head.pre_normalize or not head.final_normalize:
+FUSED_HEAD_MAX_K = 1024
+
+
+def fused_head_ok(models, head, k):
+    """Run the output layer (fan-in ``k``) and the head as ONE kernel (ops.linear_logsoftmax) when the head is plain -- a
+    single net, no RPL, weight 1, final log-softmax, 512..2048 classes -- and the layer is short: up to K = 1024 the fused
+    kernel beats the unfused pair by 6-20 % (its epilogue, not its main loop, sets the pace, and the logits round trip it
+    saves is a third of the pair's time); at K = 2048 its 15 resident clusters (120 of 148 SMs) cost what the fusion
+    saves, and the feed-forward engine hides the unfused head under the next chunk's GEMMs anyway
+    (profiles/r02_fused_head.md).  NNAM_FUSED_HEAD=0 switches it off, =force takes every eligible layer."""
+    env = os.environ.get("NNAM_FUSED_HEAD", "1")
+    if env == "0" or len(models) != 1 or head.rpl is not None or head.pre_normalize or not head.final_normalize:
         return False
     if head.weights is not None and [float(w) for w in head.weights] != [1.0]:
         return False
     n = models[0].n_out
     if models[0].network == "tdnn" or n > ops.FUSED_HEAD_MAX_CLASSES:
         return False
-    return env == "force" or n >= 512
+    return env == "force" or (n >= 512 and k <= FUSED_HEAD_MAX_K)
 
 
 class Workspace:
@@ -443,7 +448,7 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
             add, mul = _dev_vec(ft["addShift"], device), _dev_vec(ft["rescale"], device)
         prior = _dev_vec(head.prior, device)
         rpl = None if head.rpl is None else tuple(_dev_vec(head.rpl[k], device) for k in ("W", "b", "lb"))
-        fused = fused_head_ok(models, head)
+        fused = fused_head_ok(models, head, plan0.out.k if hasattr(plan0, "out") else 0)
         n_lin = len(getattr(plan0, "layers", ())) + 1
         out_on_device = isinstance(out, torch.Tensor) and out.is_cuda
         out_h = None if (out_on_device or out is None) else _as_host_tensor(out)

@@ -770,7 +770,7 @@ def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, o
     ops.gather_transform(x_dev, d_src, add, mul, iv_dev, out_kind=plan.act_kind, ldo=ld_in, out=(a_hi, a_lo))
     n_out = models[0].n_out
     logits = []
-    fused = fused_head_ok(models, head)
+    fused = fused_head_ok(models, head, plans[0].out.k)
     for k, (m, pl) in enumerate(zip(models, plans)):
         if m.in_size != d_in or m.n_out != n_out:
             raise NnamError("forward_utterances: ensemble members must share input and output sizes")

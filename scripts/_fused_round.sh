@@ -1,3 +1,8 @@
 cd /root/repo
-for a in "65536 512 0 0" "65536 512 1 0" "65536 512 0 1" "65536 2048 0 0" "65536 2048 1 0"; do timeout 120 python scripts/gpu_fused_one.py $a; done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_logsoftmax -c 1 -o gpurun_out/fused_k512 python scripts/gpu_fused_one.py 65536 512 0 0 > gpurun_out/fused_ncu.log 2>&1; tail -3 gpurun_out/fused_ncu.log
+for w in cfg3 cfg4 cfg1 cfg2 cfg3t; do
+ for f in 1 0; do
+  NNAM_FUSED_HEAD=$f timeout 300 python bench.py --workload $w --no-cpu-baseline --no-cli --no-strong --extra "" --steps 6 --warmup 3 2>/dev/null | python -c "
+import sys, json
+r=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$w fused=$f', round(r['value']/1e6,2), 'M/s', round(r['ms_per_step'],2), 'ms  e2e', round(r['e2e']['value']/1e6,2), round(r['roofline']['frac'],3), r['clocks']['sm_mhz'])"
+ done
+done

@@ -163,3 +163,39 @@ def test_compact_transfer_matches_float32_transfer(nn, golden_dir):
     a = nn.predict(m, x[:2000], None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv[:2000])
     b = nn.predict(m, x[:2000], None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv[:2000], transfer="f32")
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16", "fp32"])
+def test_fused_output_layer_matches_unfused(nn, golden_dir, monkeypatch, precision):
+    """The default path runs the output layer and the head as one cluster kernel (nnam_linear_logsoftmax) for a single
+    net with 512..2048 classes; NNAM_FUSED_HEAD=0 runs nnam_linear_bias_act + nnam_head.  Same operands, so the two agree
+    to float32 rounding -- with and without a prior, float32 and compact transfer, ragged chunks; `force` also takes a
+    39-class net through it."""
+    from nnacousticmodeling_b200 import engine
+    x, off, iv = O.synth_set(23, 30, ivec_dim=100)
+    ft = nn.loadKaldiFeatureTransform(os.path.join(golden_dir, "final.feature_transform"))
+    m, _ = _mlp(nn, 17, 540, 256, 2, 1909, precision=precision)
+    ap = (-3 + np.random.default_rng(3).standard_normal(1909)).astype(np.float32)
+    res = {}
+    for env in ("0", "1"):
+        monkeypatch.setenv("NNAM_FUSED_HEAD", env)
+        assert engine.fused_head_ok([m], engine.HeadSpec(), 256) == (env == "1")
+        assert not engine.fused_head_ok([m], engine.HeadSpec(), 2048)
+        a = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv, transfer="f32")
+        b = np.zeros_like(a)
+        engine.ff_forward_frames(m, x, ft, 5, b, 0, len(x), ivectors=iv, device=0, chunk=1777, transfer="f32",
+                                 head=engine.HeadSpec(prior=ap, prior_scale=0.8))
+        c = nn.predict(m, x, None, 1909, "ff", 0, 11, 0, ft, progress=False, ivectors=iv, transfer="f16")
+        res[env] = (a, b, c)
+    for u, f in zip(res["0"][:2], res["1"][:2]):
+        assert np.abs(u - f).max() < 3e-5
+        assert np.mean(u.argmax(axis=1) == f.argmax(axis=1)) > 0.9995
+    u, f = res["0"][2], res["1"][2]
+    assert np.all(np.abs(u - f) <= 2.0 ** -10 * (u.max(axis=1, keepdims=True) - u) + 3e-5)
+    small, _ = _mlp(nn, 18, 540, 128, 2, 39, precision=precision)
+    monkeypatch.setenv("NNAM_FUSED_HEAD", "0")
+    want = nn.predict(small, x, None, 39, "ff", 0, 11, 0, ft, progress=False, ivectors=iv)
+    monkeypatch.setenv("NNAM_FUSED_HEAD", "force")
+    assert engine.fused_head_ok([small], engine.HeadSpec(), 128) and engine.fused_head_ok([m], engine.HeadSpec(), 2048)
+    got = nn.predict(small, x, None, 39, "ff", 0, 11, 0, ft, progress=False, ivectors=iv)
+    assert np.abs(got - want).max() < 3e-5

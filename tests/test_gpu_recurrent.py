@@ -431,3 +431,27 @@ def test_repeated_runs_are_bit_identical(nn, network, nb, monkeypatch):
     assert np.isfinite(outs[0]).all()
     for o in outs[1:]:
         assert np.array_equal(o, outs[0])
+
+
+@pytest.mark.parametrize("network,precision", [("lstm", "fp16"), ("lstm", "fp32"), ("blstm", "fp16"), ("gru", "bf16")])
+def test_fused_output_layer_matches_unfused_recurrent(nn, monkeypatch, network, precision):
+    """Recurrent path: the fused output layer + head (default for 512..2048 classes) scatters the packed time-major rows to
+    their frames, drops the delay rows and zero-fills the quirk-Q4 rows exactly like nnam_head_scatter."""
+    rng = np.random.default_rng(43)
+    lens = rng.integers(2, 90, size=300).tolist()
+    off = _offsets(lens)
+    x = rng.standard_normal((off[-1], 40)).astype(np.float32)
+    bid = network == "blstm"
+    m, _ = _lstm(nn, 11, network, 40, 128, 2, 1909, precision=precision, bidirectional=bid)
+    td = 0 if bid else 3
+    res = {}
+    for env in ("0", "1"):
+        monkeypatch.setenv("NNAM_FUSED_HEAD", env)
+        res[env] = (nn.predict(m, x, off, 1909, network, 0, 1, td, None, progress=False, transfer="f32"),
+                    nn.predict(m, x, off, 1909, network, 0, 1, td, None, progress=False, transfer="f16"))
+    u, f = res["0"][0], res["1"][0]
+    assert np.array_equal(u == 0, f == 0)
+    assert np.abs(u - f).max() < 3e-5
+    u, f = res["0"][1], res["1"][1]
+    assert np.array_equal(u == 0, f == 0)
+    assert np.all(np.abs(u - f) <= 2.0 ** -10 * (u.max(axis=1, keepdims=True) - u) + 3e-5)
