@@ -429,7 +429,7 @@ def roofline_block(kern, peaks, wname, steps):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(f"{wname}:{dom}")
     if dom in ("gemm", "rnn"):
-        roof = {"bound": "tensor", "kernel": ("gemm_bias_act_2sm_kernel + gemm_bias_act_kernel + gemm_logsoftmax_kernel (output layer fused with the head)"
+        roof = {"bound": "tensor", "kernel": ("gemm_bias_act_2sm_kernel + gemm_bias_act_kernel (+ gemm_logsoftmax_kernel where the output layer runs fused with the head: K <= 1024)"
                            if dom == "gemm" else "rnn_seq_kernel"),
                 "achieved": kern[dom]["tflops"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": kern[dom]["tflops"] / peaks["tf_sustained"], "traffic": traffic,
