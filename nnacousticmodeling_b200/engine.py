@@ -666,18 +666,20 @@ MIN_WIDEN_THREADS = 12  # host threads a process needs before the compact transf
 
 def use_compact_transfer(plan, transfer=None, recurrent=False, host_threads=None, mixable=False):
     """Does a host-bound pass of ``plan`` use the compact (fp16 offsets + row maximum) transfer format?  Explicit
-    ``transfer`` ("f16" / "f32") wins, then the environment (NNAM_TRANSFER), then the path and precision mode: the
-    feed-forward path in a 16-bit mode (tolerance 5e-2) takes it -- its chunks stream, so the host widens chunk i while
-    chunk i+1 crosses PCIe (measured +22 % end to end on cfg2).  The fp32-accurate mode (tolerance 1e-3) keeps float32
-    rows, and so does the recurrent path: its rows only exist after the last layer, the widening cannot hide under
-    anything, and it measured 3-7 % slower than the plain copy.  The widening needs host cores: with 16 threads it
-    sustains 64 GB/s of float32 and wins; with the 4 threads a rank gets when 8 processes share a 32-core box it is the
-    bottleneck (10.4 M against 11.9 M frames/s on 8 GPUs, where plain copies already run at 98 % of the box's 92.6 GB/s
-    D2H ceiling), so ALL-compact is only chosen when the process has at least MIN_WIDEN_THREADS.  With a pinned
-    destination (``mixable``) the feed-forward path instead sends a measured FRACTION of the chunks compact and the rest as
-    float32 rows, which helps with any number of threads (_TransferStats; profiles/r02_transfer.md)."""
+    ``transfer`` ("f16" / "f32") wins, then the environment (NNAM_TRANSFER), then the precision mode and the host: the
+    16-bit modes (tolerance 5e-2) take it, the fp32-accurate mode (tolerance 1e-3) keeps float32 rows.  Feed-forward
+    path: chunks stream, the host widens chunk i while chunk i+1 crosses PCIe (+22 % to +80 % end to end on cfg2).
+    Recurrent path: rows only exist after the last layer of a subset of utterances; each subset is packed into one
+    contiguous block, crosses PCIe in pieces and is scattered to its frames by the widening threads (cfg3 8.1 M vs 6.3 M,
+    cfg4 6.5 M vs 5.5 M, cfg3t 9.8 M vs 6.5 M frames/s where the piece ring stays in the last-level cache; a tie
+    -- +4 % / -1 % / +13 % -- on a box where it does not).  The widening needs host cores: with the 4 threads a rank gets
+    when 8 processes share a 32-core box it is the bottleneck (10.4 M against 11.9 M frames/s on 8 GPUs, where plain
+    copies already run at 98 % of the box's 92.6 GB/s D2H ceiling), so ALL-compact is only chosen when the process has
+    at least MIN_WIDEN_THREADS.  With a pinned destination (``mixable``) the feed-forward path instead sends a measured
+    FRACTION of the chunks compact and the rest as float32 rows, which helps with any number of threads
+    (_TransferStats; profiles/r02_transfer.md)."""
     threads = host_threads or default_host_threads()
-    auto = "f32" if (plan.split or recurrent or (threads < MIN_WIDEN_THREADS and not mixable)) else "f16"
+    auto = "f32" if (plan.split or (threads < MIN_WIDEN_THREADS and not (mixable and not recurrent))) else "f16"
     mode = transfer or os.environ.get("NNAM_TRANSFER") or auto
     if mode not in ("f16", "f32"):
         raise NnamError(f"transfer must be 'f16' or 'f32' (got {mode!r})")

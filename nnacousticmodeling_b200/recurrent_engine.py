@@ -860,7 +860,7 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         n_out = models[0].n_out
         on_dev = isinstance(out, torch.Tensor) and out.is_cuda
         n_rows = f_hi - f_lo
-        compact = (not on_dev) and engine.use_compact_transfer(plan, transfer, recurrent=True)
+        compact = (not on_dev) and engine.use_compact_transfer(plan, transfer, recurrent=True, host_threads=host_threads)
         out16 = None
         if compact:
             ld16 = round_up(n_out, 8)

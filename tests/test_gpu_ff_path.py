@@ -147,7 +147,8 @@ def test_compact_transfer_matches_float32_transfer(nn, golden_dir):
     assert not np.array_equal(f32, f16)
     plan = engine.get_plan(m, 0)  # the default: compact in a 16-bit mode when the process has cores to widen with
     assert engine.use_compact_transfer(plan, host_threads=16) and not engine.use_compact_transfer(plan, host_threads=4)
-    assert not engine.use_compact_transfer(plan, host_threads=16, recurrent=True)
+    assert engine.use_compact_transfer(plan, host_threads=16, recurrent=True)
+    assert not engine.use_compact_transfer(plan, host_threads=4, recurrent=True, mixable=True)  # no mixing there
     dist = f32.max(axis=1, keepdims=True) - f32
     assert np.all(np.abs(f16 - f32) <= 2.0 ** -11 * dist + 2e-5)
     assert np.array_equal(f16.argmax(axis=1), f32.argmax(axis=1))

@@ -384,7 +384,7 @@ def test_exchange_buffer_contents_on_entry_are_irrelevant(nn, network, nb):
 
 
 def test_recurrent_compact_transfer(nn):
-    """Recurrent path with transfer="f16" (opt-in there): compact rows through the pinned staging area, widened on the
+    """Recurrent path with transfer="f16" (the default of the 16-bit modes): compact rows through the pinned staging area, widened on the
     host per phase; quirk Q4 rows stay exactly 0, everything else within the format's bound of the float32 transfer."""
     rng = np.random.default_rng(41)
     lens = rng.integers(2, 70, size=260).tolist()
@@ -392,8 +392,14 @@ def test_recurrent_compact_transfer(nn):
     x = rng.standard_normal((off[-1], 40)).astype(np.float32)
     m, _ = _lstm(nn, 9, "lstm", 40, 128, 2, 1909, precision="fp16")
     f32 = nn.predict(m, x, off, 1909, "lstm", 0, 1, 3, None, progress=False, transfer="f32")
-    assert np.array_equal(nn.predict(m, x, off, 1909, "lstm", 0, 1, 3, None, progress=False), f32)  # default: float32 rows
     f16 = nn.predict(m, x, off, 1909, "lstm", 0, 1, 3, None, progress=False, transfer="f16")
+    from nnacousticmodeling_b200 import engine  # default: compact when the process has the threads to widen with
+    auto = f16 if engine.default_host_threads() >= engine.MIN_WIDEN_THREADS else f32
+    assert np.array_equal(nn.predict(m, x, off, 1909, "lstm", 0, 1, 3, None, progress=False), auto)
+    m.precision = "fp32"  # the fp32-accurate mode keeps float32 rows
+    a = nn.predict(m, x, off, 1909, "lstm", 0, 1, 3, None, progress=False)
+    assert np.array_equal(a, nn.predict(m, x, off, 1909, "lstm", 0, 1, 3, None, progress=False, transfer="f32"))
+    m.precision = "fp16"
     assert np.array_equal(f16 == 0, f32 == 0)
     dist = f32.max(axis=1, keepdims=True) - f32
     assert np.all(np.abs(f16 - f32) <= 2.0 ** -11 * dist + 2e-5)
