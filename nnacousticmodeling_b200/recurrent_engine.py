@@ -804,6 +804,84 @@ def _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, starts, lens, o
              out16=out16)
 
 
+class _PackedDrainer:
+    """Ships the packed compact rows of finished utterance subsets to the host on its own thread, so that the thread
+    which launches kernels never blocks on the staging ring (launching one subset takes several ms of host time, and the
+    previous subset's rows should be on the wire meanwhile).  The packed rows cross PCIe in pieces of a few thousand rows
+    through a small ring of pinned buffers; engine._ChunkWriter's helper thread widens each piece into its frame
+    positions of ``out`` while the piece is still in the last-level cache (as in the feed-forward path)."""
+
+    def __init__(self, plan, out, out16, n_out, side, device, threads):
+        import queue
+        import threading
+        self.piece = max(256, int(os.environ.get("NNAM_PIECE_ROWS", "4096")))
+        self.slots = max(2, int(os.environ.get("NNAM_PIECE_SLOTS", "4")))
+        ld16 = out16[0].stride(0)
+        key = ("f16", self.piece, n_out, self.slots)
+        cache = plan.__dict__.setdefault("_stage", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = [(torch.empty((self.piece, ld16), dtype=torch.float16, pin_memory=True),
+                           torch.empty((self.piece,), dtype=torch.float32, pin_memory=True)) for _ in range(self.slots)]
+        self.stage = cache[key]
+        out_np = out.numpy() if isinstance(out, torch.Tensor) else out
+        self.writer = engine._ChunkWriter(self.stage, True, out_np, None, n_out, threads)
+        self.out16, self.side, self.device = out16, side, device
+        self.k = 0
+        self.err = None
+        self.q = queue.Queue()
+        self.thread = threading.Thread(target=self._run, name="nnam-drain", daemon=True)
+        self.thread.start()
+
+    def add(self, done, p0, dst_rows):
+        self.q.put((done, p0, dst_rows))
+
+    def _run(self):
+        try:
+            with torch.cuda.device(self.device):
+                while True:
+                    item = self.q.get()
+                    if item is None:
+                        return
+                    if self.err is None:
+                        self._drain(*item)
+        except BaseException as e:  # noqa: BLE001 -- re-raised in close()
+            self.err = e
+            while self.q.get() is not None:
+                pass
+
+    def _drain(self, done, p0, dst_rows):
+        side, stage, piece = self.side, self.stage, self.piece
+        side.wait_event(done)
+        for a0 in range(0, len(dst_rows), piece):
+            a1 = min(a0 + piece, len(dst_rows))
+            slot = self.k % self.slots
+            self.k += 1
+            self.writer.wait_free(slot)
+            with torch.cuda.stream(side):
+                stage[slot][0][:a1 - a0].copy_(self.out16[0][p0 + a0:p0 + a1], non_blocking=True)
+                stage[slot][1][:a1 - a0].copy_(self.out16[1][p0 + a0:p0 + a1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            self.writer.submit(slot, 0, dst_rows[a0:a1], ev)
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
+        self.writer.close()
+        if self.err is not None:
+            raise self.err
+
+    def abort(self):
+        self.err = self.err or NnamError("aborted")
+        self.q.put(None)
+        self.thread.join()
+        try:
+            self.writer.close()
+        except Exception:  # noqa: BLE001 -- the original error is the one to report
+            pass
+
+
 def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, timedelay=0, device=0, head=None,
                        fix_timedelay_tail=False, nb=DEFAULT_BATCH, transfer=None, host_threads=None):
     """Recurrent hot path on ONE device for utterances [u0, u1) (predict_folds.py:28-68 semantics).
@@ -871,75 +949,53 @@ def forward_utterances(model, x, offsets, out, u0, u1, ft=None, ivectors=None, t
         phases = [np.arange(len(lens))] if (on_dev or stepwise) else _phase_split(lens)
         main = torch.cuda.current_stream()
         side = None
-        queued = []  # compact: (phase-done event, first packed output row, destination rows) per phase
+        drainer = None  # compact: helper thread that ships finished subsets while this thread launches the next one
         packed = 0
-        for idx in phases:
-            whole = len(idx) == len(lens)
-            p_starts, p_lens = (starts, lens) if whole else (starts[idx], lens[idx])
-            # compact format: the rows of this subset are packed one utterance after the other, so that they cross PCIe
-            # as ONE contiguous block (a subset's utterances lie all over the shard); the host scatters them back
-            o_starts = None
-            if compact:
-                o_starts = packed + np.concatenate([[0], np.cumsum(p_lens[:-1])]).astype(np.int64)
-            _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, p_starts, p_lens, out_dev, timedelay,
-                           fix_timedelay_tail, nb, device, stepwise, out16=out16, out_starts=o_starts)
-            if on_dev:
-                continue
-            out_host = None if compact else _as_host_tensor(out)
-            if len(phases) == 1 and not compact:
-                out_host[f_lo:f_hi].copy_(out_dev, non_blocking=True)
-                continue
-            if side is None:
-                side = plan.__dict__.get("_d2h_stream")
+        try:
+            for idx in phases:
+                whole = len(idx) == len(lens)
+                p_starts, p_lens = (starts, lens) if whole else (starts[idx], lens[idx])
+                # compact format: the rows of this subset are packed one utterance after the other, so that they cross PCIe
+                # as ONE contiguous block (a subset's utterances lie all over the shard); the host scatters them back
+                o_starts = None
+                if compact:
+                    o_starts = packed + np.concatenate([[0], np.cumsum(p_lens[:-1])]).astype(np.int64)
+                _forward_phase(models, plans, head, x_dev, iv_dev, add, mul, p_starts, p_lens, out_dev, timedelay,
+                               fix_timedelay_tail, nb, device, stepwise, out16=out16, out_starts=o_starts)
+                if on_dev:
+                    continue
+                out_host = None if compact else _as_host_tensor(out)
+                if len(phases) == 1 and not compact:
+                    out_host[f_lo:f_hi].copy_(out_dev, non_blocking=True)
+                    continue
                 if side is None:
-                    side = plan._d2h_stream = torch.cuda.Stream()
-            done = torch.cuda.Event()
-            done.record(main)
-            if compact:
-                n_p = int(p_lens.sum())
-                dst_rows = f_lo + np.repeat(p_starts - np.concatenate([[0], np.cumsum(p_lens[:-1])]), p_lens) + np.arange(n_p)
-                queued.append((done, packed, dst_rows.astype(np.int64)))
-                packed += n_p
-                continue
-            # rows of this subset, as maximal runs of neighbouring utterances, on the copy stream
-            brk = np.nonzero(np.diff(idx) != 1)[0] + 1
-            with torch.cuda.stream(side):
-                side.wait_event(done)
-                for run in np.split(idx, brk):
-                    r0, r1 = int(starts[run[0]]), int(starts[run[-1]] + lens[run[-1]])
-                    out_host[f_lo + r0:f_lo + r1].copy_(out_dev[r0:r1], non_blocking=True)
-        if queued:
-            # Every kernel of every phase is queued by now, so this thread may block on the ring: the packed rows cross
-            # PCIe in pieces of a few thousand rows through a small ring of pinned buffers and a helper thread widens
-            # each piece into its frame positions of ``out`` while the piece is still in the last-level cache
-            # (engine._ChunkWriter, as in the feed-forward path); phase k drains while the GPU computes phase k+1.
-            threads = host_threads or engine.default_host_threads()
-            piece = max(256, int(os.environ.get("NNAM_PIECE_ROWS", "4096")))
-            slots = max(2, int(os.environ.get("NNAM_PIECE_SLOTS", "4")))
-            key = ("f16", piece, n_out, slots)
-            cache = plan.__dict__.setdefault("_stage", {})
-            if key not in cache:
-                cache.clear()
-                cache[key] = [(torch.empty((piece, ld16), dtype=torch.float16, pin_memory=True),
-                               torch.empty((piece,), dtype=torch.float32, pin_memory=True)) for _ in range(slots)]
-            stage = cache[key]
-            out_np = out.numpy() if isinstance(out, torch.Tensor) else out
-            writer = engine._ChunkWriter(stage, True, out_np, None, n_out, threads)
-            k = 0
-            for done, p0, dst_rows in queued:
-                side.wait_event(done)
-                for a0 in range(0, len(dst_rows), piece):
-                    a1 = min(a0 + piece, len(dst_rows))
-                    slot = k % slots
-                    k += 1
-                    writer.wait_free(slot)
-                    with torch.cuda.stream(side):
-                        stage[slot][0][:a1 - a0].copy_(out16[0][p0 + a0:p0 + a1], non_blocking=True)
-                        stage[slot][1][:a1 - a0].copy_(out16[1][p0 + a0:p0 + a1], non_blocking=True)
-                        ev = torch.cuda.Event()
-                        ev.record(side)
-                    writer.submit(slot, 0, dst_rows[a0:a1], ev)
-            writer.close()
+                    side = plan.__dict__.get("_d2h_stream")
+                    if side is None:
+                        side = plan._d2h_stream = torch.cuda.Stream()
+                done = torch.cuda.Event()
+                done.record(main)
+                if compact:
+                    n_p = int(p_lens.sum())
+                    dst_rows = f_lo + np.repeat(p_starts - np.concatenate([[0], np.cumsum(p_lens[:-1])]), p_lens) + np.arange(n_p)
+                    if drainer is None:
+                        drainer = _PackedDrainer(plan, out, out16, n_out, side, device,
+                                                 host_threads or engine.default_host_threads())
+                    drainer.add(done, packed, dst_rows.astype(np.int64))
+                    packed += n_p
+                    continue
+                # rows of this subset, as maximal runs of neighbouring utterances, on the copy stream
+                brk = np.nonzero(np.diff(idx) != 1)[0] + 1
+                with torch.cuda.stream(side):
+                    side.wait_event(done)
+                    for run in np.split(idx, brk):
+                        r0, r1 = int(starts[run[0]]), int(starts[run[-1]] + lens[run[-1]])
+                        out_host[f_lo + r0:f_lo + r1].copy_(out_dev[r0:r1], non_blocking=True)
+            if drainer is not None:
+                drainer.close()
+                drainer = None
+        finally:
+            if drainer is not None:  # an error above: let the helper thread go
+                drainer.abort()
         main.synchronize()
         if side is not None:
             side.synchronize()
