@@ -21,7 +21,7 @@ from ._native import NnamError
 from .ops import (ELEM_BF16, ELEM_F16, OUT_BF16, OUT_BF16_SPLIT, OUT_F16, OUT_F32, SPLIT_A, SPLIT_AW, SPLIT_NONE,
                   SPLIT_W, round_up)
 
-DEFAULT_CHUNK = 65536
+DEFAULT_CHUNK = int(os.environ.get("NNAM_CHUNK_ROWS", "65536"))  # frames per feed-forward chunk (tuning aid)
 
 
 class Precision:
@@ -375,7 +375,7 @@ class RowSink:
 
 
 def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, device=0, head=None,
-                      chunk=DEFAULT_CHUNK, presliced=False, sink=None, transfer=None, host_threads=None):
+                      chunk=None, presliced=False, sink=None, transfer=None, host_threads=None):
     """Feed-forward hot loop on ONE device for frames [f0, f1) of the whole array ``x``.
 
     models    : one MLP or a list (ensemble -> logits combined in the head with head.weights)
@@ -407,6 +407,13 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         plans = [get_plan(m, device) for m in models]
         plan0 = plans[0]
         ws = plan0.ws
+        if chunk is None:
+            # A GEMM launch over 65,536 frames of a 1024-wide layer lasts ~100 us, of which the prologue, the pipeline fill
+            # and the last tile's drain are ~8 %: small single nets take chunks of twice the size (cfg1: 66.7 -> 71.9 M
+            # frames/s; no effect on cfg2, whose launches last 300-400 us).  Sinks keep the small staging buffers.
+            small = (len(models) == 1 and sink is None and models[0].network == "ff"
+                     and max((lin.n for lin in plan0.layers), default=0) <= 1024)
+            chunk = DEFAULT_CHUNK * 2 if (small and "NNAM_CHUNK_ROWS" not in os.environ) else DEFAULT_CHUNK
         main = torch.cuda.current_stream()
         side = plan0.__dict__.setdefault("_side_stream", torch.cuda.Stream(device=device))
         # Host inputs are uploaded chunk by chunk on their own stream (`up`): the GEMMs of chunk 0 start after ~1/18 of
