@@ -410,8 +410,9 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         if chunk is None:
             # A GEMM launch over 65,536 frames of a 1024-wide layer lasts ~100 us, of which the prologue, the pipeline fill
             # and the last tile's drain are ~8 %: small single nets take chunks of twice the size (cfg1: 66.7 -> 71.9 M
-            # frames/s; no effect on cfg2, whose launches last 300-400 us).  Sinks keep the small staging buffers.
-            small = (len(models) == 1 and sink is None and models[0].network == "ff"
+            # frames/s; no effect on cfg2, whose launches last 300-400 us) -- when the rows stay in HBM: with a host
+            # destination the pass is bound by PCIe, and the longer first / last chunk costs more than the launches save.
+            small = (len(models) == 1 and isinstance(out, torch.Tensor) and out.is_cuda and models[0].network == "ff"
                      and max((lin.n for lin in plan0.layers), default=0) <= 1024)
             chunk = DEFAULT_CHUNK * 2 if (small and "NNAM_CHUNK_ROWS" not in os.environ) else DEFAULT_CHUNK
         main = torch.cuda.current_stream()
