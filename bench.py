@@ -550,13 +550,15 @@ def run_ours(args):
         achieved = world * d2h / e2e_s / 1e9
         e2e = {"value": world * n / e2e_s, "unit": "frames/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "host_output_bytes_per_step": n * N_CLASSES * 4,
-               "transfer": ((f"mixed: {stats.compact_fraction():.2f} of the chunks compact (fp16 offsets from the row maximum "
+               "transfer": ((f"mixed: {stats.current:.2f} of the chunks compact (fp16 offsets from the row maximum "
                              f"+ the maximum, widened to the float32 (N, 1909) layout by host threads), the rest float32 "
                              f"rows; measured PCIe {stats.pcie / 1e9:.1f} GB/s, widening {stats.widen / 1e9:.1f} GB/s")
                             if (compact and stats is not None) else
                             ("compact: fp16 offsets from the row maximum + the maximum, widened to the float32 (N, 1909) "
                              "layout by host threads" if compact else "float32 rows")),
                "host_threads": engine.default_host_threads() if compact else 0,
+               "probed_compact_fractions": ({f"{k:.3f}": round(v) for k, v in stats.tried.items()}
+                                            if (compact and stats is not None and stats.tried) else None),
                "max_abs_host_vs_device_leg": host_vs_dev,
                "d2h": {"achieved_gbs": achieved, "ceiling_gbs": ceiling, "frac": achieved / ceiling,
                        "how": f"{world} rank(s) x cudaMemcpyAsync device -> pinned host, 4 x 1 GiB, best of 3; "

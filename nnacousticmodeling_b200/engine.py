@@ -11,6 +11,7 @@ HBM layout (per device)
 from __future__ import annotations
 
 import os
+import time
 import threading
 
 import numpy as np
@@ -407,6 +408,7 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         plans = [get_plan(m, device) for m in models]
         plan0 = plans[0]
         ws = plan0.ws
+        t_pass = time.perf_counter()
         if chunk is None:
             # A GEMM launch over 65,536 frames of a 1024-wide layer lasts ~100 us, of which the prologue, the pipeline fill
             # and the last tile's drain are ~8 %: small single nets take chunks of twice the size (cfg1: 66.7 -> 71.9 M
@@ -638,7 +640,7 @@ def ff_forward_frames(models, x, ft, splice, out, f0=0, f1=None, ivectors=None, 
         if writer is not None:
             writer.close()
         if stats is not None:
-            stats.update(copies, writer)
+            stats.update(copies, writer, f1 - f0, time.perf_counter() - t_pass)
     return out
 
 
@@ -654,12 +656,37 @@ class _TransferStats:
 
     def __init__(self, threads):
         self.pcie, self.widen, self.last_d2h_bytes = 55e9, 4.4e9 * threads, None
+        # With few threads (several ranks sharing the host) the two servers are not independent -- the widening threads
+        # and the DMA compete for the same DRAM, and float32 and compact chunks alternate on one copy stream -- so the
+        # model's x can lose against plain float32 rows (2 GPUs, 12 threads each: 11.1 M frames/s mixed against a
+        # 108 GB/s = 14 M frames/s copy ceiling).  There the first passes PROBE: the model's x, then 0 (float32 only), then
+        # x / 2; afterwards the fraction with the best measured frames/s is kept (and its measurement refreshed).
+        self.probe = threads < MIN_WIDEN_THREADS
+        self.tried = {}      # fraction -> frames/s of whole passes
+        self.current = None  # fraction of the pass in flight
 
-    def compact_fraction(self):
+    def model_fraction(self):
         x = 1.0 / (self.pcie / max(self.widen, 1e6) + 0.5)
         return 1.0 if x > 0.97 else max(x, 0.0)
 
-    def update(self, copies, writer):
+    def compact_fraction(self):
+        x = self.model_fraction()
+        if self.probe:
+            x = round(x, 2)
+            if len(self.tried) == 0:
+                self.first = x        # from the prior rates
+            elif 0.0 not in self.tried:
+                x = 0.0               # float32 rows only
+            elif len(self.tried) == 2:
+                # the model again, now from the rates measured under this box's contention -- or half the first guess
+                # if that says the same
+                x = x if abs(x - self.first) > 0.1 else round(self.first / 2, 2)
+            else:
+                x = max(self.tried, key=self.tried.get)
+        self.current = x
+        return x
+
+    def update(self, copies, writer, frames=0, seconds=0.0):
         ms = sum(a.elapsed_time(b) for a, b, _ in copies)
         nbytes = sum(n for _, _, n in copies)
         self.last_d2h_bytes = nbytes
@@ -667,6 +694,10 @@ class _TransferStats:
             self.pcie = 0.5 * self.pcie + 0.5 * nbytes / (ms * 1e-3)
         if writer is not None and writer.widen_s > 1e-3 and writer.widen_bytes > (64 << 20):
             self.widen = 0.5 * self.widen + 0.5 * writer.widen_bytes / writer.widen_s
+        if self.probe and self.current is not None and frames >= 100000 and seconds > 0:
+            rate = frames / seconds
+            old = self.tried.get(self.current)
+            self.tried[self.current] = rate if old is None else 0.5 * old + 0.5 * rate
 
 
 MIN_WIDEN_THREADS = 12  # host threads a process needs before the compact transfer beats the plain float32 copy

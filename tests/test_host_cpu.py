@@ -136,3 +136,22 @@ def test_npy_file_sink_writes_what_np_save_writes(tmp_path):
     bad = sink_cls(str(tmp_path / "c.npy"), 10, 39)
     with pytest.raises(nn.NnamError):
         bad.write(5, 10, y[:5])
+
+
+def test_transfer_stats_probe_then_keep_the_best_fraction():
+    """Few widening threads (several ranks on one host): the compact fraction is probed -- model, 0 (float32 rows only),
+    a third candidate -- and the best measured one is kept; with enough threads the model's value is used directly."""
+    from nnacousticmodeling_b200.engine import MIN_WIDEN_THREADS, _TransferStats
+    st = _TransferStats(4)
+    assert st.probe and 4 < MIN_WIDEN_THREADS
+    seen = []
+    for _ in range(8):
+        x = st.compact_fraction()
+        seen.append(x)
+        rate = {True: 11e6, False: 9e6}[x == 0.0] if x in (0.0, seen[0]) else 12e6
+        st.update([], None, 500000, 500000 / rate)
+    assert seen[1] == 0.0 and len(set(seen[:3])) == 3
+    assert all(x == seen[2] for x in seen[3:])          # the third candidate measured best and is kept
+    assert len(st.tried) == 3
+    st2 = _TransferStats(MIN_WIDEN_THREADS)
+    assert not st2.probe and st2.compact_fraction() == st2.model_fraction()
