@@ -656,12 +656,12 @@ class _TransferStats:
 
     def __init__(self, threads):
         self.pcie, self.widen, self.last_d2h_bytes = 55e9, 4.4e9 * threads, None
-        # With few threads (several ranks sharing the host) the two servers are not independent -- the widening threads
+        # With several ranks sharing the host (or few threads) the two servers are not independent -- the widening threads
         # and the DMA compete for the same DRAM, and float32 and compact chunks alternate on one copy stream -- so the
         # model's x can lose against plain float32 rows (2 GPUs, 12 threads each: 11.1 M frames/s mixed against a
         # 108 GB/s = 14 M frames/s copy ceiling).  There the first passes PROBE: the model's x, then 0 (float32 only), then
         # x / 2; afterwards the fraction with the best measured frames/s is kept (and its measurement refreshed).
-        self.probe = threads < MIN_WIDEN_THREADS
+        self.probe = threads < MIN_WIDEN_THREADS or int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1
         self.tried = {}      # fraction -> frames/s of whole passes
         self.current = None  # fraction of the pass in flight
 
