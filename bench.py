@@ -534,7 +534,8 @@ def run_ours(args):
     if args.no_e2e:  # profiling runs only (ncu): the printed line is then not a bench value
         e2e = {"value": None, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
     else:
-        for _ in range(3):  # also lets the transfer mix settle on this box's measured PCIe / widening rates
+        for _ in range(4):  # also lets the transfer mix settle (engine._TransferStats probes during these passes)
+            barrier()       # ranks share the host: measure the candidates with every rank running
             b.step_e2e()
         e2e_s = max_over_ranks(timed_host(torch, b.step_e2e, steps, barrier))
         from nnacousticmodeling_b200 import engine

@@ -664,6 +664,7 @@ class _TransferStats:
         self.probe = threads < MIN_WIDEN_THREADS or int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1
         self.tried = {}      # fraction -> frames/s of whole passes
         self.current = None  # fraction of the pass in flight
+        self.cold = True     # the first candidate has only been measured on the first (cold) pass
 
     def model_fraction(self):
         x = 1.0 / (self.pcie / max(self.widen, 1e6) + 0.5)
@@ -681,6 +682,8 @@ class _TransferStats:
                 # the model again, now from the rates measured under this box's contention -- or half the first guess
                 # if that says the same
                 x = x if abs(x - self.first) > 0.1 else round(self.first / 2, 2)
+            elif self.cold:
+                x = self.first        # its first measurement included the one-time allocations of a first pass
             else:
                 x = max(self.tried, key=self.tried.get)
         self.current = x
@@ -697,6 +700,8 @@ class _TransferStats:
         if self.probe and self.current is not None and frames >= 100000 and seconds > 0:
             rate = frames / seconds
             old = self.tried.get(self.current)
+            if self.cold and old is not None and self.current == self.first:
+                old, self.cold = None, False
             self.tried[self.current] = rate if old is None else 0.5 * old + 0.5 * rate
 
 

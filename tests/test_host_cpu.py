@@ -151,7 +151,8 @@ def test_transfer_stats_probe_then_keep_the_best_fraction():
         rate = {True: 11e6, False: 9e6}[x == 0.0] if x in (0.0, seen[0]) else 12e6
         st.update([], None, 500000, 500000 / rate)
     assert seen[1] == 0.0 and len(set(seen[:3])) == 3
-    assert all(x == seen[2] for x in seen[3:])          # the third candidate measured best and is kept
+    assert seen[3] == seen[0]                           # the first candidate again: its first pass was a cold one
+    assert all(x == seen[2] for x in seen[4:])          # the third candidate measured best and is kept
     assert len(st.tried) == 3
     st2 = _TransferStats(MIN_WIDEN_THREADS)
     assert not st2.probe and st2.compact_fraction() == st2.model_fraction()
