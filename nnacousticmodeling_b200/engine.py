@@ -656,12 +656,14 @@ class _TransferStats:
 
     def __init__(self, threads):
         self.pcie, self.widen, self.last_d2h_bytes = 55e9, 4.4e9 * threads, None
-        # With several ranks sharing the host (or few threads) the two servers are not independent -- the widening threads
-        # and the DMA compete for the same DRAM, and float32 and compact chunks alternate on one copy stream -- so the
-        # model's x can lose against plain float32 rows (2 GPUs, 12 threads each: 11.1 M frames/s mixed against a
-        # 108 GB/s = 14 M frames/s copy ceiling).  There the first passes PROBE: the model's x, then 0 (float32 only), then
-        # x / 2; afterwards the fraction with the best measured frames/s is kept (and its measurement refreshed).
-        self.probe = threads < MIN_WIDEN_THREADS or int(os.environ.get("LOCAL_WORLD_SIZE", "1")) > 1
+        # The two servers are not independent -- the widening threads and the DMA compete for the same DRAM (2 ranks x 12
+        # threads pushed a rank's PCIe rate from 54 to 20 GB/s), float32 and compact chunks alternate on one copy stream,
+        # and whether the piece ring stays in the last-level cache depends on the box -- so the model's x is only the
+        # first guess.  The first passes PROBE: the model's x from the prior rates, 0 (float32 rows only), the model's x
+        # from the rates measured meanwhile (or half the first guess if that says the same), the first one again (its
+        # first pass was a cold one); afterwards the fraction with the best measured frames/s is kept and its measurement
+        # refreshed.  NNAM_TRANSFER_PROBE=0 keeps the model's value.
+        self.probe = os.environ.get("NNAM_TRANSFER_PROBE", "1") != "0"
         self.tried = {}      # fraction -> frames/s of whole passes
         self.current = None  # fraction of the pass in flight
         self.cold = True     # the first candidate has only been measured on the first (cold) pass

@@ -138,12 +138,13 @@ def test_npy_file_sink_writes_what_np_save_writes(tmp_path):
         bad.write(5, 10, y[:5])
 
 
-def test_transfer_stats_probe_then_keep_the_best_fraction():
-    """Few widening threads (several ranks on one host): the compact fraction is probed -- model, 0 (float32 rows only),
-    a third candidate -- and the best measured one is kept; with enough threads the model's value is used directly."""
-    from nnacousticmodeling_b200.engine import MIN_WIDEN_THREADS, _TransferStats
+def test_transfer_stats_probe_then_keep_the_best_fraction(monkeypatch):
+    """The compact fraction of the transfer mix is probed -- model, 0 (float32 rows only), a third candidate, the first
+    again -- and the best measured one is kept; NNAM_TRANSFER_PROBE=0 uses the model's value directly."""
+    from nnacousticmodeling_b200.engine import _TransferStats
+    monkeypatch.delenv("NNAM_TRANSFER_PROBE", raising=False)
     st = _TransferStats(4)
-    assert st.probe and 4 < MIN_WIDEN_THREADS
+    assert st.probe
     seen = []
     for _ in range(8):
         x = st.compact_fraction()
@@ -154,5 +155,6 @@ def test_transfer_stats_probe_then_keep_the_best_fraction():
     assert seen[3] == seen[0]                           # the first candidate again: its first pass was a cold one
     assert all(x == seen[2] for x in seen[4:])          # the third candidate measured best and is kept
     assert len(st.tried) == 3
-    st2 = _TransferStats(MIN_WIDEN_THREADS)
+    monkeypatch.setenv("NNAM_TRANSFER_PROBE", "0")
+    st2 = _TransferStats(16)
     assert not st2.probe and st2.compact_fraction() == st2.model_fraction()
