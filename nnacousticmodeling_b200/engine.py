@@ -683,6 +683,7 @@ class _TransferStats:
             elif len(self.tried) == 2:
                 # the model again, now from the rates measured under this box's contention -- or half the first guess
                 # if that says the same
+                x = 1.0 if x >= 0.85 else x  # nearly everything compact: take all of it (no alternation of formats)
                 x = x if abs(x - self.first) > 0.1 else round(self.first / 2, 2)
             elif self.cold:
                 x = self.first        # its first measurement included the one-time allocations of a first pass
