@@ -77,6 +77,14 @@ __device__ __forceinline__ void st_async_f32x2(uint32_t cluster_addr, float a, f
                "f"(a), "f"(b), "r"(cluster_bar)
                : "memory");
 }
+// the row addresses come out of shared memory as integers: say that they are global (a plain C++ store through the
+// reinterpreted pointer compiles to the generic ST, which resolves the address space per access)
+__device__ __forceinline__ void st_global_f32(unsigned long long addr, float v) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_global_v4(unsigned long long addr, const uint4& v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void named_bar_sync_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // running (max, sum exp) over one 32-column chunk held as raw accumulator bits + the staged bias slice
@@ -371,7 +379,7 @@ __global__ void __maxnreg__(168)
               const uint4 val = *reinterpret_cast<const uint4*>(box + r_ * 128 + ((ch ^ (r_ & 7)) << 4));
               uint16_t* d = reinterpret_cast<uint16_t*>(base) + cw;
               if (left >= 8) {
-                *reinterpret_cast<uint4*>(d) = val;
+                st_global_v4(base + static_cast<unsigned long long>(cw) * 2ull, val);
               } else {
                 const uint32_t w[4] = {val.x, val.y, val.z, val.w};
                 for (int e = 0; e < left; ++e) d[e] = static_cast<uint16_t>((w[e >> 1] >> ((e & 1) * 16)) & 0xffffu);
@@ -387,7 +395,7 @@ __global__ void __maxnreg__(168)
             if ((vmask >> rr) & 1u) {  // warp-uniform
               const unsigned long long base = rowptr[rr];  // broadcast
               const float val = *reinterpret_cast<const float*>(box + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + ((lane & 3) << 2));
-              if (col_ok) *reinterpret_cast<float*>(base + lane_off) = val;
+              if (col_ok) st_global_f32(base + lane_off, val);
             }
           }
         }
