@@ -616,7 +616,10 @@ def run_ours(args):
         torch.cuda.empty_cache()
         line["extra"] = []
         for wname in extras:
-            line["extra"].append(extra_record(args, torch, wname, local, steps, warmup, barrier, peaks))
+            try:  # an extra record must never cost the headline line
+                line["extra"].append(extra_record(args, torch, wname, local, steps, warmup, barrier, peaks))
+            except Exception as e:  # noqa: BLE001
+                line["extra"].append({"workload": wname, "error": repr(e)})
     elif rank == 0:
         line["cpu_baseline"] = None
     if rank == 0:
