@@ -133,3 +133,62 @@ def test_phase_split_covers_every_utterance_once(monkeypatch):
     assert len(_phase_split(np.full(400, 100))) == 1   # few frames
     monkeypatch.setenv("NNAM_RNN_PHASES", "1")
     assert len(_phase_split(lens)) == 1
+
+
+def test_cost_model_gives_long_groups_several_batches(monkeypatch):
+    """pick_schedule on a test-shaped set with the kernels' measured step costs (faked here: the C ABI's nnam_rnn_plan
+    needs a device): the mixed schedule wins, its long part holds MORE batches than groups (a group works through its
+    batches one after the other while the group with the longest batch walks that one), and the packed row space
+    still covers every (utterance, step) exactly once."""
+    import types
+    from nnacousticmodeling_b200 import recurrent_engine as R
+    from nnacousticmodeling_b200 import synth
+    plans = {16: (0, 9, 9000, 4), 32: (0, 7, 4300, 1), 64: (0, 9, 7900, 1), 128: (0, 9, 12500, 2)}
+    monkeypatch.setattr(R.ops, "rnn_plan", lambda cell, hidden, nb, nsplit: plans[nb])
+    monkeypatch.setattr(R.ops, "rnn_solo_step_cycles", lambda cell, hidden, nb, nsplit: 10100)
+    monkeypatch.delenv("NNAM_RNN_MIXED", raising=False)
+    monkeypatch.delenv("NNAM_RNN_MIXED_GROUPS", raising=False)
+    monkeypatch.delenv("NNAM_RNN_MIXED_BATCHES", raising=False)
+    plan = types.SimpleNamespace(cell=R.CELL_LSTM, hidden=512, n_dirs=1, split=False)
+    steps = synth.synth_lengths(np.random.default_rng(1234), 1344) + 5
+    sched, tag = R.pick_schedule(plan, steps, torch.device("cpu"))
+    assert isinstance(sched, R.MixedSchedule) and tag[0] == "mixed"
+    _, k_long, g_long, nb_long = tag
+    assert nb_long == 32 and k_long % 32 == 0 and k_long // 32 > g_long >= 2   # several batches per long group
+    (sa, _), (sb, nb_b) = sched.parts
+    assert nb_b == 128 and sa.n_groups == g_long and sa.n_groups + sb.n_groups <= 9
+    assert sched.n_rows == int(steps.sum())
+    utt = sched.order[sched.row_sorted_utt]
+    assert len(set(zip(utt.tolist(), sched.row_step.tolist()))) == sched.n_rows
+    # the long part's critical lane is not longer than the bulk part's modelled time (that is what the search balances)
+    assert sa.max_group_steps * 4300 <= 1.15 * sb.max_group_steps * 12500
+    # forcing one batch per group reproduces the previous behaviour
+    monkeypatch.setenv("NNAM_RNN_MIXED_GROUPS", "3")
+    monkeypatch.setenv("NNAM_RNN_MIXED_BATCHES", "3")
+    plan2 = types.SimpleNamespace(cell=R.CELL_LSTM, hidden=512, n_dirs=1, split=False)
+    _, tag2 = R.pick_schedule(plan2, steps, torch.device("cpu"))
+    assert tag2 == ("mixed", 96, 3, 32)
+
+
+def test_fused_output_layer_gate(monkeypatch):
+    """engine.fused_head_ok: one net, plain head, 512..2048 classes, fan-in <= 1024; environment overrides."""
+    import types
+    from nnacousticmodeling_b200 import engine
+    monkeypatch.delenv("NNAM_FUSED_HEAD", raising=False)
+    net = types.SimpleNamespace(n_out=1909, network="ff")
+    plain = engine.HeadSpec()
+    assert engine.fused_head_ok([net], plain, 512) and engine.fused_head_ok([net], plain, 1024)
+    assert not engine.fused_head_ok([net], plain, 2048)
+    assert not engine.fused_head_ok([net, net], plain, 512)
+    assert not engine.fused_head_ok([net], engine.HeadSpec(rpl={"W": 1}), 512)
+    assert not engine.fused_head_ok([net], engine.HeadSpec(final_normalize=False), 512)
+    assert not engine.fused_head_ok([net], engine.HeadSpec(weights=[0.5]), 512)
+    assert engine.fused_head_ok([net], engine.HeadSpec(prior=np.zeros(1909, np.float32), prior_scale=0.7), 512)
+    assert not engine.fused_head_ok([types.SimpleNamespace(n_out=39, network="ff")], plain, 128)
+    assert not engine.fused_head_ok([types.SimpleNamespace(n_out=1909, network="tdnn")], plain, 512)
+    assert not engine.fused_head_ok([types.SimpleNamespace(n_out=4000, network="ff")], plain, 512)
+    monkeypatch.setenv("NNAM_FUSED_HEAD", "0")
+    assert not engine.fused_head_ok([net], plain, 512)
+    monkeypatch.setenv("NNAM_FUSED_HEAD", "force")
+    assert engine.fused_head_ok([net], plain, 2048)
+    assert engine.fused_head_ok([types.SimpleNamespace(n_out=39, network="ff")], plain, 128)
