@@ -158,3 +158,42 @@ def test_transfer_stats_probe_then_keep_the_best_fraction(monkeypatch):
     monkeypatch.setenv("NNAM_TRANSFER_PROBE", "0")
     st2 = _TransferStats(16)
     assert not st2.probe and st2.compact_fraction() == st2.model_fraction()
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/nnam_b200.h against the ctypes table of _native.py: same number of arguments, and the
+    same KIND per argument (pointer / integer width / float), so a changed C signature cannot silently drift from the
+    binding (ctypes would pass garbage, not fail)."""
+    from ctypes import c_char_p, c_float, c_int, c_longlong, c_void_p
+    hdr = open(os.path.join(ROOT, "include", "nnam_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b([A-Za-z_][\w \*]*?)\b(nnam_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr)
+    assert len(protos) == len(_native._SIGNATURES)
+
+    def kind_of_c(decl):
+        decl = decl.strip()
+        if decl in ("void", ""):
+            return None
+        if "*" in decl:
+            return "ptr"
+        t = re.sub(r"\b(const|unsigned|signed)\b", "", decl).split()
+        base = " ".join(t[:-1]) if len(t) > 1 else t[0]
+        return {"int": "i32", "long long": "i64", "float": "f32"}[base]
+
+    def kind_of_ctypes(t):
+        if t in (c_int,):
+            return "i32"
+        if t is c_longlong:
+            return "i64"
+        if t is c_float:
+            return "f32"
+        if t in (c_void_p, c_char_p) or hasattr(t, "contents") or getattr(t, "_type_", None) is not None:
+            return "ptr"
+        raise AssertionError(f"unexpected ctypes type {t}")
+
+    for ret, name, args in protos:
+        res, argtypes = _native._SIGNATURES[name]
+        c_kinds = [k for k in (kind_of_c(a) for a in args.split(",")) if k is not None]
+        py_kinds = [kind_of_ctypes(t) for t in argtypes]
+        assert c_kinds == py_kinds, f"{name}: header {c_kinds} vs ctypes {py_kinds}"
+        assert ("*" in ret) == (res in (c_char_p, c_void_p)), name
